@@ -1,0 +1,189 @@
+/*
+ * sleekit_b200 -- C ABI of the B200 (sm_100a) implementation of sleekit's
+ * layer-wise quantization hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - matrices are dense row-major; W is [r, n] (r output rows, n input
+ *     features), H is [n, n], X is [S, n];
+ *   - every entry point only ENQUEUES work on `stream` (a cudaStream_t passed
+ *     as void*) and returns 0, or a negative slk_status on a usage / launch
+ *     error; slk_last_error() gives the thread-local message;
+ *   - nothing here allocates or frees caller-visible memory: scratch is
+ *     sized by the matching *_ws_bytes() query and passed in;
+ *   - no C++ types, no exceptions, no torch types cross this boundary.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to the reference repo, Coloquinte/sleekit).
+ */
+#ifndef SLEEKIT_B200_H
+#define SLEEKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLK_ABI_VERSION 1
+
+typedef enum slk_status {
+  SLK_OK = 0,
+  SLK_ERR_ARG = -1,    /* bad shape / null pointer / unsupported option */
+  SLK_ERR_CUDA = -2,   /* a CUDA runtime call failed */
+  SLK_ERR_WS = -3      /* workspace too small */
+} slk_status;
+
+/* Rounding direction (sleekit/codebook.py:43-95, 155-188). */
+typedef enum slk_round_mode { SLK_NEAREST = 0, SLK_UP = 1, SLK_DOWN = 2 } slk_round_mode;
+
+/* Codebook passed by host pointer; `values` / `limits` are device pointers.
+ * kind 0: UniformCodebook(size, lo, hi)                       codebook.py:4-41
+ * kind 1: Codebook(values, limits)                            codebook.py:98-113 */
+typedef struct slk_codebook {
+  int32_t kind;
+  int32_t size;
+  double lo;            /* codebook.min(); uniform: also the zero point            */
+  double hi;            /* codebook.max()                                           */
+  double step;          /* uniform: (hi-lo)/(size-1) as a Python float, else 0      */
+  const float* values;  /* table: [size] ascending, fp32                            */
+  const float* limits;  /* table: [size-1] bin limits, fp32                         */
+} slk_codebook;
+
+int slk_abi_version(void);
+const char* slk_last_error(void);
+/* Fills sm_count / compute capability of the current device. */
+int slk_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---- K4: codebook rounding ------------------------------------------------
+ * UniformCodebook.quantize_{index,value,up,down}   codebook.py:43-95
+ * Codebook.quantize_{index,value,up,down}          codebook.py:155-188
+ * out_val / out_idx may each be NULL.  out_idx element width is 1 byte for
+ * size <= 256, 2 bytes for size <= 65536, else 4 (codebook.py:50-54).
+ * Table codebooks always produce fp32 values (as the reference does). */
+int slk_round_f32(const float* x, int64_t count, const slk_codebook* cb_host, int mode,
+                  float* out_val, void* out_idx, void* stream);
+int slk_round_f64(const double* x, int64_t count, const slk_codebook* cb_host, int mode,
+                  void* out_val, void* out_idx, void* stream);
+
+/* ---- scaling primitives ---------------------------------------------------
+ * x viewed as [outer, len, inner]; s has `len` entries.
+ * mode 0: out = x / s            apply_scaling              scaling.py:21-25
+ * mode 1: out = x / (1 / s)      the de-scaling of quantize_with_scaling, scaling.py:80 */
+int slk_scale_axis_f32(const float* x, int64_t outer, int64_t len, int64_t inner, const float* s,
+                       int mode, float* out, void* stream);
+int slk_scale_axis_f64(const double* x, int64_t outer, int64_t len, int64_t inner, const double* s,
+                       int mode, double* out, void* stream);
+/* compute_non_saturating_scaling on a [r, n] view, axis 0   scaling.py:44-55 */
+int slk_row_noclip_scale_f32(const float* w, int64_t r, int64_t n, double cb_min, double cb_max,
+                             float* out, void* stream);
+int slk_row_noclip_scale_f64(const double* w, int64_t r, int64_t n, double cb_min, double cb_max,
+                             double* out, void* stream);
+/* compute_norm_scaling on a [r, n] view, axis 0             scaling.py:35-41 */
+int slk_row_rms_scale_f32(const float* w, int64_t r, int64_t n, float* out, void* stream);
+int slk_row_rms_scale_f64(const double* w, int64_t r, int64_t n, double* out, void* stream);
+
+/* ---- K5: fused scale-grid search (MSE / diagonal-H) -------------------------
+ * compute_min_mse_scaling with H None or 1-D                scaling.py:98-134
+ * factors: [G] fp32 grid (np.linspace(..., dtype=float32), made by the caller)
+ * hdiag: NULL, or [n] of fp32 (h_dtype 1) / fp64 (h_dtype 2)
+ * out_scale [r] = init * best factor; out_err [r] (may be NULL) best error;
+ * out_init [r] (may be NULL) the non-saturating scale. */
+int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb_host,
+                         const float* factors, int32_t G, const void* hdiag, int32_t h_dtype,
+                         float* out_scale, float* out_err, float* out_init, void* stream);
+
+/* ---- K6: H-weighted error ---------------------------------------------------
+ * channelwise_error  ((W-Q) @ H * (W-Q)).sum(-1)            obq.py:89-95
+ * _compute_mse with a 2-D H                                 scaling.py:91-95
+ * q may be NULL, in which case `w` already holds the residual. */
+size_t slk_hweighted_error_ws_bytes(int64_t r, int64_t n, int32_t elem_bytes);
+int slk_hweighted_error_f32(const float* w, const float* q, const float* h, int64_t r, int64_t n,
+                            void* ws, size_t ws_bytes, float* out, void* stream);
+int slk_hweighted_error_f64(const double* w, const double* q, const double* h, int64_t r, int64_t n,
+                            void* ws, size_t ws_bytes, double* out, void* stream);
+/* mean of a vector (quantization_error's .mean())           obq.py:98-103 */
+int slk_mean_f32(const float* v, int64_t count, float* out, void* stream);
+int slk_mean_f64(const double* v, int64_t count, double* out, void* stream);
+
+/* compute_gain                                               obq.py:220-231 */
+int slk_gain_f32(const float* w, const float* q, const float* h, const float* cand, int64_t r,
+                 int64_t n, float* out, void* stream);
+int slk_gain_f64(const double* w, const double* q, const double* h, const double* cand, int64_t r,
+                 int64_t n, double* out, void* stream);
+
+/* full-H scale-grid search: compute_min_mse_scaling with a 2-D H  scaling.py:98-134
+ * h_dtype 1: H fp32, 2: H fp64 (errors then accumulate in fp64). */
+size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t h_dtype);
+int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb_host,
+                               const float* factors, int32_t G, const void* h, int32_t h_dtype,
+                               void* ws, size_t ws_bytes, float* out_scale, float* out_err,
+                               void* stream);
+
+/* ---- K1: calibration statistics ---------------------------------------------
+ * Sleekit.add_batch                                         statistics.py:76-87
+ * x: [S, n] with row stride ldx (samples are rows).  Updates, in place,
+ *   mean = mean*keep + colsum(x)/new_count ;  hess = hess*keep + x^T x/new_count
+ * keep = old_count/(old_count+S), new_count = old_count+S (both given by caller). */
+int slk_hessian_accum_f32(const float* x, int64_t S, int64_t n, int64_t ldx, float* hess,
+                          float* mean, double keep, double new_count, void* stream);
+/* remove_input_bias  H - outer(m, m)                        obq.py:14-25 */
+int slk_remove_input_bias_f32(const float* h, const float* m, int64_t n, float* out, void* stream);
+int slk_remove_input_bias_f64(const double* h, const double* m, int64_t n, double* out, void* stream);
+
+/* ---- ordering -----------------------------------------------------------------
+ * damp * mean(diag H) as an fp32 scalar                      obq.py:198
+ * add_mode 0: writes dampval only.                                              */
+int slk_damp_value_f32(const float* h, int64_t n, double damp, float* out_dampval, void* stream);
+/* column sums over rows of |q(w)-w| (mode 0) or (q(w)-w)^2 (mode 1), fp32,
+ * rows added in order                                        obq.py:60-69 */
+int slk_col_resid_sums_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb_host,
+                           int mode, float* out, void* stream);
+/* keys[j] = -(double(H[j,j]) + dampval) [* colsum[j]]        obq.py:64,69,81 */
+int slk_order_keys(const float* h, int64_t n, const float* dampval, const float* colsum,
+                   double* keys, void* stream);
+/* stable ascending argsort of fp64 keys -> int64 order        obq.py:64,69,81 */
+int slk_argsort_f64(const double* keys, int64_t n, int64_t* order, void* stream);
+/* dst[:, j] = src[:, idx[j]] (gather) or dst[:, idx[j]] = src[:, j] (scatter)  obq.py:202,212-213 */
+int slk_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* idx, int scatter,
+                         float* dst, void* stream);
+
+/* ---- K2: damp + permute + fp64 factor of the inverse --------------------------
+ * H_opt = H + dampval*I; H_opt[order][:, order]; compute_hessian_chol
+ *                                                             obq.py:198-205, 38-55
+ * order may be NULL (identity), dampval may be NULL (0).  u64 / u32 may each be
+ * NULL.  info (int32, device) receives 0, or 1 + the first pivot (in factor
+ * order) that was not positive -> the Python layer raises LinAlgError. */
+size_t slk_hinv_ws_bytes(int64_t n);
+int slk_hinv_from_f32(const float* h, int64_t n, const int64_t* order, const float* dampval,
+                      void* ws, size_t ws_bytes, double* u64, float* u32, int32_t* info,
+                      void* stream);
+int slk_hinv_from_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, double* u64,
+                      float* u32, int32_t* info, void* stream);
+
+/* ---- K3: GPTQ / OBQ sweep ------------------------------------------------------
+ * _quantize_opt_block / _quantize_opt_core                    obq.py:106-137
+ * q: [r, n] in: scaled, column-permuted weights; out: quantized values.
+ * e: [r, n] out: scaled residuals.  u64: fp64 factor (leaf arithmetic),
+ * u32: its fp32 rounding (trailing updates).  leaf <= 32. */
+int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, const double* u64,
+                       const float* u32, const slk_codebook* cb_host, int32_t leaf,
+                       int32_t fanout, void* stream);
+
+/* ---- K7: best-first local search ------------------------------------------------
+ * quantize_local_search / LocalSearchQuantizer                obq.py:234-358
+ * q: [r, n] in/out quantized values (must lie on the codebook). */
+size_t slk_local_search_ws_bytes(int64_t r, int64_t n);
+int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n,
+                         const slk_codebook* cb_host, int32_t moves, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* bias correction  bias += ((W - Wq) * mean).sum(1)          statistics.py:187-190 */
+int slk_bias_delta_f32(const float* w, const float* wq, const float* mean, int64_t r, int64_t n,
+                       float* delta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLEEKIT_B200_H */

@@ -1,0 +1,206 @@
+// Shared device/host helpers for the sleekit_b200 kernels (sm_100a).
+// Everything numeric here follows the reference's op-by-op rounding
+// (sleekit/codebook.py:43-95, scaling.py:58-81): separately rounded IEEE ops,
+// never a fused multiply-add and never a reciprocal-multiply in place of a divide.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sleekit_b200.h"
+
+namespace slk {
+
+void set_error(const char* fmt, ...);
+
+#define SLK_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::slk::set_error(__VA_ARGS__);  \
+      return SLK_ERR_ARG;             \
+    }                                 \
+  } while (0)
+
+#define SLK_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      ::slk::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                       __FILE__, __LINE__);                                        \
+      return SLK_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+#define SLK_LAUNCH_CHECK()                                                         \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      ::slk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),\
+                       __FILE__, __LINE__);                                        \
+      return SLK_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+int sm_count();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// IEEE op wrappers, one rounding each, immune to -fmad contraction.
+// ---------------------------------------------------------------------------
+template <typename T> struct Ieee;
+template <> struct Ieee<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float rint(float a) { return rintf(a); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+template <> struct Ieee<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double rint(double a) { return ::rint(a); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+
+// ---------------------------------------------------------------------------
+// Device view of a codebook.  Uniform grids carry zero/step already rounded to
+// the compute dtype (NEP 50: the Python float meets an fp32 array as fp32).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DevGrid {
+  int kind;   // 0 uniform, 1 table
+  int size;
+  T zero;
+  T step;
+  const float* values;
+  const float* limits;
+};
+
+template <typename T>
+static inline DevGrid<T> make_grid(const slk_codebook* cb) {
+  DevGrid<T> g;
+  g.kind = cb->kind;
+  g.size = cb->size;
+  g.zero = (T)cb->lo;
+  g.step = (T)cb->step;
+  g.values = cb->values;
+  g.limits = cb->limits;
+  return g;
+}
+
+static inline int check_codebook(const slk_codebook* cb) {
+  SLK_REQUIRE(cb != nullptr, "codebook is NULL");
+  SLK_REQUIRE(cb->kind == 0 || cb->kind == 1, "codebook kind %d not in {0,1}", cb->kind);
+  SLK_REQUIRE(cb->size >= 1, "codebook size %d", cb->size);
+  if (cb->kind == 0) {
+    SLK_REQUIRE(cb->size >= 2 && cb->step > 0, "uniform codebook needs size >= 2 and step > 0");
+  } else {
+    SLK_REQUIRE(cb->values != nullptr && (cb->size == 1 || cb->limits != nullptr),
+                "table codebook needs values and limits");
+  }
+  return SLK_OK;
+}
+
+// number of limits <= x  == np.digitize(x, limits) for ascending limits
+template <typename T>
+__device__ __forceinline__ int table_bin(const float* __restrict__ limits, int nlim, T x) {
+  if (nlim <= 32) {
+    int k = 0;
+    for (int i = 0; i < nlim; ++i) k += ((T)__ldg(limits + i) <= x) ? 1 : 0;
+    return k;
+  }
+  int lo = 0, hi = nlim;  // first index with limit > x
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((T)__ldg(limits + mid) <= x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Slot (integer-valued T) a uniform grid assigns to x; shift is 0, +1 or -1.
+template <typename T>
+__device__ __forceinline__ T uniform_slot(const DevGrid<T>& g, T x, int mode) {
+  typedef Ieee<T> F;
+  T t = F::div(F::sub(x, g.zero), g.step);
+  T lo = (T)0, hi = (T)(g.size - 1);
+  if (mode == SLK_UP) { t = F::add(t, (T)1); lo = (T)1; }
+  else if (mode == SLK_DOWN) { t = F::sub(t, (T)1); hi = (T)(g.size - 2); }
+  T k = F::rint(t);
+  k = k < lo ? lo : k;   // np.clip: NaN propagates, like the comparisons here
+  k = k > hi ? hi : k;
+  return k;
+}
+
+template <typename T>
+__device__ __forceinline__ T uniform_value_of_slot(const DevGrid<T>& g, T k) {
+  typedef Ieee<T> F;
+  return F::add(F::mul(k, g.step), g.zero);
+}
+
+// index a table grid assigns in the given mode (value = values[idx])
+template <typename T>
+__device__ __forceinline__ int table_index(const DevGrid<T>& g, T x, int mode) {
+  int k = table_bin<T>(g.limits, g.size - 1, x);
+  if (mode == SLK_UP) k = k + 1 < g.size ? k + 1 : g.size - 1;
+  else if (mode == SLK_DOWN) k = k > 0 ? k - 1 : 0;
+  return k;
+}
+
+// Nearest value, generic over the two kinds (fp32 hot path).
+__device__ __forceinline__ float grid_value(const DevGrid<float>& g, float x) {
+  if (g.kind == 0) return uniform_value_of_slot<float>(g, uniform_slot<float>(g, x, SLK_NEAREST));
+  return __ldg(g.values + table_index<float>(g, x, SLK_NEAREST));
+}
+
+__device__ __forceinline__ int grid_index(const DevGrid<float>& g, float x) {
+  if (g.kind == 0) return (int)uniform_slot<float>(g, x, SLK_NEAREST);
+  return table_index<float>(g, x, SLK_NEAREST);
+}
+
+__device__ __forceinline__ float grid_value_of_index(const DevGrid<float>& g, int k) {
+  if (g.kind == 0) return uniform_value_of_slot<float>(g, (float)k);
+  return __ldg(g.values + k);
+}
+
+// ---------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(0xffffffffu, v, o); v = u > v ? u : v; }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }
+  return v;
+}
+
+// Block-wide sum; `scratch` must hold >= 32 T.  Result valid in every thread.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  T t = lane < nw ? scratch[lane] : (T)0;
+  return warp_sum(t);
+}
+
+}  // namespace slk

@@ -1,0 +1,232 @@
+// K1 / K6 / K7-init: the dense contractions of the hot path, on the shared GEMM core.
+//   slk_hessian_accum_f32      Sleekit.add_batch                 statistics.py:76-87
+//   slk_hweighted_error_*      channelwise_error / _compute_mse  obq.py:89-95, scaling.py:91-95
+//   slk_gain_*                 compute_gain                      obq.py:220-231
+//   slk_scale_search_fullh_f32 compute_min_mse_scaling, 2-D H    scaling.py:98-134
+#include "gemm.cuh"
+
+namespace slk {
+
+// out[m] = sum over column tiles of part[m, t], fixed order -> deterministic
+template <typename T>
+__global__ void __launch_bounds__(256) rowdot_reduce_kernel(const T* __restrict__ part, int64_t rows, int64_t tiles,
+                                                            T* __restrict__ out) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  T s = (T)0;
+  for (int64_t t = 0; t < tiles; ++t) s += part[m * tiles + t];
+  out[m] = s;
+}
+
+template <typename T>
+static int hweighted_error_impl(const T* w, const T* q, const T* h, int64_t r, int64_t n, void* ws,
+                                size_t ws_bytes, T* out, cudaStream_t st) {
+  SLK_REQUIRE(r >= 0 && n >= 1, "bad shape");
+  if (r == 0) return SLK_OK;
+  SLK_REQUIRE(w && h && out, "NULL pointer");
+  const int64_t tiles = rowdot_tiles<T>(n);
+  SLK_REQUIRE(ws && ws_bytes >= (size_t)(r * tiles) * sizeof(T), "workspace too small");
+  GemmParams<T> p = gemm_params<T>(w, n, h, n, (T*)ws, 0, r, n, n);
+  p.A2 = q;
+  int rc = gemm_launch<T, false, false, EPI_ROWDOT>(p, 1, st);
+  if (rc) return rc;
+  rowdot_reduce_kernel<T><<<(int)ceil_div(r, 256), 256, 0, st>>>((const T*)ws, r, tiles, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+template <typename T>
+static int gain_impl(const T* w, const T* q, const T* h, const T* cand, int64_t r, int64_t n, T* out,
+                     cudaStream_t st) {
+  SLK_REQUIRE(w && q && h && cand && out && r >= 1 && n >= 1, "bad arguments");
+  // acc = (q - w) @ H ; the epilogue applies obq.py:231 with diag(H) read in place (stride n+1)
+  GemmParams<T> p = gemm_params<T>(q, n, h, n, out, n, r, n, n);
+  p.A2 = w;
+  p.x0 = cand; p.x1 = q; p.ldx = n;
+  p.x2 = h; p.x2_stride = n + 1;
+  return gemm_launch<T, false, false, EPI_GAIN>(p, 1, st);
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t S, int64_t n, int64_t ldx,
+                                                     float* __restrict__ mean, float keep, float count) {
+  // one thread per column, coalesced across the warp; fp64 running sum, rounded once
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double acc = 0.0;
+  for (int64_t i = 0; i < S; ++i) acc += (double)__ldg(x + i * ldx + j);
+  mean[j] = __fadd_rn(__fmul_rn(mean[j], keep), __fdiv_rn((float)acc, count));
+}
+
+// ---- full-H scale search pieces --------------------------------------------
+// resid[(g - g0) * r + row, j] = descale(quant(w / (f_g * init))) - w   (scaling.py:128-130 -> 73-80)
+template <typename TE>
+__global__ void __launch_bounds__(256) grid_resid_kernel(const float* __restrict__ w, int64_t r, int64_t n,
+                                                         DevGrid<float> g, const float* __restrict__ factors,
+                                                         int g0, int gcount, const float* __restrict__ init,
+                                                         TE* __restrict__ resid) {
+  const int64_t total = (int64_t)gcount * r * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t j = i % n;
+    int64_t row = (i / n) % r;
+    int gi = (int)(i / (n * r));
+    float scale = __fmul_rn(__ldg(factors + g0 + gi), __ldg(init + row));
+    float rs = __fdiv_rn(1.0f, scale);
+    float x = __ldg(w + row * n + j);
+    float v = grid_value(g, __fdiv_rn(x, scale));
+    float dq = __fdiv_rn(v, rs);
+    resid[i] = (TE)__fsub_rn(dq, x);
+  }
+}
+
+// strict '<', grid order, best error kept in fp32 (scaling.py:125-134)
+template <typename TE>
+__global__ void __launch_bounds__(256) grid_argmin_kernel(const TE* __restrict__ err, int64_t r, int g0, int gcount,
+                                                          const float* __restrict__ factors,
+                                                          float* __restrict__ best_err, float* __restrict__ best_f) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  float be = best_err[row], bf = best_f[row];
+  for (int gi = 0; gi < gcount; ++gi) {
+    TE e = err[(int64_t)gi * r + row];
+    if (e < (TE)be) { be = (float)e; bf = __ldg(factors + g0 + gi); }
+  }
+  best_err[row] = be;
+  best_f[row] = bf;
+}
+
+__global__ void __launch_bounds__(256) fill_inf_kernel(float* a, float* b, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = __int_as_float(0x7f800000); b[i] = __int_as_float(0x7f800000); }
+}
+
+__global__ void __launch_bounds__(256) finish_scale_kernel(const float* __restrict__ init, const float* __restrict__ best_f,
+                                                           const float* __restrict__ best_err, int64_t r,
+                                                           float* __restrict__ out_scale, float* __restrict__ out_err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r) return;
+  out_scale[i] = __fmul_rn(init[i], best_f[i]);
+  if (out_err) out_err[i] = best_err[i];
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// how many grid points are evaluated per GEMM launch
+static inline int fullh_chunk(int64_t r, int64_t n, int G, size_t elem) {
+  const size_t budget = (size_t)1 << 30;  // <= 1 GiB of residuals per chunk
+  int64_t per = (int64_t)(budget / ((size_t)r * n * elem));
+  if (per < 1) per = 1;
+  if (per > G) per = G;
+  return (int)per;
+}
+
+}  // namespace slk
+
+using namespace slk;
+
+extern "C" {
+
+size_t slk_hweighted_error_ws_bytes(int64_t r, int64_t n, int32_t elem_bytes) {
+  int64_t tiles = elem_bytes == 8 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
+  return (size_t)(r * tiles) * (size_t)elem_bytes + 256;
+}
+
+int slk_hweighted_error_f32(const float* w, const float* q, const float* h, int64_t r, int64_t n, void* ws,
+                            size_t ws_bytes, float* out, void* stream) {
+  return hweighted_error_impl<float>(w, q, h, r, n, ws, ws_bytes, out, (cudaStream_t)stream);
+}
+int slk_hweighted_error_f64(const double* w, const double* q, const double* h, int64_t r, int64_t n, void* ws,
+                            size_t ws_bytes, double* out, void* stream) {
+  return hweighted_error_impl<double>(w, q, h, r, n, ws, ws_bytes, out, (cudaStream_t)stream);
+}
+
+int slk_gain_f32(const float* w, const float* q, const float* h, const float* cand, int64_t r, int64_t n,
+                 float* out, void* stream) {
+  return gain_impl<float>(w, q, h, cand, r, n, out, (cudaStream_t)stream);
+}
+int slk_gain_f64(const double* w, const double* q, const double* h, const double* cand, int64_t r, int64_t n,
+                 double* out, void* stream) {
+  return gain_impl<double>(w, q, h, cand, r, n, out, (cudaStream_t)stream);
+}
+
+int slk_hessian_accum_f32(const float* x, int64_t S, int64_t n, int64_t ldx, float* hess, float* mean, double keep,
+                          double new_count, void* stream) {
+  SLK_REQUIRE(x && hess && mean && S >= 1 && n >= 1 && ldx >= n, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  colsum_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(x, S, n, ldx, mean, (float)keep, (float)new_count);
+  SLK_LAUNCH_CHECK();
+  // H = H*keep + X^T X / count : A = X^T (stored [K=S, M=n]), B = X ([K=S, N=n])
+  GemmParams<float> p = gemm_params<float>(x, ldx, x, ldx, hess, n, n, n, S);
+  p.keep = (float)keep;
+  p.count = (float)new_count;
+  return gemm_launch<float, true, false, EPI_HESS>(p, 1, st);
+}
+
+size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t h_dtype) {
+  size_t elem = h_dtype == 2 ? 8 : 4;
+  int chunk = fullh_chunk(r, n, G, elem);
+  int64_t tiles = h_dtype == 2 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
+  size_t bytes = 0;
+  bytes += align256((size_t)chunk * r * n * elem);       // residuals
+  bytes += align256((size_t)chunk * r * tiles * elem);   // row-dot partials
+  bytes += align256((size_t)chunk * r * elem);           // errors
+  bytes += 3 * align256((size_t)r * sizeof(float));      // init, best_err, best_f
+  return bytes;
+}
+
+int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb, const float* factors,
+                               int32_t G, const void* h, int32_t h_dtype, void* ws, size_t ws_bytes,
+                               float* out_scale, float* out_err, void* stream) {
+  int rc = check_codebook(cb);
+  if (rc) return rc;
+  SLK_REQUIRE(w && factors && h && out_scale && r >= 1 && n >= 1 && G >= 1, "bad arguments");
+  SLK_REQUIRE(h_dtype == 1 || h_dtype == 2, "h_dtype %d", h_dtype);
+  SLK_REQUIRE(ws && ws_bytes >= slk_scale_search_fullh_ws_bytes(r, n, G, h_dtype), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t elem = h_dtype == 2 ? 8 : 4;
+  const int chunk = fullh_chunk(r, n, G, elem);
+  const int64_t tiles = h_dtype == 2 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
+  char* base = (char*)ws;
+  void* resid = base; base += align256((size_t)chunk * r * n * elem);
+  void* part = base; base += align256((size_t)chunk * r * tiles * elem);
+  void* errs = base; base += align256((size_t)chunk * r * elem);
+  float* init = (float*)base; base += align256((size_t)r * sizeof(float));
+  float* best_err = (float*)base; base += align256((size_t)r * sizeof(float));
+  float* best_f = (float*)base;
+
+  rc = slk_row_noclip_scale_f32(w, r, n, cb->lo, cb->hi, init, stream);
+  if (rc) return rc;
+  fill_inf_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(best_err, best_f, r);
+  SLK_LAUNCH_CHECK();
+  DevGrid<float> g = make_grid<float>(cb);
+  for (int g0 = 0; g0 < G; g0 += chunk) {
+    const int gc = (G - g0) < chunk ? (G - g0) : chunk;
+    const int64_t rows = (int64_t)gc * r;
+    int blocks = (int)(ceil_div(rows * n, 256) < (int64_t)sm_count() * 16 ? ceil_div(rows * n, 256) : (int64_t)sm_count() * 16);
+    if (h_dtype == 1) {
+      grid_resid_kernel<float><<<blocks, 256, 0, st>>>(w, r, n, g, factors, g0, gc, init, (float*)resid);
+      SLK_LAUNCH_CHECK();
+      GemmParams<float> p = gemm_params<float>((const float*)resid, n, (const float*)h, n, (float*)part, 0, rows, n, n);
+      rc = gemm_launch<float, false, false, EPI_ROWDOT>(p, 1, st);
+      if (rc) return rc;
+      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const float*)part, rows, tiles, (float*)errs);
+      SLK_LAUNCH_CHECK();
+      grid_argmin_kernel<float><<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, r, g0, gc, factors, best_err, best_f);
+    } else {
+      grid_resid_kernel<double><<<blocks, 256, 0, st>>>(w, r, n, g, factors, g0, gc, init, (double*)resid);
+      SLK_LAUNCH_CHECK();
+      GemmParams<double> p = gemm_params<double>((const double*)resid, n, (const double*)h, n, (double*)part, 0, rows, n, n);
+      rc = gemm_launch<double, false, false, EPI_ROWDOT>(p, 1, st);
+      if (rc) return rc;
+      rowdot_reduce_kernel<double><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const double*)part, rows, tiles, (double*)errs);
+      SLK_LAUNCH_CHECK();
+      grid_argmin_kernel<double><<<(int)ceil_div(r, 256), 256, 0, st>>>((const double*)errs, r, g0, gc, factors, best_err, best_f);
+    }
+    SLK_LAUNCH_CHECK();
+  }
+  finish_scale_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(init, best_f, best_err, r, out_scale, out_err);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,545 @@
+// K4: codebook rounding, plus the HBM-bound elementwise / reduction helpers of the
+// hot path (row scales, axis scaling, bias removal, column permutation, ordering keys).
+// All of them are one pass over their input, 128-bit vectorised where the layout allows,
+// with grids sized in multiples of the SM count.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace slk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+static inline int stream_grid(int64_t work_items, int per_block, int max_waves = 8) {
+  int64_t blocks = ceil_div(work_items, per_block);
+  int64_t cap = (int64_t)sm_count() * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------
+// rounding
+// ---------------------------------------------------------------------------
+template <typename T, typename VT>
+__device__ __forceinline__ void round_one(const DevGrid<T>& g, T x, int mode, VT* out_val,
+                                          void* out_idx, int idx_bytes, int64_t i) {
+  if (g.kind == 0) {
+    T k = uniform_slot<T>(g, x, mode);
+    if (out_val) out_val[i] = (VT)uniform_value_of_slot<T>(g, k);
+    if (out_idx) {
+      unsigned u = (unsigned)k;
+      if (idx_bytes == 1) ((uint8_t*)out_idx)[i] = (uint8_t)u;
+      else if (idx_bytes == 2) ((uint16_t*)out_idx)[i] = (uint16_t)u;
+      else ((uint32_t*)out_idx)[i] = u;
+    }
+  } else {
+    int k = table_index<T>(g, x, mode);
+    if (out_val) out_val[i] = (VT)__ldg(g.values + k);
+    if (out_idx) {
+      if (idx_bytes == 1) ((uint8_t*)out_idx)[i] = (uint8_t)k;
+      else if (idx_bytes == 2) ((uint16_t*)out_idx)[i] = (uint16_t)k;
+      else ((uint32_t*)out_idx)[i] = (uint32_t)k;
+    }
+  }
+}
+
+// fp32 fast path: 4 values per thread per step, 128-bit loads and stores.
+__global__ void __launch_bounds__(256) round_f32_vec4_kernel(const float4* __restrict__ x, int64_t nvec,
+                                                             DevGrid<float> g, int mode,
+                                                             float4* __restrict__ out_val,
+                                                             uint32_t* __restrict__ out_idx8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 v = __ldcs(x + i);
+    float in[4] = {v.x, v.y, v.z, v.w};
+    float val[4];
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (g.kind == 0) {
+        float s = uniform_slot<float>(g, in[k], mode);
+        val[k] = uniform_value_of_slot<float>(g, s);
+        packed |= ((uint32_t)s & 0xffu) << (8 * k);
+      } else {
+        int s = table_index<float>(g, in[k], mode);
+        val[k] = __ldg(g.values + s);
+        packed |= ((uint32_t)s & 0xffu) << (8 * k);
+      }
+    }
+    if (out_val) __stcs(out_val + i, make_float4(val[0], val[1], val[2], val[3]));
+    if (out_idx8) out_idx8[i] = packed;
+  }
+}
+
+template <typename T, typename VT>
+__global__ void __launch_bounds__(256) round_scalar_kernel(const T* __restrict__ x, int64_t begin, int64_t count,
+                                                           DevGrid<T> g, int mode, VT* out_val,
+                                                           void* out_idx, int idx_bytes) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    round_one<T, VT>(g, x[i], mode, out_val, out_idx, idx_bytes, i);
+}
+
+static inline int index_bytes(int size) { return size <= 256 ? 1 : (size <= 65536 ? 2 : 4); }
+
+template <typename T>
+static int round_impl(const T* x, int64_t count, const slk_codebook* cb, int mode, void* out_val,
+                      void* out_idx, cudaStream_t st) {
+  int rc = check_codebook(cb);
+  if (rc) return rc;
+  SLK_REQUIRE(mode >= 0 && mode <= 2, "round mode %d", mode);
+  SLK_REQUIRE(count >= 0, "negative count");
+  if (count == 0) return SLK_OK;
+  SLK_REQUIRE(x != nullptr, "x is NULL");
+  SLK_REQUIRE(cb->kind == 1 || cb->size >= 2, "uniform codebook of size < 2");
+  if (cb->kind == 0 && mode != SLK_NEAREST) SLK_REQUIRE(cb->size >= 2, "up/down need size >= 2");
+  DevGrid<T> g = make_grid<T>(cb);
+  const int ib = index_bytes(cb->size);
+  int64_t done = 0;
+  if (sizeof(T) == 4 && ib == 1) {
+    bool aligned = ((uintptr_t)x % 16 == 0) && (!out_val || (uintptr_t)out_val % 16 == 0) &&
+                   (!out_idx || (uintptr_t)out_idx % 4 == 0);
+    int64_t nvec = aligned ? count / 4 : 0;
+    if (nvec > 0) {
+      round_f32_vec4_kernel<<<stream_grid(nvec, 256), 256, 0, st>>>(
+          (const float4*)x, nvec, *(DevGrid<float>*)&g, mode, (float4*)out_val, (uint32_t*)out_idx);
+      SLK_LAUNCH_CHECK();
+      done = nvec * 4;
+    }
+  }
+  if (done < count) {
+    if (sizeof(T) == 8 && cb->kind == 1)
+      round_scalar_kernel<T, float><<<stream_grid(count - done, 256), 256, 0, st>>>(
+          x, done, count, g, mode, (float*)out_val, out_idx, ib);
+    else
+      round_scalar_kernel<T, T><<<stream_grid(count - done, 256), 256, 0, st>>>(
+          x, done, count, g, mode, (T*)out_val, out_idx, ib);
+    SLK_LAUNCH_CHECK();
+  }
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// axis scaling: out[o, a, i] = x[o, a, i] / s[a]   (or / (1/s[a]))
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) scale_axis_kernel(const T* __restrict__ x, int64_t total, int64_t len,
+                                                         int64_t inner, const T* __restrict__ s, int mode,
+                                                         T* __restrict__ out) {
+  typedef Ieee<T> F;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t a = (i / inner) % len;
+    T d = s[a];
+    if (mode == 1) d = F::div((T)1, d);
+    out[i] = F::div(x[i], d);
+  }
+}
+
+// rows contiguous (inner == n, one divisor per row): 128-bit path for fp32
+__global__ void __launch_bounds__(256) scale_rows_vec4_kernel(const float4* __restrict__ x, int64_t r, int64_t nvec,
+                                                              const float* __restrict__ s, int mode,
+                                                              float4* __restrict__ out) {
+  const int64_t total = r * nvec;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float d = __ldg(s + i / nvec);
+    if (mode == 1) d = __fdiv_rn(1.0f, d);
+    float4 v = __ldcs(x + i);
+    v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
+    __stcs(out + i, v);
+  }
+}
+
+template <typename T>
+static int scale_axis_impl(const T* x, int64_t outer, int64_t len, int64_t inner, const T* s, int mode,
+                           T* out, cudaStream_t st) {
+  SLK_REQUIRE(outer >= 0 && len >= 0 && inner >= 0, "negative extent");
+  SLK_REQUIRE(mode == 0 || mode == 1, "scale mode %d", mode);
+  int64_t total = outer * len * inner;
+  if (total == 0) return SLK_OK;
+  SLK_REQUIRE(x && s && out, "NULL pointer");
+  if (sizeof(T) == 4 && inner % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)out % 16 == 0 && outer == 1) {
+    scale_rows_vec4_kernel<<<stream_grid(total / 4, 256), 256, 0, st>>>(
+        (const float4*)x, len, inner / 4, (const float*)s, mode, (float4*)out);
+  } else {
+    scale_axis_kernel<T><<<stream_grid(total, 256), 256, 0, st>>>(x, total, len, inner, s, mode, out);
+  }
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-row scales
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) row_noclip_scale_kernel(const T* __restrict__ w, int64_t r, int64_t n,
+                                                               T cb_min, T cb_max, T* __restrict__ out) {
+  typedef Ieee<T> F;
+  __shared__ T smin[32], smax[32];
+  for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
+    const T* p = w + row * n;
+    T lo = p[0], hi = p[0];
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+      T v = p[j];
+      lo = v < lo ? v : lo;
+      hi = v > hi ? v : hi;
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int nw = (blockDim.x + 31) >> 5;
+      lo = threadIdx.x < nw ? smin[threadIdx.x] : smin[0];
+      hi = threadIdx.x < nw ? smax[threadIdx.x] : smax[0];
+      lo = warp_min(lo); hi = warp_max(hi);
+      if (threadIdx.x == 0) {
+        // scaling.py:53-54: max(max/maxcode, min/mincode), floored at float32(1e-16)
+        T a = F::div(hi, cb_max), b = F::div(lo, cb_min);
+        T s = a > b ? a : b;
+        T fl = (T)1.0e-16f;
+        out[row] = s > fl ? s : fl;
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) row_rms_scale_kernel(const T* __restrict__ w, int64_t r, int64_t n,
+                                                            T* __restrict__ out) {
+  typedef Ieee<T> F;
+  __shared__ double scratch[32];
+  for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
+    const T* p = w + row * n;
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+      T v = p[j];
+      acc += (double)F::mul(v, v);
+    }
+    acc = block_sum<double>(acc, scratch);
+    if (threadIdx.x == 0) {
+      // scaling.py:40-41: sqrt(max(mean(x^2), 1e-16)); the mean is rounded to the data dtype
+      T m = F::div((T)acc, (T)n);
+      T fl = (T)1.0e-16;
+      m = m > fl ? m : fl;
+      out[row] = F::sqrt(m);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// H - outer(m, m)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) remove_bias_kernel(const T* __restrict__ h, const T* __restrict__ m, int64_t n,
+                                                          T* __restrict__ out) {
+  typedef Ieee<T> F;
+  const int64_t total = n * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t a = i / n, b = i - a * n;
+    out[i] = F::sub(h[i], F::mul(m[a], m[b]));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// column gather / scatter of a [r, n] matrix
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) permute_cols_kernel(const float* __restrict__ src, int64_t r, int64_t n,
+                                                           const int64_t* __restrict__ idx, int scatter,
+                                                           float* __restrict__ dst) {
+  const int64_t total = r * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t row = i / n, j = i - row * n;
+    int64_t k = __ldg(idx + j);
+    if (scatter) dst[row * n + k] = src[i];
+    else dst[i] = __ldg(src + row * n + k);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ordering helpers
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) damp_value_kernel(const float* __restrict__ h, int64_t n, float damp,
+                                                         float* __restrict__ out) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += (double)h[j * (n + 1)];
+  acc = block_sum<double>(acc, scratch);
+  if (threadIdx.x == 0) {
+    // obq.py:198: damp (Python float, weak) * float32 mean -> float32
+    float mean = __fdiv_rn((float)acc, (float)n);
+    out[0] = __fmul_rn(damp, mean);
+  }
+}
+
+// one thread per column, rows added in order (numpy's axis-0 reduction order)
+__global__ void __launch_bounds__(128) col_resid_sums_kernel(const float* __restrict__ w, int64_t r, int64_t n,
+                                                             DevGrid<float> g, int mode, float* __restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float acc = 0.0f;
+  for (int64_t i = 0; i < r; ++i) {
+    float x = __ldg(w + i * n + j);
+    float d = __fsub_rn(grid_value(g, x), x);
+    float t = mode == 0 ? fabsf(d) : __fmul_rn(d, d);
+    acc = __fadd_rn(acc, t);
+  }
+  out[j] = acc;
+}
+
+__global__ void __launch_bounds__(256) order_keys_kernel(const float* __restrict__ h, int64_t n,
+                                                         const float* __restrict__ dampval,
+                                                         const float* __restrict__ colsum, double* __restrict__ keys) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double d = (double)h[j * (n + 1)];
+  if (dampval) d = __dadd_rn(d, (double)dampval[0]);
+  double k = -d;
+  if (colsum) k = __dmul_rn(k, (double)colsum[j]);
+  keys[j] = k;
+}
+
+// Stable rank sort: order[rank(j)] = j with rank = #{i : key_i < key_j or (== and i < j)}.
+// O(n^2) compares spread over the grid; n <= a few 10^4 here, so this is microseconds and
+// needs no scratch.  NaN keys sort last (as numpy does).
+__global__ void __launch_bounds__(256) argsort_rank_kernel(const double* __restrict__ keys, int64_t n,
+                                                           int64_t* __restrict__ order) {
+  __shared__ double tile[1024];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double kj = j < n ? keys[j] : 0.0;
+  const bool nanj = kj != kj;
+  int64_t rank = 0;
+  for (int64_t base = 0; base < n; base += 1024) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 1024; t += blockDim.x) tile[t] = base + t < n ? keys[base + t] : 0.0;
+    __syncthreads();
+    int lim = (int)((n - base) < 1024 ? (n - base) : 1024);
+    if (j < n) {
+      for (int t = 0; t < lim; ++t) {
+        double ki = tile[t];
+        int64_t i = base + t;
+        bool nani = ki != ki;
+        bool before;
+        if (nanj) before = !nani || i < j;
+        else before = !nani && (ki < kj || (ki == kj && i < j));
+        rank += before ? 1 : 0;
+      }
+    }
+  }
+  if (j < n) order[rank] = j;
+}
+
+__global__ void __launch_bounds__(256) mean_kernel_f32(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += (double)v[j];
+  acc = block_sum<double>(acc, scratch);
+  if (threadIdx.x == 0) out[0] = __fdiv_rn((float)acc, (float)n);
+}
+__global__ void __launch_bounds__(256) mean_kernel_f64(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += v[j];
+  acc = block_sum<double>(acc, scratch);
+  if (threadIdx.x == 0) out[0] = acc / (double)n;
+}
+
+// delta[row] = sum_j (w - wq)[row, j] * mean[j]
+__global__ void __launch_bounds__(256) bias_delta_kernel(const float* __restrict__ w, const float* __restrict__ wq,
+                                                         const float* __restrict__ mean, int64_t r, int64_t n,
+                                                         float* __restrict__ delta) {
+  __shared__ double scratch[32];
+  for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+      float d = __fsub_rn(w[row * n + j], wq[row * n + j]);
+      acc += (double)__fmul_rn(d, __ldg(mean + j));
+    }
+    acc = block_sum<double>(acc, scratch);
+    if (threadIdx.x == 0) delta[row] = (float)acc;
+  }
+}
+
+}  // namespace slk
+
+using namespace slk;
+
+template <typename T>
+static int row_noclip_impl(const T* w, int64_t r, int64_t n, double cb_min, double cb_max, T* out, void* stream) {
+  SLK_REQUIRE(r >= 0 && n >= 1, "bad shape [%lld, %lld]", (long long)r, (long long)n);
+  SLK_REQUIRE(cb_min < 0 && cb_max > 0, "Codebook should have both negative and positive values.");
+  if (r == 0) return SLK_OK;
+  SLK_REQUIRE(w && out, "NULL pointer");
+  int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  row_noclip_scale_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(w, r, n, (T)cb_min, (T)cb_max, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+template <typename T>
+static int row_rms_impl(const T* w, int64_t r, int64_t n, T* out, void* stream) {
+  SLK_REQUIRE(r >= 0 && n >= 1, "bad shape");
+  if (r == 0) return SLK_OK;
+  SLK_REQUIRE(w && out, "NULL pointer");
+  int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  row_rms_scale_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(w, r, n, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+template <typename T>
+static int remove_bias_impl(const T* h, const T* m, int64_t n, T* out, void* stream) {
+  SLK_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return SLK_OK;
+  SLK_REQUIRE(h && m && out, "NULL pointer");
+  remove_bias_kernel<T><<<stream_grid(n * n, 256), 256, 0, (cudaStream_t)stream>>>(h, m, n, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+extern "C" {
+
+int slk_abi_version(void) { return SLK_ABI_VERSION; }
+const char* slk_last_error(void) { return slk::g_err; }
+
+int slk_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) {
+  int dev = 0;
+  SLK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  SLK_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count_host) *sm_count_host = p.multiProcessorCount;
+  if (cc_major_host) *cc_major_host = p.major;
+  if (cc_minor_host) *cc_minor_host = p.minor;
+  return SLK_OK;
+}
+
+int slk_round_f32(const float* x, int64_t count, const slk_codebook* cb, int mode, float* out_val,
+                  void* out_idx, void* stream) {
+  return round_impl<float>(x, count, cb, mode, out_val, out_idx, (cudaStream_t)stream);
+}
+int slk_round_f64(const double* x, int64_t count, const slk_codebook* cb, int mode, void* out_val,
+                  void* out_idx, void* stream) {
+  return round_impl<double>(x, count, cb, mode, out_val, out_idx, (cudaStream_t)stream);
+}
+
+int slk_scale_axis_f32(const float* x, int64_t outer, int64_t len, int64_t inner, const float* s, int mode,
+                       float* out, void* stream) {
+  return scale_axis_impl<float>(x, outer, len, inner, s, mode, out, (cudaStream_t)stream);
+}
+int slk_scale_axis_f64(const double* x, int64_t outer, int64_t len, int64_t inner, const double* s, int mode,
+                       double* out, void* stream) {
+  return scale_axis_impl<double>(x, outer, len, inner, s, mode, out, (cudaStream_t)stream);
+}
+
+int slk_row_noclip_scale_f32(const float* w, int64_t r, int64_t n, double cb_min, double cb_max, float* out,
+                             void* stream) {
+  return row_noclip_impl<float>(w, r, n, cb_min, cb_max, out, stream);
+}
+int slk_row_noclip_scale_f64(const double* w, int64_t r, int64_t n, double cb_min, double cb_max, double* out,
+                             void* stream) {
+  return row_noclip_impl<double>(w, r, n, cb_min, cb_max, out, stream);
+}
+
+int slk_row_rms_scale_f32(const float* w, int64_t r, int64_t n, float* out, void* stream) {
+  return row_rms_impl<float>(w, r, n, out, stream);
+}
+int slk_row_rms_scale_f64(const double* w, int64_t r, int64_t n, double* out, void* stream) {
+  return row_rms_impl<double>(w, r, n, out, stream);
+}
+
+int slk_remove_input_bias_f32(const float* h, const float* m, int64_t n, float* out, void* stream) {
+  return remove_bias_impl<float>(h, m, n, out, stream);
+}
+int slk_remove_input_bias_f64(const double* h, const double* m, int64_t n, double* out, void* stream) {
+  return remove_bias_impl<double>(h, m, n, out, stream);
+}
+
+int slk_damp_value_f32(const float* h, int64_t n, double damp, float* out_dampval, void* stream) {
+  SLK_REQUIRE(h && out_dampval && n >= 1, "bad arguments");
+  damp_value_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(h, n, (float)damp, out_dampval);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_col_resid_sums_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb, int mode, float* out,
+                           void* stream) {
+  int rc = check_codebook(cb);
+  if (rc) return rc;
+  SLK_REQUIRE(w && out && r >= 0 && n >= 1 && (mode == 0 || mode == 1), "bad arguments");
+  col_resid_sums_kernel<<<(int)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(w, r, n, make_grid<float>(cb), mode, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_order_keys(const float* h, int64_t n, const float* dampval, const float* colsum, double* keys,
+                   void* stream) {
+  SLK_REQUIRE(h && keys && n >= 1, "bad arguments");
+  order_keys_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(h, n, dampval, colsum, keys);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_argsort_f64(const double* keys, int64_t n, int64_t* order, void* stream) {
+  SLK_REQUIRE(keys && order && n >= 1, "bad arguments");
+  argsort_rank_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, order);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* idx, int scatter, float* dst,
+                         void* stream) {
+  SLK_REQUIRE(r >= 0 && n >= 0, "negative extent");
+  if (r * n == 0) return SLK_OK;
+  SLK_REQUIRE(src && idx && dst && src != dst, "bad pointers");
+  permute_cols_kernel<<<stream_grid(r * n, 256), 256, 0, (cudaStream_t)stream>>>(src, r, n, idx, scatter, dst);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_mean_f32(const float* v, int64_t count, float* out, void* stream) {
+  SLK_REQUIRE(v && out && count >= 1, "bad arguments");
+  mean_kernel_f32<<<1, 256, 0, (cudaStream_t)stream>>>(v, count, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+int slk_mean_f64(const double* v, int64_t count, double* out, void* stream) {
+  SLK_REQUIRE(v && out && count >= 1, "bad arguments");
+  mean_kernel_f64<<<1, 256, 0, (cudaStream_t)stream>>>(v, count, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_bias_delta_f32(const float* w, const float* wq, const float* mean, int64_t r, int64_t n, float* delta,
+                       void* stream) {
+  SLK_REQUIRE(w && wq && mean && delta && r >= 1 && n >= 1, "bad arguments");
+  int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  bias_delta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, wq, mean, r, n, delta);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+}  // extern "C"

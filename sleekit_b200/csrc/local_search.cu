@@ -1,0 +1,147 @@
+// K7: best-first local search.
+//   LocalSearchQuantizer / quantize_local_search            obq.py:234-358
+//   compute_gain                                            obq.py:220-231
+// The reference keeps six [r, n] arrays and patches both gain matrices after every flip
+// (obq.py:299-336).  Rows never interact, so here one CTA owns one row and keeps only
+//   codes[n] (uint16)  and  p[n] = ((Q - W) @ H)[row]  (fp32)
+// in shared memory; gains are recomputed from p on every move,
+//   gain(j, D) = -D^2 * H[j,j] - 2 * p[j] * D       (obq.py:231)
+// the best up / best down flips are found with a block arg-max (first index wins ties, as
+// np.argmax), the reference's selection rule (obq.py:339-342) picks one, and p is advanced by
+// the one row of H the flip touches: p += delta * H[b, :].  Per move and row the traffic is one
+// row of H (4n bytes, L2-resident across rows) instead of ~20n bytes of gain patches.
+#include "gemm.cuh"
+
+namespace slk {
+
+__global__ void __launch_bounds__(256) ls_diag_kernel(const float* __restrict__ h, int64_t n, float* __restrict__ d) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) d[j] = h[j * (n + 1)];
+}
+
+struct Best { float v; int i; };
+
+__device__ __forceinline__ Best best_of(Best a, Best b) {
+  // larger value wins; on equal values the smaller index wins
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+
+__device__ __forceinline__ Best warp_best(Best x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = best_of(x, y);
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(256) local_search_kernel(float* __restrict__ Q, const float* __restrict__ P,
+                                                           const float* __restrict__ H, const float* __restrict__ hdiag,
+                                                           int64_t r, int64_t n, DevGrid<float> g, int moves) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* p = (float*)smem_raw;                       // [n]
+  uint16_t* code = (uint16_t*)(p + n);               // [n]
+  __shared__ Best red_up[8], red_dn[8];
+  __shared__ int s_col, s_newk;
+  __shared__ float s_delta;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float NEG_INF = __int_as_float(0xff800000);
+  const int top = g.size - 1;
+
+  for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
+    for (int64_t j = tid; j < n; j += blockDim.x) {
+      p[j] = P[row * n + j];
+      code[j] = (uint16_t)grid_index(g, Q[row * n + j]);
+    }
+    __syncthreads();
+    for (int mv = 0; mv < moves; ++mv) {
+      Best bu, bd;
+      bu.v = NEG_INF; bu.i = 0x7fffffff; bd = bu;
+      for (int64_t j = tid; j < n; j += blockDim.x) {
+        const int k = code[j];
+        const float v = grid_value_of_index(g, k);
+        const float hj = __ldg(hdiag + j);
+        const float p2 = __fmul_rn(2.0f, p[j]);
+        const float du = k < top ? __fsub_rn(grid_value_of_index(g, k + 1), v) : 0.0f;
+        const float dd = k > 0 ? __fsub_rn(grid_value_of_index(g, k - 1), v) : 0.0f;
+        const float gu = __fsub_rn(__fmul_rn(-__fmul_rn(du, du), hj), __fmul_rn(p2, du));
+        const float gd = __fsub_rn(__fmul_rn(-__fmul_rn(dd, dd), hj), __fmul_rn(p2, dd));
+        if (gu > bu.v) { bu.v = gu; bu.i = (int)j; }
+        if (gd > bd.v) { bd.v = gd; bd.i = (int)j; }
+      }
+      bu = warp_best(bu); bd = warp_best(bd);
+      if (lane == 0) { red_up[wid] = bu; red_dn[wid] = bd; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { bu = best_of(bu, red_up[k]); bd = best_of(bd, red_dn[k]); }
+        const bool up = (bu.v > bd.v) && (bu.v > 0.0f);      // obq.py:341
+        const bool down = !up && (bd.v > 0.0f);               // obq.py:342
+        if (up || down) {
+          const int col = up ? bu.i : bd.i;
+          const int k = code[col];
+          const int nk = up ? k + 1 : k - 1;
+          s_col = col; s_newk = nk;
+          s_delta = __fsub_rn(grid_value_of_index(g, nk), grid_value_of_index(g, k));
+        } else {
+          s_col = -1;
+        }
+      }
+      __syncthreads();
+      const int col = s_col;
+      if (col < 0) break;  // local optimum: later moves would not change this row either
+      const float delta = s_delta;
+      const float* hrow = H + (int64_t)col * n;
+      for (int64_t j = tid; j < n; j += blockDim.x) p[j] = __fmaf_rn(delta, __ldg(hrow + j), p[j]);
+      if (tid == 0) code[col] = (uint16_t)s_newk;
+      __syncthreads();
+    }
+    for (int64_t j = tid; j < n; j += blockDim.x) Q[row * n + j] = grid_value_of_index(g, code[j]);
+    __syncthreads();
+  }
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace slk
+
+using namespace slk;
+
+extern "C" {
+
+size_t slk_local_search_ws_bytes(int64_t r, int64_t n) {
+  return align256((size_t)r * n * sizeof(float)) + align256((size_t)n * sizeof(float));
+}
+
+int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
+                         int32_t moves, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_codebook(cb);
+  if (rc) return rc;
+  SLK_REQUIRE(r >= 0 && n >= 1 && moves >= 0, "bad arguments");
+  SLK_REQUIRE(cb->size <= 65536, "local search supports codebooks up to 65536 entries");
+  if (r == 0 || moves == 0) return SLK_OK;
+  SLK_REQUIRE(w && q && h, "NULL pointer");
+  SLK_REQUIRE(ws && ws_bytes >= slk_local_search_ws_bytes(r, n), "workspace too small");
+  const size_t smem = (size_t)n * 6 + 16;
+  SLK_REQUIRE(smem <= 220 * 1024, "row of %lld columns does not fit in shared memory", (long long)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* P = (float*)ws;
+  float* hdiag = (float*)((char*)ws + align256((size_t)r * n * sizeof(float)));
+  ls_diag_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(h, n, hdiag);
+  SLK_LAUNCH_CHECK();
+  // P = (Q - W) @ H                                           obq.py:229-231
+  GemmParams<float> p = gemm_params<float>(q, n, h, n, P, n, r, n, n);
+  p.A2 = w;
+  rc = gemm_launch<float, false, false, EPI_STORE>(p, 1, st);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    SLK_CUDA(cudaFuncSetAttribute(local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  local_search_kernel<<<grid, 256, smem, st>>>(q, P, h, hdiag, r, n, make_grid<float>(cb), moves);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+}  // extern "C"

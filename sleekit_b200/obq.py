@@ -1,0 +1,277 @@
+"""Drop-in for ``sleekit.obq`` (reference: sleekit/obq.py), on CUDA kernels.
+
+Public names, argument order, defaults, array layouts and error behaviour
+follow the reference.  Host numpy arrays in -> host numpy arrays out; CUDA
+torch tensors pass through and stay on the device (no synchronisation).
+"""
+
+import numpy as np
+import torch
+
+from . import _convert as cv
+from . import ops
+
+__all__ = [
+    "np", "random_psd_matrix", "remove_input_bias", "remove_dead_values", "compute_hessian_chol",
+    "compute_hessian_order", "channelwise_error", "quantization_error", "quantize_opt", "compute_gain",
+    "LocalSearchQuantizer", "quantize_local_search", "_quantize_opt_core", "_quantize_opt_block",
+]
+
+MAX_LEAF = 32  # widest column block the leaf kernel sweeps (one lane per column)
+
+
+def random_psd_matrix(size, rank, damp=0.0):
+    """Wishart-distributed PSD test matrix, fp64 (obq.py:4-11).  Host RNG helper, not hot path."""
+    factor = np.random.randn(size, rank).astype(np.float32)
+    gram = factor @ factor.T
+    return gram + damp * np.linalg.norm(gram, ord=2, axis=1) * np.eye(size)
+
+
+def remove_input_bias(H, input_bias):
+    """H - outer(m, m) (obq.py:14-25)."""
+    assert H.ndim == 2
+    assert input_bias.ndim == 1
+    assert H.shape[0] == H.shape[1]
+    assert H.shape[0] == input_bias.shape[0]
+    dt = cv.torch_float(np.result_type(cv.float_dtype_of(H), cv.float_dtype_of(input_bias)))
+    out = ops.remove_input_bias(cv.to_dev(H, dt), cv.to_dev(input_bias, dt))
+    return cv.back(out, H)
+
+
+def remove_dead_values(H, W):
+    """In place: dead inputs (zero diagonal) get the mean diagonal and zero weights (obq.py:28-35).
+    An O(n) mutation of caller-owned arrays, done where they live."""
+    if cv.is_tensor(H):
+        d = H.diagonal()
+        fill = d.mean()
+        dead = d == 0
+        d[dead] = fill
+        W[:, dead] = 0
+        return
+    d = H.diagonal()
+    fill = d.mean()
+    dead = d == 0
+    H[dead, dead] = fill
+    W[:, dead] = 0
+
+
+def _raise_if_not_pd(info):
+    bad = int(info.item())
+    if bad != 0:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+
+
+def compute_hessian_chol(H):
+    """Upper factor U with inv(H) = U^T U, fp64 (obq.py:38-55)."""
+    h = cv.to_dev(H, torch.float64)
+    assert h.ndim == 2 and h.shape[0] == h.shape[1]
+    u64, _, info = ops.hinv(h, want64=True, want32=False)
+    if not cv.is_tensor(H):
+        _raise_if_not_pd(info)
+    return cv.back(u64, H)
+
+
+def _device_order(Wd, Hd, quantizer, act_order, diag64=None):
+    """argsort keys of obq.py:58-86 for a device W (fp32) and the fp64 diagonal of H_opt."""
+    n = Wd.shape[1]
+    if act_order == "none":
+        return torch.arange(n, dtype=torch.int64, device=Wd.device)
+    d = diag64 if diag64 is not None else Hd.diagonal().to(torch.float64)
+    if act_order == "diag":
+        keys = -d
+    elif act_order in ("err", "sqerr"):
+        col = ops.col_resid_sums(Wd, quantizer, squared=(act_order == "sqerr"))
+        keys = -d * col.to(torch.float64)
+    elif act_order in ("inv_diag", "combined_diag"):
+        u64, _, _ = ops.hinv(Hd.to(torch.float64).contiguous(), want64=True, want32=False)
+        inv_diag = (u64 * u64).sum(dim=0)  # diag(U^T U)
+        keys = inv_diag if act_order == "inv_diag" else -d / inv_diag
+    elif act_order == "pivot":
+        raise NotImplementedError(
+            "act_order='pivot' (obq.py:140-166) is outside the accelerated hot path (SURVEY 8f-4)")
+    else:
+        raise RuntimeError(f"Invalid act_order value {act_order}")
+    return ops.argsort(keys.contiguous())
+
+
+def compute_hessian_order(W, H, quantizer, act_order):
+    """Column ordering heuristics (obq.py:58-86); returns int64 indices."""
+    if act_order not in ("err", "sqerr", "combined_diag", "inv_diag", "pivot", "diag", "none"):
+        raise RuntimeError(f"Invalid act_order value {act_order}")
+    Wd = cv.to_dev(W, torch.float32)
+    Hd = cv.to_dev(H)
+    order = _device_order(Wd, Hd, quantizer, act_order)
+    return cv.back(order, W)
+
+
+def channelwise_error(W, Q, H):
+    """((W-Q) @ H * (W-Q)).sum(-1) per row (obq.py:89-95)."""
+    dt_np = np.result_type(cv.float_dtype_of(W), cv.float_dtype_of(Q), cv.float_dtype_of(H))
+    dt = cv.torch_float(dt_np)
+    # the residual is formed in the dtype of W and Q, then promoted with H (numpy semantics)
+    wq = cv.torch_float(np.result_type(cv.float_dtype_of(W), cv.float_dtype_of(Q)))
+    Wd, Qd = cv.to_dev(W, wq), cv.to_dev(Q, wq)
+    lead = Wd.shape[:-1]
+    Wd, Qd = Wd.reshape(-1, Wd.shape[-1]), Qd.reshape(-1, Qd.shape[-1])
+    Hd = cv.to_dev(H, dt)
+    if wq == dt:
+        err = ops.hweighted_error(Wd, Qd, Hd)
+    else:
+        err = ops.hweighted_error((Wd - Qd).to(dt), None, Hd)
+    return cv.back(err.reshape(lead), W)
+
+
+def quantization_error(W, Q, H):
+    """Mean of channelwise_error, a scalar of the promoted dtype (obq.py:98-103)."""
+    if cv.is_tensor(W):
+        return ops.mean(channelwise_error(W, Q, H).reshape(-1).contiguous())
+    dt_np = np.result_type(cv.float_dtype_of(W), cv.float_dtype_of(Q), cv.float_dtype_of(H))
+    rows = channelwise_error(cv.to_dev(W), cv.to_dev(Q), cv.to_dev(H))
+    m = ops.mean(rows.reshape(-1).contiguous())
+    return np.dtype(dt_np).type(m.item())  # a numpy scalar, so f-strings print as the reference's do
+
+
+def _sweep_leaf(min_block_size):
+    return int(min(max(int(min_block_size), 1), MAX_LEAF))
+
+
+def _quantize_opt_block(Q, E, Hinv, quantizer, min_block_size, num_blocks):
+    """Blocked sweep, in place on Q and E (obq.py:121-137).  Leaves wider than 32 columns are
+    split further (the result is the same algebra; the reference's own test_blockobq shows the
+    blocking does not matter)."""
+    if cv.is_tensor(Q):
+        u64 = cv.to_dev(Hinv, torch.float64)
+        ops.gptq_sweep(Q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks, e=E)
+        return
+    q = cv.to_dev(Q, torch.float32)
+    u64 = cv.to_dev(Hinv, torch.float64)
+    q, e = ops.gptq_sweep(q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks)
+    Q[...] = cv.to_host(q)
+    E[...] = cv.to_host(e)
+
+
+def _quantize_opt_core(Q, E, Hinv, quantizer):
+    """Unblocked sweep, in place (obq.py:106-118)."""
+    _quantize_opt_block(Q, E, Hinv, quantizer, MAX_LEAF, 8)
+
+
+def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
+                check=False):
+    """quantize_opt on device tensors (fp32 W [r,n], fp32 H [n,n]); returns quantized values [r,n].
+    The whole chain -- damp, keys, argsort, gather, fp64 factor, sweep, scatter, local search --
+    is enqueued on the current stream without a host round trip."""
+    dampval = ops.damp_value(Hd, damp)                                   # obq.py:198
+    if act_order == "none":
+        order = None
+    elif act_order in ("diag", "err", "sqerr"):
+        col = None
+        if act_order != "diag":
+            col = ops.col_resid_sums(Wd, quantizer, squared=(act_order == "sqerr"))
+        order = ops.argsort(ops.order_keys(Hd, dampval, col))            # obq.py:199
+    else:
+        hopt_diag = Hd.diagonal().to(torch.float64) + dampval.to(torch.float64)
+        hopt = Hd.to(torch.float64)
+        hopt.diagonal().add_(dampval.to(torch.float64))
+        order = _device_order(Wd, hopt, quantizer, act_order, hopt_diag)
+    Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
+    u64, u32, info = ops.hinv(Hd, order, dampval)                         # obq.py:204-205
+    ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209
+    if order is not None:
+        Q = ops.permute_cols(Q, order, scatter=True)                      # obq.py:212-213
+    if check:
+        _raise_if_not_pd(info)
+    if nb_ls_moves:
+        ops.local_search(Wd, Q, Hd, quantizer, nb_ls_moves)               # obq.py:216
+    return Q
+
+
+def quantize_opt(W, H, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8):
+    """GPTQ-like error-compensated quantization (obq.py:169-217)."""
+    assert W.ndim == 2
+    assert H.ndim == 2
+    assert H.shape[0] == H.shape[1]
+    assert H.shape[0] == W.shape[1]
+    assert min_block_size >= 1
+    Wd = cv.to_dev(W, torch.float32)   # obq.py:195-196: both cast to fp32
+    Hd = cv.to_dev(H, torch.float32)
+    Q = gptq_device(Wd, Hd, quantizer, act_order, damp, nb_ls_moves, min_block_size, num_blocks,
+                    check=not cv.is_tensor(W))
+    return cv.back(Q, W)
+
+
+def compute_gain(W, Q, H, candidates):
+    """Gain of moving each weight to its candidate (obq.py:220-231)."""
+    dt = cv.torch_float(np.result_type(*(cv.float_dtype_of(a) for a in (W, Q, H, candidates))))
+    out = ops.gain(cv.to_dev(W, dt), cv.to_dev(Q, dt), cv.to_dev(H, dt), cv.to_dev(candidates, dt))
+    return cv.back(out, W)
+
+
+class LocalSearchQuantizer:
+    """Best-first single-weight flips (obq.py:234-346).  State lives on the device; the
+    attributes the reference exposes (err, Q_up, Q_down, gain_up, gain_down) are derived from
+    the current Q on access.  ``quantize_local_search`` runs all moves in one kernel launch."""
+
+    def __init__(self, W, Q, H, quantizer):
+        assert W.ndim == 2
+        assert H.ndim == 2
+        assert H.shape[0] == H.shape[1]
+        assert H.shape[0] == W.shape[1]
+        assert Q.shape == W.shape
+        self._like = W
+        self._W = cv.to_dev(W, torch.float32)
+        self._Q = cv.to_dev(Q, torch.float32).clone()
+        self._H = cv.to_dev(H, torch.float32)
+        self.quantizer = quantizer
+
+    @property
+    def nchannels(self):
+        return self._W.shape[0]
+
+    @property
+    def W(self):
+        return cv.back(self._W, self._like)
+
+    @property
+    def Q(self):
+        return cv.back(self._Q, self._like)
+
+    @property
+    def H(self):
+        return cv.back(self._H, self._like)
+
+    @property
+    def err(self):
+        return cv.back(ops.hweighted_error(self._W, self._Q, self._H), self._like)
+
+    def _cand(self, mode):
+        return ops.round_to_codebook(self._Q, self.quantizer, mode)[0]
+
+    @property
+    def Q_up(self):
+        return cv.back(self._cand(ops.UP), self._like)
+
+    @property
+    def Q_down(self):
+        return cv.back(self._cand(ops.DOWN), self._like)
+
+    @property
+    def gain_up(self):
+        return cv.back(ops.gain(self._W, self._Q, self._H, self._cand(ops.UP)), self._like)
+
+    @property
+    def gain_down(self):
+        return cv.back(ops.gain(self._W, self._Q, self._H, self._cand(ops.DOWN)), self._like)
+
+    def do_move(self):
+        ops.local_search(self._W, self._Q, self._H, self.quantizer, 1)
+
+
+def quantize_local_search(W, Q, H, quantizer, nb_moves):
+    """nb_moves best-first flips per row (obq.py:349-358)."""
+    if nb_moves == 0:
+        return Q
+    Wd = cv.to_dev(W, torch.float32)
+    Qd = cv.to_dev(Q, torch.float32).clone()
+    Hd = cv.to_dev(H, torch.float32)
+    ops.local_search(Wd, Qd, Hd, quantizer, nb_moves)
+    return cv.back(Qd, W)

@@ -1,0 +1,381 @@
+"""Device-tensor front end of the C ABI.
+
+Every function here takes and returns ``torch`` CUDA tensors (contiguous, row
+major), enqueues kernels on the current CUDA stream and never synchronises.
+torch is used for device memory and streams only; all arithmetic of the hot
+path runs in ``libsleekit_b200.so``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SlkCodebook
+
+NEAREST, UP, DOWN = 0, 1, 2
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "sleekit_b200 runs its hot path on a CUDA device (B200, sm_100a) only; "
+            "no CUDA device is visible and there is no CPU fallback"
+        )
+
+
+def device():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+
+
+def _chk(t, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+# ---------------------------------------------------------------------------
+# codebooks
+# ---------------------------------------------------------------------------
+
+
+class DeviceCodebook:
+    """Host struct + the device tables it points to (kept alive together)."""
+
+    def __init__(self, kind, size, lo, hi, step, values=None, limits=None):
+        self.kind, self.size = int(kind), int(size)
+        self.lo, self.hi, self.step = float(lo), float(hi), float(step)
+        self.values, self.limits = values, limits
+        self.struct = SlkCodebook(self.kind, self.size, self.lo, self.hi, self.step,
+                                  values.data_ptr() if values is not None else None,
+                                  limits.data_ptr() if limits is not None else None)
+
+    @property
+    def ref(self):
+        return C.byref(self.struct)
+
+    @property
+    def index_dtype(self):
+        return torch.uint8 if self.size <= 2**8 else (torch.uint16 if self.size <= 2**16 else torch.uint32)
+
+
+def device_codebook(cb):
+    """Build (and cache on the object) the device view of a codebook-like object.
+
+    Accepted: anything exposing (codebook_size, min_val, max_val) -- UniformCodebook,
+    codebook.py:4-41 -- or (values, thresholds) -- Codebook, codebook.py:98-113.
+    Arbitrary Python callables cannot run on the device and are rejected."""
+    if isinstance(cb, DeviceCodebook):
+        return cb
+    dev = device()
+    cached = getattr(cb, "_slk_dev", None)
+    key = None
+    if hasattr(cb, "codebook_size") and hasattr(cb, "min_val"):
+        key = ("u", int(cb.codebook_size), float(cb.min_val), float(cb.max_val), dev.index)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        size = int(cb.codebook_size)
+        lo, hi = float(cb.min_val), float(cb.max_val)
+        d = DeviceCodebook(0, size, lo, hi, (hi - lo) / (size - 1))
+    elif hasattr(cb, "values") and hasattr(cb, "thresholds"):
+        vals = np.ascontiguousarray(cb.values, dtype=np.float32)
+        lims = np.ascontiguousarray(cb.thresholds, dtype=np.float32)
+        key = ("t", vals.tobytes(), lims.tobytes(), dev.index)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        tv = torch.from_numpy(vals.copy()).to(dev)
+        tl = torch.from_numpy(lims.copy()).to(dev) if lims.size else torch.zeros(1, dtype=torch.float32, device=dev)
+        d = DeviceCodebook(1, vals.size, float(vals[0]), float(vals[-1]), 0.0, tv, tl)
+    else:
+        raise TypeError(
+            "quantizer must be a UniformCodebook or Codebook (or expose their attributes); "
+            f"{type(cb).__name__} cannot be evaluated on the device and there is no host fallback"
+        )
+    try:
+        cb._slk_dev = (key, d)
+    except Exception:
+        pass
+    return d
+
+
+# ---------------------------------------------------------------------------
+# K4 rounding and the scaling primitives
+# ---------------------------------------------------------------------------
+
+
+def round_to_codebook(x, cb, mode=NEAREST, want_val=True, want_idx=False):
+    cb = device_codebook(cb)
+    _chk(x)
+    assert x.dtype in (torch.float32, torch.float64)
+    val = idx = None
+    if want_val:
+        vdt = torch.float32 if (cb.kind == 1 or x.dtype == torch.float32) else torch.float64
+        val = torch.empty(x.shape, dtype=vdt, device=x.device)
+    if want_idx:
+        idx = torch.empty(x.shape, dtype=cb.index_dtype, device=x.device)
+    fn = "slk_round_f32" if x.dtype == torch.float32 else "slk_round_f64"
+    _lib.call(fn, _ptr(x), x.numel(), cb.ref, mode, _ptr(val), _ptr(idx), _stream())
+    return val, idx
+
+
+def scale_axis(x, s, outer, length, inner, mode=0):
+    """out[o, a, i] = x[o, a, i] / s[a]  (mode 1: / (1 / s[a]))."""
+    _chk(x)
+    _chk(s, x.dtype)
+    assert s.numel() == length and x.numel() == outer * length * inner
+    out = torch.empty_like(x)
+    fn = "slk_scale_axis_f32" if x.dtype == torch.float32 else "slk_scale_axis_f64"
+    _lib.call(fn, _ptr(x), outer, length, inner, _ptr(s), mode, _ptr(out), _stream())
+    return out
+
+
+def scale_rows(w, s, mode=0):
+    return scale_axis(w, s, 1, w.shape[0], w[0].numel(), mode)
+
+
+def row_noclip_scale(w2d, cb_min, cb_max):
+    _chk(w2d)
+    out = torch.empty(w2d.shape[0], dtype=w2d.dtype, device=w2d.device)
+    fn = "slk_row_noclip_scale_f32" if w2d.dtype == torch.float32 else "slk_row_noclip_scale_f64"
+    _lib.call(fn, _ptr(w2d), w2d.shape[0], w2d.shape[1], float(cb_min), float(cb_max), _ptr(out), _stream())
+    return out
+
+
+def row_rms_scale(w2d):
+    _chk(w2d)
+    out = torch.empty(w2d.shape[0], dtype=w2d.dtype, device=w2d.device)
+    fn = "slk_row_rms_scale_f32" if w2d.dtype == torch.float32 else "slk_row_rms_scale_f64"
+    _lib.call(fn, _ptr(w2d), w2d.shape[0], w2d.shape[1], _ptr(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------
+# K5 / full-H scale search
+# ---------------------------------------------------------------------------
+
+
+def scale_search(w, cb, factors, hdiag=None, want_err=False, want_init=False):
+    cb = device_codebook(cb)
+    _chk(w, torch.float32)
+    _chk(factors, torch.float32)
+    r, n = w.shape
+    h_dtype = 0
+    if hdiag is not None:
+        _chk(hdiag)
+        assert hdiag.numel() == n
+        h_dtype = 1 if hdiag.dtype == torch.float32 else 2
+        assert hdiag.dtype in (torch.float32, torch.float64)
+    out = torch.empty(r, dtype=torch.float32, device=w.device)
+    err = torch.empty(r, dtype=torch.float32, device=w.device) if want_err else None
+    init = torch.empty(r, dtype=torch.float32, device=w.device) if want_init else None
+    _lib.call("slk_scale_search_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(hdiag), h_dtype,
+              _ptr(out), _ptr(err), _ptr(init), _stream())
+    return out, err, init
+
+
+def scale_search_fullh(w, cb, factors, h, want_err=False):
+    cb = device_codebook(cb)
+    _chk(w, torch.float32)
+    _chk(factors, torch.float32)
+    _chk(h)
+    r, n = w.shape
+    assert h.shape == (n, n)
+    h_dtype = 1 if h.dtype == torch.float32 else 2
+    lib = _lib.load()
+    nbytes = lib.slk_scale_search_fullh_ws_bytes(r, n, factors.numel(), h_dtype)
+    ws = _ws(nbytes, w.device)
+    out = torch.empty(r, dtype=torch.float32, device=w.device)
+    err = torch.empty(r, dtype=torch.float32, device=w.device) if want_err else None
+    _lib.call("slk_scale_search_fullh_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(h), h_dtype,
+              _ptr(ws), nbytes, _ptr(out), _ptr(err), _stream())
+    return out, err
+
+
+# ---------------------------------------------------------------------------
+# K6 errors, gains
+# ---------------------------------------------------------------------------
+
+
+def hweighted_error(w, q, h):
+    """((w - q) @ h * (w - q)).sum(-1); q may be None (w is the residual)."""
+    _chk(w)
+    _chk(h, w.dtype)
+    r, n = w.shape
+    if q is not None:
+        _chk(q, w.dtype)
+    lib = _lib.load()
+    esz = 4 if w.dtype == torch.float32 else 8
+    nbytes = lib.slk_hweighted_error_ws_bytes(r, n, esz)
+    ws = _ws(nbytes, w.device)
+    out = torch.empty(r, dtype=w.dtype, device=w.device)
+    fn = "slk_hweighted_error_f32" if esz == 4 else "slk_hweighted_error_f64"
+    _lib.call(fn, _ptr(w), _ptr(q), _ptr(h), r, n, _ptr(ws), nbytes, _ptr(out), _stream())
+    return out
+
+
+def mean(v):
+    _chk(v)
+    out = torch.empty((), dtype=v.dtype, device=v.device)
+    fn = "slk_mean_f32" if v.dtype == torch.float32 else "slk_mean_f64"
+    _lib.call(fn, _ptr(v), v.numel(), _ptr(out), _stream())
+    return out
+
+
+def gain(w, q, h, cand):
+    for t in (w, q, h, cand):
+        _chk(t, w.dtype)
+    r, n = w.shape
+    out = torch.empty_like(w)
+    fn = "slk_gain_f32" if w.dtype == torch.float32 else "slk_gain_f64"
+    _lib.call(fn, _ptr(w), _ptr(q), _ptr(h), _ptr(cand), r, n, _ptr(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------
+# K1 statistics
+# ---------------------------------------------------------------------------
+
+
+def hessian_accum(x, hess, mean_vec, keep, new_count):
+    """In place: mean = mean*keep + colsum(x)/new_count; hess = hess*keep + x^T x/new_count."""
+    _chk(x, torch.float32)
+    _chk(hess, torch.float32)
+    _chk(mean_vec, torch.float32)
+    S, n = x.shape
+    assert hess.shape == (n, n) and mean_vec.shape == (n,)
+    _lib.call("slk_hessian_accum_f32", _ptr(x), S, n, n, _ptr(hess), _ptr(mean_vec), float(keep), float(new_count),
+              _stream())
+
+
+def remove_input_bias(h, m):
+    _chk(h)
+    _chk(m, h.dtype)
+    out = torch.empty_like(h)
+    fn = "slk_remove_input_bias_f32" if h.dtype == torch.float32 else "slk_remove_input_bias_f64"
+    _lib.call(fn, _ptr(h), _ptr(m), h.shape[0], _ptr(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------
+# ordering
+# ---------------------------------------------------------------------------
+
+
+def damp_value(h, damp):
+    _chk(h, torch.float32)
+    out = torch.empty(1, dtype=torch.float32, device=h.device)
+    _lib.call("slk_damp_value_f32", _ptr(h), h.shape[0], float(damp), _ptr(out), _stream())
+    return out
+
+
+def col_resid_sums(w, cb, squared):
+    cb = device_codebook(cb)
+    _chk(w, torch.float32)
+    out = torch.empty(w.shape[1], dtype=torch.float32, device=w.device)
+    _lib.call("slk_col_resid_sums_f32", _ptr(w), w.shape[0], w.shape[1], cb.ref, 1 if squared else 0, _ptr(out),
+              _stream())
+    return out
+
+
+def order_keys(h, dampval=None, colsum=None):
+    _chk(h, torch.float32)
+    keys = torch.empty(h.shape[0], dtype=torch.float64, device=h.device)
+    _lib.call("slk_order_keys", _ptr(h), h.shape[0], _ptr(dampval), _ptr(colsum), _ptr(keys), _stream())
+    return keys
+
+
+def argsort(keys):
+    _chk(keys, torch.float64)
+    order = torch.empty(keys.numel(), dtype=torch.int64, device=keys.device)
+    _lib.call("slk_argsort_f64", _ptr(keys), keys.numel(), _ptr(order), _stream())
+    return order
+
+
+def permute_cols(src, idx, scatter=False):
+    _chk(src, torch.float32)
+    _chk(idx, torch.int64)
+    dst = torch.empty_like(src)
+    _lib.call("slk_permute_cols_f32", _ptr(src), src.shape[0], src.shape[1], _ptr(idx), 1 if scatter else 0,
+              _ptr(dst), _stream())
+    return dst
+
+
+# ---------------------------------------------------------------------------
+# K2 / K3 / K7
+# ---------------------------------------------------------------------------
+
+
+def hinv(h, order=None, dampval=None, want64=True, want32=True):
+    """Upper factor U of the inverse of (h + dampval*I)[order][:, order]; returns (u64, u32, info)."""
+    _chk(h)
+    n = h.shape[0]
+    lib = _lib.load()
+    nbytes = lib.slk_hinv_ws_bytes(n)
+    ws = _ws(nbytes, h.device)
+    u64 = torch.empty((n, n), dtype=torch.float64, device=h.device) if want64 else None
+    u32 = torch.empty((n, n), dtype=torch.float32, device=h.device) if want32 else None
+    info = torch.empty(1, dtype=torch.int32, device=h.device)
+    if h.dtype == torch.float32:
+        if order is not None:
+            _chk(order, torch.int64)
+        _lib.call("slk_hinv_from_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(u64), _ptr(u32),
+                  _ptr(info), _stream())
+    else:
+        assert h.dtype == torch.float64 and order is None and dampval is None
+        _lib.call("slk_hinv_from_f64", _ptr(h), n, _ptr(ws), nbytes, _ptr(u64), _ptr(u32), _ptr(info), _stream())
+    return u64, u32, info
+
+
+def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None):
+    """In place on q ([rows, n] scaled, permuted weights -> quantized values); returns (q, e)."""
+    cb = device_codebook(cb)
+    _chk(q, torch.float32)
+    _chk(u64, torch.float64)
+    _chk(u32, torch.float32)
+    if e is None:
+        e = torch.empty_like(q)
+    _lib.call("slk_gptq_sweep_f32", _ptr(q), _ptr(e), q.shape[0], q.shape[1], _ptr(u64), _ptr(u32), cb.ref,
+              int(leaf), int(fanout), _stream())
+    return q, e
+
+
+def local_search(w, q, h, cb, moves):
+    """In place on q (values on the codebook)."""
+    cb = device_codebook(cb)
+    _chk(w, torch.float32)
+    _chk(q, torch.float32)
+    _chk(h, torch.float32)
+    if moves <= 0:
+        return q
+    r, n = w.shape
+    lib = _lib.load()
+    nbytes = lib.slk_local_search_ws_bytes(r, n)
+    ws = _ws(nbytes, w.device)
+    _lib.call("slk_local_search_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(ws), nbytes, _stream())
+    return q
+
+
+def bias_delta(w, wq, mean_vec):
+    _chk(w, torch.float32)
+    _chk(wq, torch.float32)
+    _chk(mean_vec, torch.float32)
+    out = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+    _lib.call("slk_bias_delta_f32", _ptr(w), _ptr(wq), _ptr(mean_vec), w.shape[0], w.shape[1], _ptr(out), _stream())
+    return out

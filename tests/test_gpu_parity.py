@@ -1,0 +1,523 @@
+"""GPU parity tests: the CUDA path (through the public API, hence through the C ABI) against
+the committed golden vectors of the reference and against the numpy oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): rounding indices and values bit-exact; chosen scale-grid point
+equal; GPTQ layer error within 1e-3 relative of the reference with the code agreement reported;
+fp64 factor to fp64 round-off; local search identical from identical inputs."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sleekit_oracle as orc
+from sleekit_b200 import workloads as wl
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+UNI = [(2, 1), (3, 1), (4, 1), (8, 1), (16, 1), (9, 2), (9, 3)]
+
+
+@pytest.fixture(scope="module")
+def slk():
+    import sleekit_b200
+    from sleekit_b200 import codebook, obq, scaling
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.codebook, ns.obq, ns.scaling, ns.Sleekit = codebook, obq, scaling, sleekit_b200.Sleekit
+    return ns
+
+
+def agree(a, b):
+    return float((np.asarray(a) == np.asarray(b)).mean())
+
+
+def rel(a, b):
+    return abs(float(a) - float(b)) / abs(float(b))
+
+
+# ---------------------------------------------------------------------------
+# K4 rounding
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("c,hi", UNI)
+def test_uniform_rounding_bit_exact_vs_golden(slk, c, hi):
+    g = load_golden("rounding")
+    tag = f"u{c}_{hi}"
+    cfg = g[tag + "_cfg"]
+    lo_v, hi_v = (int(cfg[1]), int(cfg[2])) if hi != 3 else (float(cfg[1]), float(cfg[2]))
+    cb = slk.codebook.UniformCodebook(int(cfg[0]), lo_v, hi_v)
+    for suffix, x in (("", g[tag + "_x"]), ("64", g[tag + "_x"].astype(np.float64))):
+        for name, fn in (("idx", cb.quantize_index), ("val", cb.quantize_value), ("up", cb.quantize_up),
+                         ("down", cb.quantize_down)):
+            got, want = fn(x), g[f"{tag}_{name}{suffix}"]
+            assert got.dtype == want.dtype and got.shape == want.shape
+            np.testing.assert_array_equal(got, want, err_msg=f"{tag} {name}{suffix}")
+
+
+def test_table_rounding_bit_exact_vs_golden(slk):
+    g = load_golden("rounding")
+    cb = slk.codebook.Codebook(g["nf4_values"])
+    x = g["nf4_x"]
+    for name, fn in (("idx", cb.quantize_index), ("val", cb.quantize_value), ("up", cb.quantize_up),
+                     ("down", cb.quantize_down)):
+        got = fn(x)
+        assert got.dtype == g["nf4_" + name].dtype
+        np.testing.assert_array_equal(got, g["nf4_" + name])
+    # reference tests/test_codebook.py:6-32 (Python lists, saturation, N-D)
+    cb = slk.codebook.Codebook([-1.0, 2.0, 4.0, 8.0])
+    x = [-2.0, -1.0, 0.0, 0.9, 1.9, 2.9, 3.1, 5.9, 6.1, 9.0]
+    np.testing.assert_array_equal(cb.quantize_index(x), [0, 0, 0, 1, 1, 1, 2, 2, 3, 3])
+    np.testing.assert_array_equal(cb(x), [-1, -1, -1, 2, 2, 2, 4, 4, 8, 8])
+    np.testing.assert_array_equal(cb.quantize_up(x), [2, 2, 2, 4, 4, 4, 8, 8, 8, 8])
+    np.testing.assert_array_equal(cb.quantize_down(x), [-1, -1, -1, -1, -1, -1, 2, 2, 4, 4])
+    nd = np.random.default_rng(0).standard_normal((3, 4, 5))
+    assert cb(nd).shape == (3, 4, 5)
+
+
+def test_rounding_large_random_vs_oracle_and_idempotent(slk):
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal(2_000_003) * 0.7).astype(np.float32)  # odd length: vector body + scalar tail
+    for c in (3, 8, 16, 300):
+        cb = slk.codebook.UniformCodebook(c, -1, 1)
+        ref = orc.UniformGrid(c, -1, 1)
+        np.testing.assert_array_equal(cb.quantize_index(x), ref.index(x))
+        v = cb(x)
+        np.testing.assert_array_equal(v, ref.value(x))
+        np.testing.assert_array_equal(cb(v), v)  # q(q(x)) == q(x), tests/test_codebook.py:35-40
+        np.testing.assert_array_equal(cb.quantize_up(x), ref.up(x))
+        np.testing.assert_array_equal(cb.quantize_down(x), ref.down(x))
+    # unaligned views and empty input
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    np.testing.assert_array_equal(cb(x[1:1001]), orc.UniformGrid(8, -1, 1).value(x[1:1001].copy()))
+    assert cb(np.zeros((0, 5), np.float32)).shape == (0, 5)
+
+
+def test_uniform_equals_table_on_fp64_3d(slk):
+    # reference tests/test_codebook.py:43-57
+    data = np.random.default_rng(3).standard_normal((10, 20, 30))
+    ucb = slk.codebook.UniformCodebook(9, -2, 2)
+    tcb = slk.codebook.Codebook.uniform(9, -2, 2)
+    np.testing.assert_array_equal(ucb.quantize_index(data), tcb.quantize_index(data))
+    np.testing.assert_allclose(ucb(data), tcb(data))
+    np.testing.assert_allclose(ucb.quantize_up(data), tcb.quantize_up(data))
+    np.testing.assert_allclose(ucb.quantize_down(data), tcb.quantize_down(data))
+
+
+# ---------------------------------------------------------------------------
+# scales and the scale-grid search
+# ---------------------------------------------------------------------------
+
+
+def test_scales_vs_golden(slk):
+    g = load_golden("scales")
+    W, H = g["W"], g["H"]
+    S = slk.scaling
+    for c in (3, 8):
+        cb = slk.codebook.UniformCodebook(c, -1, 1)
+        np.testing.assert_array_equal(S.compute_non_saturating_scaling(W, cb, 0), g[f"max_c{c}"])
+        np.testing.assert_array_equal(S.compute_min_mse_scaling(W, cb, 0), g[f"mse_c{c}"])
+        np.testing.assert_array_equal(S.compute_min_mse_scaling(W, cb, 0, H=H.diagonal()), g[f"diag_c{c}"])
+        assert agree(S.compute_min_mse_scaling(W, cb, 0, H=H), g[f"full_c{c}"]) >= 0.9
+        np.testing.assert_array_equal(S.compute_scaling(W, cb, H, mode="diag5"), g[f"diag5_c{c}"])
+        assert agree(S.compute_scaling(W, cb, H, mode="hessian2"), g[f"hess2_c{c}"]) >= 0.9
+        np.testing.assert_array_equal(S.compute_min_mse_scaling(W, cb, 1, grid_size=17, min_factor=0.2),
+                                      g[f"axis1_c{c}"])
+    np.testing.assert_allclose(S.compute_norm_scaling(W, 0), g["norm0"], rtol=2e-7)
+    np.testing.assert_allclose(S.compute_norm_scaling(W, 1), g["norm1"], rtol=2e-7)
+    np.testing.assert_array_equal(
+        S.compute_non_saturating_scaling(W, slk.codebook.Codebook([-1.0, 0.0, 10.0, 20.0]), 0), g["max_tab0"])
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    np.testing.assert_array_equal(S.quantize_with_scaling(W, g["diag_c8"], cb), g["qws_plain"])
+    np.testing.assert_array_equal(S.apply_scaling(W, g["diag_c8"], 0), g["apply"])
+
+
+def test_scale_known_answers(slk):
+    # reference tests/test_scaling.py:16-41, 56-72
+    S = slk.scaling
+    data = np.array([[0.0, 10.0], [5.0, 5.0]], dtype=np.float32)
+    sc = S.compute_norm_scaling(data, 0)
+    np.testing.assert_allclose(sc, [10.0 / np.sqrt(2), 5.0], rtol=1e-6)
+    np.testing.assert_allclose(S.apply_scaling(data, sc, 0), [[0.0, np.sqrt(2)], [1.0, 1.0]], rtol=1e-6)
+    np.testing.assert_allclose(S.apply_scaling(S.apply_scaling(data, sc, 0), 1 / sc, 0), data, rtol=1e-6)
+    sc = S.compute_norm_scaling(data, 1)
+    np.testing.assert_allclose(sc, [5.0 / np.sqrt(2), np.sqrt(125 / 2)], rtol=1e-6)
+    np.testing.assert_allclose(S.apply_scaling(data, sc, 1),
+                               [[0.0, 10.0 / np.sqrt(125 / 2)], [np.sqrt(2), 5.0 / np.sqrt(125 / 2)]], rtol=1e-6)
+    data = np.array(
+        [[0.0, 10.0, -20.0, 15.0], [5.0, 5.0, 10.0, -10.0], [1.0, 2.0, -4.0, 3.0], [0.0, 0.0, 0.0, 0.0],
+         [1.0, 10.0, 100.0, 1000.0], [-1.0, 10.0, 100.0, 1000.0]], dtype=np.float32)
+    cb = slk.codebook.Codebook([-1.0, 0.0, 10.0, 20.0])
+    np.testing.assert_allclose(S.compute_non_saturating_scaling(data, cb, 0), [20, 10, 4, 1e-16, 50, 50])
+    np.testing.assert_allclose(S.compute_non_saturating_scaling(data, cb, 1), [1, 0.5, 20, 50])
+    nd = np.random.default_rng(1).standard_normal((10, 20, 30, 40)).astype(np.float32)
+    ucb = slk.codebook.UniformCodebook(9, -2, 2)
+    for ax, ln in enumerate((10, 20, 30, 40)):
+        assert len(S.compute_norm_scaling(nd, ax)) == ln
+        assert len(S.compute_non_saturating_scaling(nd, ucb, ax)) == ln
+        np.testing.assert_array_equal(S.compute_non_saturating_scaling(nd, ucb, ax),
+                                      orc.no_clip_scale(nd, orc.UniformGrid(9, -2, 2), ax))
+
+
+@pytest.mark.parametrize("r,n,c", [(96, 768, 8), (64, 3072, 3), (33, 1000, 4)])
+def test_scale_search_selects_reference_grid_point(slk, r, n, c):
+    W, H, m = wl.synthetic_layer(r, n, 5, samples=256)
+    cb = slk.codebook.UniformCodebook(c, -1, 1)
+    grid = orc.UniformGrid(c, -1, 1)
+    for Harg in (None, H.diagonal().copy()):
+        got = slk.scaling.compute_min_mse_scaling(W, cb, 0, H=Harg)
+        want = orc.search_scale(W, grid, 0, H=Harg)
+        assert got.dtype == np.float32
+        assert agree(got, want) >= 0.99, (r, n, c, Harg is None, agree(got, want))
+    # fp64 diagonal (reference tests/test_scaling.py:97-105): errors accumulate in fp64
+    h64 = np.random.default_rng(2).random(n)
+    assert agree(slk.scaling.compute_min_mse_scaling(W, cb, 0, H=h64), orc.search_scale(W, grid, 0, H=h64)) >= 0.99
+
+
+def test_full_h_scale_search_vs_oracle(slk):
+    W, H, m = wl.synthetic_layer(48, 256, 9, samples=512)
+    cb = slk.codebook.UniformCodebook(3, -1, 1)
+    got = slk.scaling.compute_min_mse_scaling(W, cb, 0, H=H)
+    want = orc.search_scale(W, orc.UniformGrid(3, -1, 1), 0, H=H)
+    assert agree(got, want) >= 0.9
+    # chosen scales must be (near-)optimal under the oracle's own error
+    eg = orc.weighted_sq_error(H, orc.quantize_scaled(W, got, orc.UniformGrid(3, -1, 1)) - W)
+    ew = orc.weighted_sq_error(H, orc.quantize_scaled(W, want, orc.UniformGrid(3, -1, 1)) - W)
+    assert np.all(eg <= ew * (1 + 1e-4))
+    H64 = orc.strip_input_bias(H, m).astype(np.float64)
+    got = slk.scaling.compute_min_mse_scaling(W, cb, 0, H=H64)
+    want = orc.search_scale(W, orc.UniformGrid(3, -1, 1), 0, H=H64)
+    assert agree(got, want) >= 0.9
+
+
+# ---------------------------------------------------------------------------
+# K2 factor, ordering
+# ---------------------------------------------------------------------------
+
+
+def test_factor_vs_golden_and_identities(slk):
+    g = load_golden("sweep")
+    U = slk.obq.compute_hessian_chol(g["Hd"])
+    assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"]
+    np.testing.assert_allclose(U, g["U"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(np.tril(U, -1), 0)
+    np.testing.assert_array_equal(slk.obq.remove_input_bias(g["H"], g["mean"]), g["Hc"])
+    # reference tests/test_obq.py:21-32
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((4, 6)).astype(np.float32)
+    H = A @ A.T + 1e-6 * np.eye(4)
+    U = slk.obq.compute_hessian_chol(H)
+    np.testing.assert_allclose(U, np.linalg.cholesky(np.linalg.inv(H)).T)
+    np.testing.assert_allclose(np.linalg.inv(U.T @ U), H)
+
+
+@pytest.mark.parametrize("n", [50, 64, 200, 768, 1000])
+def test_factor_vs_oracle(slk, n):
+    _, H, _ = wl.synthetic_layer(4, n, 11, samples=max(2 * n, 256))
+    Hd = H + 0.01 * H.diagonal().mean() * np.eye(n)
+    U = slk.obq.compute_hessian_chol(Hd)
+    want = orc.inverse_upper_factor(Hd)
+    scale = np.abs(want).max()
+    assert np.abs(U - want).max() <= 1e-9 * scale
+    np.testing.assert_allclose(U.T @ U @ Hd, np.eye(n), atol=1e-7)
+
+
+def test_factor_not_positive_definite_raises(slk):
+    H = np.eye(70)
+    H[40, 40] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        slk.obq.compute_hessian_chol(H)
+    with pytest.raises(np.linalg.LinAlgError):
+        W = np.ones((4, 70), np.float32)
+        slk.obq.quantize_opt(W, H.astype(np.float32), slk.codebook.UniformCodebook(4, -1, 1), damp=0.0)
+
+
+def test_ordering_vs_golden(slk):
+    g = load_golden("sweep")
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    for rule in ("diag", "none", "err", "sqerr"):
+        got = slk.obq.compute_hessian_order(g["Ws"], g["Hd"], cb, rule)
+        assert got.dtype == np.int64
+        np.testing.assert_array_equal(got, g[f"order_{rule}"], err_msg=rule)
+    with pytest.raises(RuntimeError):
+        slk.obq.compute_hessian_order(g["Ws"], g["Hd"], cb, "bogus")
+    for rule in ("inv_diag", "combined_diag"):
+        np.testing.assert_array_equal(slk.obq.compute_hessian_order(g["Ws"], g["Hd"], cb, rule),
+                                      orc.column_order(g["Ws"], g["Hd"], orc.UniformGrid(8, -1, 1), rule))
+
+
+# ---------------------------------------------------------------------------
+# K3 sweep / GPTQ
+# ---------------------------------------------------------------------------
+
+
+def test_sweep_with_reference_factor_vs_golden(slk):
+    g = load_golden("sweep")
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    Q = g["Ws"].copy()
+    E = np.zeros_like(Q)
+    slk.obq._quantize_opt_block(Q, E, g["U"], cb, 32, 8)
+    assert agree(Q, g["sweep_Q"]) >= 0.999
+    np.testing.assert_allclose(E, g["sweep_E"], rtol=2e-3, atol=1e-5)
+    # a single 32-wide leaf has no GEMM in it: bit-exact with the reference arithmetic
+    Q1 = g["Ws"][:, :32].copy()
+    E1 = np.zeros_like(Q1)
+    U1 = np.ascontiguousarray(g["U"][:32, :32])
+    slk.obq._quantize_opt_core(Q1, E1, U1, cb)
+    Qr = g["Ws"][:, :32].copy()
+    Er = np.zeros_like(Qr)
+    orc.sweep_in_place(Qr, Er, U1, orc.UniformGrid(8, -1, 1))
+    np.testing.assert_array_equal(Q1, Qr)
+    np.testing.assert_array_equal(E1, Er)
+
+
+def test_gptq_vs_golden(slk):
+    g = load_golden("sweep")
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    grid = orc.UniformGrid(8, -1, 1)
+    Ws, H = g["Ws"], g["H"]
+    cases = [(dict(act_order=r, damp=0.01), f"gptq_{r}") for r in ("diag", "none", "err", "sqerr")]
+    cases += [(dict(act_order="sqerr", damp=0.03), "gptq_damp3"),
+              (dict(act_order="diag", damp=0.01, nb_ls_moves=20), "gptq_ls20")]
+    for kw, key in cases:
+        got = slk.obq.quantize_opt(Ws, H, cb, **kw)
+        assert got.dtype == np.float32
+        np.testing.assert_array_equal(grid.value(got), got)  # every output is a codeword
+        a = agree(got, g[key])
+        e_got, e_ref = orc.mean_error(Ws, got, H), orc.mean_error(Ws, g[key], H)
+        assert a >= 0.99 and rel(e_got, e_ref) <= 1e-3, (key, a, e_got, e_ref)
+    got = slk.scaling.quantize_with_scaling(g["W"], g["scale"], cb, H=H, act_order="diag", damp=0.01)
+    assert agree(got, g["qws_gptq"]) >= 0.99
+    np.testing.assert_allclose(slk.obq.channelwise_error(g["W"], g["qws_gptq"], H), g["err_rows"], rtol=1e-4)
+    e = slk.obq.quantization_error(g["W"], g["qws_gptq"], H)
+    assert isinstance(e, np.float32) and rel(e, g["err_mean"]) < 1e-5
+    cb4 = slk.codebook.UniformCodebook(4, -1, 1)
+    got = slk.scaling.quantize_with_scaling(g["W2"], g["scale2"], cb4, H=g["H2"])  # ragged 200-column recursion
+    assert agree(got, g["qws2"]) >= 0.99
+    got = slk.scaling.quantize_with_scaling(g["W2"], g["scale2"], cb4, H=g["H2"], nb_ls_moves=15)
+    assert agree(got, g["qws2_ls"]) >= 0.99
+
+
+@pytest.mark.parametrize("r,n,c,rule,damp", [(768, 768, 8, "diag", 0.01), (128, 3072, 8, "diag", 0.01),
+                                               (200, 1024, 3, "sqerr", 0.03), (64, 1100, 4, "err", 0.01)])
+def test_gptq_stagewise_vs_oracle(slk, r, n, c, rule, damp):
+    """Same W, H and scales into both implementations (BASELINE config 1 is the first case)."""
+    W, H, m = wl.synthetic_layer(r, n, 0)
+    cb, grid = slk.codebook.UniformCodebook(c, -1, 1), orc.UniformGrid(c, -1, 1)
+    sc = orc.search_scale(W, grid, 0, H=H.diagonal())
+    want = orc.quantize_scaled(W, sc, grid, H=H, rule=rule, damp=damp)
+    got = slk.scaling.quantize_with_scaling(W, sc, cb, H=H, act_order=rule, damp=damp)
+    codes_w = grid.index(orc.divide_rows(want, sc, 0))
+    codes_g = grid.index(orc.divide_rows(got, sc, 0))
+    a = agree(codes_g, codes_w)
+    e_got, e_ref = orc.mean_error(W, got, H), orc.mean_error(W, want, H)
+    print(f"[{r}x{n} c={c} {rule}] code agreement {a:.6f}  layer error {e_got:.6e} vs {e_ref:.6e}")
+    assert a >= 0.999
+    assert rel(e_got, e_ref) <= 1e-3
+    # GPTQ must beat plain rounding at the same scales (reference tests/test_obq.py:35-54)
+    assert e_got <= orc.mean_error(W, orc.quantize_scaled(W, sc, grid), H)
+
+
+# ---------------------------------------------------------------------------
+# K7 local search, gains
+# ---------------------------------------------------------------------------
+
+
+def test_local_search_vs_golden(slk):
+    g = load_golden("local_search")
+    cb = slk.codebook.UniformCodebook(4, -1, 1)
+    Ws, H, Q0 = g["Ws"], g["H"], g["Q0"]
+    np.testing.assert_allclose(slk.obq.compute_gain(Ws, Q0, H, cb.quantize_up(Q0)), g["gain_up"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(slk.obq.compute_gain(Ws, Q0, H, cb.quantize_down(Q0)), g["gain_down"], rtol=1e-4,
+                               atol=1e-6)
+    for k in (1, 5, 30):
+        got = slk.obq.quantize_local_search(Ws, Q0, H, cb, k)
+        np.testing.assert_array_equal(got, g[f"ls_{k}"], err_msg=f"{k} moves")
+    assert slk.obq.quantize_local_search(Ws, Q0, H, cb, 0) is Q0
+    ls = slk.obq.LocalSearchQuantizer(Ws, Q0, H, cb)
+    for _ in range(5):
+        ls.do_move()
+    np.testing.assert_array_equal(ls.Q, g["ls_5"])
+    np.testing.assert_allclose(ls.err, orc.rowwise_error(Ws, g["ls_5"], H), rtol=1e-4)
+
+
+@pytest.mark.parametrize("r,n,c,moves", [(64, 1024, 4, 40), (16, 4096, 3, 25)])
+def test_local_search_vs_oracle(slk, r, n, c, moves):
+    W, H, m = wl.synthetic_layer(r, n, 3, samples=512)
+    grid, cb = orc.UniformGrid(c, -1, 1), slk.codebook.UniformCodebook(c, -1, 1)
+    sc = orc.no_clip_scale(W, grid, 0) * np.float32(0.5)
+    Ws = orc.divide_rows(W, sc, 0)
+    Q0 = grid.value(Ws)
+    want = orc.local_search(Ws, Q0, H, grid, moves)
+    got = slk.obq.quantize_local_search(Ws, Q0, H, cb, moves)
+    a = agree(got, want)
+    e_got, e_ref = orc.mean_error(Ws, got, H), orc.mean_error(Ws, want, H)
+    print(f"[local search {r}x{n} c={c} moves={moves}] agreement {a:.6f} error {e_got:.6e} vs {e_ref:.6e}")
+    assert a >= 0.9999 and rel(e_got, e_ref) <= 1e-3
+    assert e_got < orc.mean_error(Ws, Q0, H)
+
+
+def test_gain_fp64_vs_exhaustive(slk):
+    # reference tests/test_obq.py:112-140
+    rng = np.random.default_rng(8)
+    W = rng.standard_normal((10, 16))
+    A = rng.standard_normal((16, 10)).astype(np.float32)
+    H = (A @ A.T).astype(np.float64)
+    Q = np.round(W)
+    C = Q + np.square(rng.standard_normal((10, 16)))
+    base = orc.rowwise_error(W, Q, H)
+    want = np.zeros_like(Q)
+    for i in range(16):
+        cur = Q.copy()
+        cur[:, i] = C[:, i]
+        want[:, i] = base - orc.rowwise_error(W, cur, H)
+    got = slk.obq.compute_gain(W, Q, H, C)
+    assert got.dtype == np.float64
+    np.testing.assert_allclose(got, want)
+    np.testing.assert_allclose(slk.obq.channelwise_error(W, Q, H), base)
+
+
+# ---------------------------------------------------------------------------
+# obq-aware scaling, statistics, presets
+# ---------------------------------------------------------------------------
+
+
+def test_obq_scaling_vs_golden(slk):
+    g = load_golden("obq_scaling")
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    a = slk.scaling.compute_obq_scaling(g["W"], cb, 0, H=g["H"], grid_size=12, min_factor=0.3)
+    assert agree(a, g["sc_obq"]) >= 0.85
+    b = slk.scaling.compute_obq_scaling(g["W"], cb, 0, H=g["H"], grid_size=12, min_factor=0.3, act_order="sqerr",
+                                        damp=0.03)
+    assert agree(b, g["sc_obq_sqerr"]) >= 0.85
+
+
+def test_scaling_quality_ordering(slk):
+    # reference tests/test_scaling.py:130-149
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((20, 100)).astype(np.float32)
+    cb = slk.codebook.UniformCodebook(9, -3, 3)
+    A = rng.standard_normal((100, 10)).astype(np.float32)
+    H = (A @ A.T).astype(np.float64)
+    H = H + 1e-6 * np.linalg.norm(H, ord=2, axis=1) * np.eye(100)
+    S, O = slk.scaling, slk.obq
+    sc = {k: S.compute_min_mse_scaling(data, cb, 0, H=h) for k, h in
+          (("base", None), ("diag", H.diagonal()), ("hess", H))}
+    sc["obq"] = S.compute_obq_scaling(data, cb, 0, H=H)
+    err = {k: O.quantization_error(S.quantize_with_scaling(data, sc[k], cb), data, H) for k in ("base", "diag", "hess")}
+    err["obq"] = O.quantization_error(S.quantize_with_scaling(data, sc["obq"], cb, H=H), data, H)
+    assert err["hess"] <= err["base"] and err["hess"] <= err["diag"] and err["obq"] <= err["hess"]
+    for mode in ("norm", "max", "mse", "diag", "hessian", "diag1", "hessian1", "diag1.8", "hessian1.8"):
+        assert len(S.compute_scaling(data, cb, H, mode=mode)) == 20  # tests/test_scaling.py:152-165
+    with pytest.raises(RuntimeError):
+        S.compute_scaling(data, cb, H, mode="nope")
+
+
+def test_statistics_vs_golden(slk):
+    g = load_golden("statistics")
+    lin = torch.nn.Linear(48, 20)
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(g["W"]))
+        lin.bias.copy_(torch.from_numpy(g["b"]))
+    st = slk.Sleekit(lin)
+    st.add_batch(torch.from_numpy(g["X1"]))
+    assert st.count == int(g["count1"])
+    np.testing.assert_allclose(st.mean.cpu().numpy(), g["mean1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st.hessian.cpu().numpy(), g["hess1"], rtol=1e-5, atol=1e-5)
+    st.add_batch(torch.from_numpy(g["X2"]))
+    assert st.count == int(g["count2"])
+    np.testing.assert_allclose(st.mean.cpu().numpy(), g["mean2"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st.hessian.cpu().numpy(), g["hess2"], rtol=1e-5, atol=1e-5)
+    for name in ("basic", "light", "heavy"):
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(g["W"]))
+            lin.bias.copy_(torch.from_numpy(g["b"]))
+        # isolate the stage: start from the reference's own statistics
+        st.hessian.copy_(torch.from_numpy(g["hess2"]))
+        st.mean.copy_(torch.from_numpy(g["mean2"]))
+        getattr(st, {"basic": "quantize_basic", "light": "quantize_sleekit_light", "heavy": "quantize_sleekit_heavy"}[name])(3)
+        a = agree(lin.weight.detach().numpy(), g[f"{name}_W"])
+        assert a >= 0.98, (name, a)
+        np.testing.assert_allclose(lin.bias.detach().numpy(), g[f"{name}_b"], rtol=2e-2, atol=2e-3)
+    # sample counting through conv layers (reference tests/test_statistics.py:7-46)
+    conv = torch.nn.Conv2d(3, 4, 3, padding=1)
+    sc = slk.Sleekit(conv)
+    sc.add_batch(torch.randn(2, 3, 8, 8))
+    assert sc.count == 2 * 8 * 8 and sc.hessian.shape == (27, 27)
+    c1 = torch.nn.Conv1d(3, 4, 3)
+    s1 = slk.Sleekit(c1)
+    s1.add_batch(torch.randn(2, 3, 10))
+    assert s1.count == 2 * 8 and s1.hessian.shape == (9, 9)
+
+
+def test_hessian_accumulation_vs_numpy(slk):
+    from sleekit_b200 import ops
+
+    rng = np.random.default_rng(12)
+    for S, n in ((2048, 768), (300, 130), (17, 5)):
+        X = (rng.standard_normal((S, n)) * np.exp(rng.standard_normal(n)) + 0.5).astype(np.float32)
+        ref = orc.RunningStats(n)
+        ref.add_rows(X[: S // 2])
+        ref.add_rows(X[S // 2:])
+        H = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+        mean = torch.zeros(n, dtype=torch.float32, device="cuda")
+        cnt = 0
+        for part in (X[: S // 2], X[S // 2:]):
+            xs = torch.from_numpy(part).cuda()
+            keep = cnt / (cnt + part.shape[0])
+            cnt += part.shape[0]
+            ops.hessian_accum(xs, H, mean, keep, cnt)
+        Hn = H.cpu().numpy()
+        assert np.abs(Hn - ref.hessian).max() <= 2e-6 * np.abs(ref.hessian).max()
+        np.testing.assert_allclose(mean.cpu().numpy(), ref.mean, rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(Hn, Hn.T)  # symmetric to the bit: both halves use the same sums
+
+
+# ---------------------------------------------------------------------------
+# device-resident pass-through and edge cases
+# ---------------------------------------------------------------------------
+
+
+def test_device_tensors_pass_through(slk):
+    W, H, m = wl.synthetic_layer(64, 256, 2, samples=512)
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    Wd, Hd = torch.from_numpy(W).cuda(), torch.from_numpy(H).cuda()
+    sc = slk.scaling.compute_min_mse_scaling(Wd, cb, 0, H=Hd.diagonal().contiguous())
+    assert isinstance(sc, torch.Tensor) and sc.is_cuda
+    out = slk.scaling.quantize_with_scaling(Wd, sc, cb, H=Hd)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    host = slk.scaling.quantize_with_scaling(W, sc.cpu().numpy(), cb, H=H)
+    np.testing.assert_array_equal(out.cpu().numpy(), host)
+    e = slk.obq.quantization_error(Wd, out, Hd)
+    assert isinstance(e, torch.Tensor) and rel(e.item(), slk.obq.quantization_error(W, host, H)) < 1e-6
+
+
+def test_edge_cases(slk):
+    cb = slk.codebook.UniformCodebook(4, -1, 1)
+    W = np.zeros((3, 40), np.float32)
+    W[1, :] = np.linspace(-1, 1, 40)
+    sc = slk.scaling.compute_min_mse_scaling(W, cb)
+    assert sc[0] == np.float32(1e-16) * np.float32(0.05) and sc[1] > 0  # all-zero rows hit the floor
+    np.testing.assert_array_equal(sc, orc.search_scale(W, orc.UniformGrid(4, -1, 1)))
+    # dead input column: remove_dead_values then GPTQ still works
+    Wl, H, m = wl.synthetic_layer(8, 48, 1, samples=128)
+    H[:, 7] = 0
+    H[7, :] = 0
+    H2, W2 = H.copy(), Wl.copy()
+    slk.obq.remove_dead_values(H2, W2)
+    Hr, Wr = H.copy(), Wl.copy()
+    orc.patch_dead_inputs(Hr, Wr)
+    np.testing.assert_array_equal(H2, Hr)
+    np.testing.assert_array_equal(W2, Wr)
+    q = slk.obq.quantize_opt(W2, H2, slk.codebook.UniformCodebook(8, -1, 1))
+    assert np.isfinite(q).all()
+    # single row, single leaf narrower than a warp
+    q = slk.obq.quantize_opt(W2[:1, :5].copy(), np.ascontiguousarray(H2[:5, :5]), slk.codebook.UniformCodebook(8, -1, 1))
+    want = orc.gptq(W2[:1, :5].copy(), np.ascontiguousarray(H2[:5, :5]), orc.UniformGrid(8, -1, 1))
+    np.testing.assert_array_equal(q, want)
+    with pytest.raises(TypeError):
+        slk.obq.quantize_opt(W2, H2, lambda x: np.round(x))

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import sleekit_oracle as orc
+from sleekit_b200 import workloads as wl
 from tests.conftest import load_golden
 
 UNI = [(2, 1), (3, 1), (4, 1), (8, 1), (16, 1), (9, 2), (9, 3)]
@@ -176,9 +177,9 @@ def test_statistics_match_reference():
 
 
 def test_synthetic_layer_is_deterministic():
-    a = orc.synthetic_layer(8, 64, 3, samples=128)
-    b = orc.synthetic_layer(8, 64, 3, samples=128)
+    a = wl.synthetic_layer(8, 64, 3, samples=128)
+    b = wl.synthetic_layer(8, 64, 3, samples=128)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x, y)
-    assert len(orc.layer_shapes("opt-125m")) == 72
-    assert sum(r * n for r, n in orc.layer_shapes("opt-125m")) == 84934656
+    assert len(wl.layer_shapes("opt-125m")) == 72
+    assert sum(r * n for r, n in wl.layer_shapes("opt-125m")) == 84934656
