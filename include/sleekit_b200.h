@@ -53,6 +53,8 @@ typedef struct slk_codebook {
 
 int slk_abi_version(void);
 const char* slk_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t slk_launch_count(void);
 /* Fills sm_count / compute capability of the current device. */
 int slk_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 

@@ -40,6 +40,7 @@ _CB = C.POINTER(SlkCodebook)
 SIGNATURES = {
     "slk_abi_version": (_INT, []),
     "slk_last_error": (C.c_char_p, []),
+    "slk_launch_count": (_I64, []),
     "slk_device_info": (_INT, [C.POINTER(_INT)] * 3),
     "slk_round_f32": (_INT, [_P, _I64, _CB, _INT, _P, _P, _P]),
     "slk_round_f64": (_INT, [_P, _I64, _CB, _INT, _P, _P, _P]),

@@ -13,6 +13,7 @@
 namespace slk {
 
 void set_error(const char* fmt, ...);
+void note_launch();  // bumps the process-wide kernel-launch counter (slk_launch_count)
 
 #define SLK_REQUIRE(cond, ...)        \
   do {                                \
@@ -34,6 +35,7 @@ void set_error(const char* fmt, ...);
 
 #define SLK_LAUNCH_CHECK()                                                         \
   do {                                                                             \
+    ::slk::note_launch();                                                          \
     cudaError_t e__ = cudaGetLastError();                                          \
     if (e__ != cudaSuccess) {                                                      \
       ::slk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),\

@@ -17,6 +17,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void note_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -425,6 +428,7 @@ extern "C" {
 
 int slk_abi_version(void) { return SLK_ABI_VERSION; }
 const char* slk_last_error(void) { return slk::g_err; }
+int64_t slk_launch_count(void) { return (int64_t)__atomic_load_n(&slk::g_launches, __ATOMIC_RELAXED); }
 
 int slk_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) {
   int dev = 0;

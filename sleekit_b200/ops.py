@@ -18,6 +18,39 @@ from ._lib import SlkCodebook
 
 NEAREST, UP, DOWN = 0, 1, 2
 
+# Optional per-call device timing (bench.py): set PROFILE to a dict and every wrapped entry
+# point records a CUDA event pair on the stream it launches on.  None = no overhead.
+PROFILE = None
+
+
+def _timed(name):
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            if PROFILE is None:
+                return fn(*a, **k)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            PROFILE.setdefault(name, []).append((s, e))
+            return out
+
+        return wrapper
+
+    return deco
+
+
+def profile_totals_ms(profile):
+    """{name: (total ms, calls)} after a synchronize."""
+    return {k: (sum(s.elapsed_time(e) for s, e in v), len(v)) for k, v in profile.items()}
+
+
+def launch_count():
+    return int(_lib.load().slk_launch_count())
+
 
 def require_cuda():
     if not torch.cuda.is_available():
@@ -120,6 +153,7 @@ def device_codebook(cb):
 # ---------------------------------------------------------------------------
 
 
+@_timed("round_to_codebook")
 def round_to_codebook(x, cb, mode=NEAREST, want_val=True, want_idx=False):
     cb = device_codebook(cb)
     _chk(x)
@@ -135,6 +169,7 @@ def round_to_codebook(x, cb, mode=NEAREST, want_val=True, want_idx=False):
     return val, idx
 
 
+@_timed("scale_axis")
 def scale_axis(x, s, outer, length, inner, mode=0):
     """out[o, a, i] = x[o, a, i] / s[a]  (mode 1: / (1 / s[a]))."""
     _chk(x)
@@ -150,6 +185,7 @@ def scale_rows(w, s, mode=0):
     return scale_axis(w, s, 1, w.shape[0], w[0].numel(), mode)
 
 
+@_timed("row_noclip_scale")
 def row_noclip_scale(w2d, cb_min, cb_max):
     _chk(w2d)
     out = torch.empty(w2d.shape[0], dtype=w2d.dtype, device=w2d.device)
@@ -171,6 +207,7 @@ def row_rms_scale(w2d):
 # ---------------------------------------------------------------------------
 
 
+@_timed("scale_search")
 def scale_search(w, cb, factors, hdiag=None, want_err=False, want_init=False):
     cb = device_codebook(cb)
     _chk(w, torch.float32)
@@ -190,6 +227,7 @@ def scale_search(w, cb, factors, hdiag=None, want_err=False, want_init=False):
     return out, err, init
 
 
+@_timed("scale_search_fullh")
 def scale_search_fullh(w, cb, factors, h, want_err=False):
     cb = device_codebook(cb)
     _chk(w, torch.float32)
@@ -213,6 +251,7 @@ def scale_search_fullh(w, cb, factors, h, want_err=False):
 # ---------------------------------------------------------------------------
 
 
+@_timed("hweighted_error")
 def hweighted_error(w, q, h):
     """((w - q) @ h * (w - q)).sum(-1); q may be None (w is the residual)."""
     _chk(w)
@@ -253,6 +292,7 @@ def gain(w, q, h, cand):
 # ---------------------------------------------------------------------------
 
 
+@_timed("hessian_accum")
 def hessian_accum(x, hess, mean_vec, keep, new_count):
     """In place: mean = mean*keep + colsum(x)/new_count; hess = hess*keep + x^T x/new_count."""
     _chk(x, torch.float32)
@@ -264,6 +304,7 @@ def hessian_accum(x, hess, mean_vec, keep, new_count):
               _stream())
 
 
+@_timed("remove_input_bias")
 def remove_input_bias(h, m):
     _chk(h)
     _chk(m, h.dtype)
@@ -285,6 +326,7 @@ def damp_value(h, damp):
     return out
 
 
+@_timed("col_resid_sums")
 def col_resid_sums(w, cb, squared):
     cb = device_codebook(cb)
     _chk(w, torch.float32)
@@ -301,6 +343,7 @@ def order_keys(h, dampval=None, colsum=None):
     return keys
 
 
+@_timed("argsort")
 def argsort(keys):
     _chk(keys, torch.float64)
     order = torch.empty(keys.numel(), dtype=torch.int64, device=keys.device)
@@ -308,6 +351,7 @@ def argsort(keys):
     return order
 
 
+@_timed("permute_cols")
 def permute_cols(src, idx, scatter=False):
     _chk(src, torch.float32)
     _chk(idx, torch.int64)
@@ -322,6 +366,7 @@ def permute_cols(src, idx, scatter=False):
 # ---------------------------------------------------------------------------
 
 
+@_timed("hinv")
 def hinv(h, order=None, dampval=None, want64=True, want32=True):
     """Upper factor U of the inverse of (h + dampval*I)[order][:, order]; returns (u64, u32, info)."""
     _chk(h)
@@ -343,6 +388,7 @@ def hinv(h, order=None, dampval=None, want64=True, want32=True):
     return u64, u32, info
 
 
+@_timed("gptq_sweep")
 def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None):
     """In place on q ([rows, n] scaled, permuted weights -> quantized values); returns (q, e)."""
     cb = device_codebook(cb)
@@ -356,6 +402,7 @@ def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None):
     return q, e
 
 
+@_timed("local_search")
 def local_search(w, q, h, cb, moves):
     """In place on q (values on the codebook)."""
     cb = device_codebook(cb)
@@ -372,6 +419,7 @@ def local_search(w, q, h, cb, moves):
     return q
 
 
+@_timed("bias_delta")
 def bias_delta(w, wq, mean_vec):
     _chk(w, torch.float32)
     _chk(wq, torch.float32)
