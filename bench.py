@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- GPTQ weights quantized per second on BASELINE.json's configs[1]:
+all 72 OPT-125M-shaped linear layers, 3-bit uniform codebook, diag-H scale-grid search
+(100 points) + GPTQ (diag ordering, 1 % damp) + layer error, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over the whole 72-layer set (84 934 656 weights), with
+W and H resident in HBM (`value`), and again through the numpy-facing public API with host
+buffers (`e2e`).  N > 1 (torchrun): every rank quantizes its own 72-layer set (layers are
+independent; no data-path collective) -> weak scaling, value = N * weights / max-over-ranks time.
+
+`--impl reference` times the reference's CPU algorithm (the numpy port in oracle/, the reference
+itself being pure Python that cannot travel to the GPU box) on the host cores, on a bounded
+sample of the same workload, and reports the extrapolated whole-job rate.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gptq_weights_quantized_per_s"
+UNIT = "weights/s"
+CODEBOOK = 8
+GRID = 100
+DAMP = 0.01
+SAMPLES = 2048
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="opt-125m")
+    ap.add_argument("--layers", type=int, default=0, help="debug: only the first L layers")
+    ap.add_argument("--cpu-row-div", type=int, default=4, help="CPU sample: 1/div of each layer's rows")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(model, nlayers):
+    return (f"{model}: {nlayers} linear layers, {CODEBOOK}-entry uniform codebook (3-bit), diag-H scale search "
+            f"({GRID} pts) + GPTQ (diag order, {DAMP:g} damp) + layer error, S={SAMPLES} synthetic calibration rows")
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle (numpy port of the reference) on a bounded sample
+# ---------------------------------------------------------------------------
+
+
+def cpu_layer_estimate(orc, W, H, grid, row_div):
+    """Time one layer on the host with 1/row_div of its rows and extrapolate: scale search, sweep
+    and error are linear in rows (rows never interact, obq.py:106-137, scaling.py:127-133); the
+    damp + order + fp64 factor phase does not depend on rows and is timed in full."""
+    r, n = W.shape
+    rs = max(1, r // row_div)
+    Ws = np.ascontiguousarray(W[:rs])
+    t0 = time.perf_counter()
+    sc = orc.search_scale(Ws, grid, 0, H=H.diagonal())
+    x = orc.divide_rows(Ws, sc, 0).astype(np.float32)
+    t1 = time.perf_counter()
+    Hf = H.astype(np.float32)
+    Hd = Hf + DAMP * Hf.diagonal().mean() * np.eye(n)
+    perm = orc.column_order(x, Hd, grid, "diag")
+    U = orc.inverse_upper_factor(Hd[perm][:, perm])
+    t2 = time.perf_counter()
+    Q = x[:, perm].copy()
+    E = np.zeros_like(Q)
+    orc.sweep_in_place(Q, E, U, grid)
+    Q = Q[:, np.argsort(perm)]
+    out = orc.divide_rows(Q, 1 / sc, 0)
+    err = orc.mean_error(Ws, out, H)
+    t3 = time.perf_counter()
+    row_linear = (t1 - t0) + (t3 - t2)
+    factor = t2 - t1
+    return row_linear * (r / rs) + factor, (t3 - t0), float(err)
+
+
+def cpu_sample(orc, wl, model, row_div):
+    """One sample step: each distinct layer shape of the first block once; returns the
+    extrapolated whole-block seconds, the block's weight count and the measured seconds."""
+    shapes = wl.layer_shapes(model)
+    period = len(wl.OPT125M_BLOCK) if model == "opt-125m" else len(set(shapes))
+    block = shapes[:period]
+    grid = orc.UniformGrid(CODEBOOK, -1, 1)
+    cache, est_total, measured = {}, 0.0, 0.0
+    for lid, (r, n) in enumerate(block):
+        if (r, n) not in cache:
+            W, H, _ = _CPU_INPUTS.setdefault((r, n, lid), wl.synthetic_layer(r, n, lid, samples=SAMPLES))
+            est, meas, _ = cpu_layer_estimate(orc, W, H, grid, row_div)
+            cache[(r, n)] = est
+            measured += meas
+        est_total += cache[(r, n)]
+    return est_total, sum(r * n for r, n in block), measured
+
+
+_CPU_INPUTS = {}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import sleekit_oracle as orc
+    from sleekit_b200 import workloads as wl
+
+    cores = os.cpu_count()
+    shapes = wl.layer_shapes(args.model)
+    for _ in range(args.warmup):
+        cpu_sample(orc, wl, args.model, args.cpu_row_div)
+    ests, meas = [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        est, weights, m = cpu_sample(orc, wl, args.model, args.cpu_row_div)
+        ests.append(est)
+        meas.append(m)
+    wall = time.perf_counter() - t0
+    value = weights / (sum(ests) / len(ests))
+    sample = (f"per step: one layer of each distinct shape of block 0 ({sorted(set(shapes[:6]))}), first 1/{args.cpu_row_div} "
+              f"of the rows for the row-linear phases (scale search, sweep, error; scaled back by {args.cpu_row_div}x), "
+              f"damp+order+fp64 factor in full; whole-block time = sum over its 6 layers; numpy/OpenBLAS on all host cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.model, len(shapes))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower() == "active":
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+
+
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from sleekit_b200 import codebook, obq, ops, scaling
+    from sleekit_b200 import workloads as wl
+    from sleekit_b200 import _convert as cv
+
+    shapes = wl.layer_shapes(args.model)
+    if args.layers:
+        shapes = shapes[: args.layers]
+    L = len(shapes)
+    weights = sum(r * n for r, n in shapes)
+    cb = codebook.UniformCodebook(CODEBOOK, -1, 1)
+
+    # ---- inputs: W on host (pinned) and device; H = X^T X / S built on the device by K1 ----
+    Wh, Hh, Wd, Hd, Hdiag = [], [], [], [], []
+    xtx_ms, xtx_flop = 0.0, 0.0
+    for i, (r, n) in enumerate(shapes):
+        lid = i + 1000 * rank                      # every rank owns a different layer set (weak scaling)
+        w = torch.from_numpy(wl.synthetic_weight(r, n, lid)).pin_memory()
+        x = torch.from_numpy(wl.synthetic_calibration(n, lid, SAMPLES)).to(dev)
+        h = torch.zeros((n, n), dtype=torch.float32, device=dev)
+        m = torch.zeros(n, dtype=torch.float32, device=dev)
+        ops.hessian_accum(x, h, m, 0.0, SAMPLES)    # untimed first touch
+        h.zero_(); m.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.hessian_accum(x, h, m, 0.0, SAMPLES)
+        e1.record()
+        torch.cuda.synchronize()
+        xtx_ms += e0.elapsed_time(e1)
+        xtx_flop += 2.0 * SAMPLES * n * n
+        Wh.append(w)
+        Wd.append(w.to(dev))
+        Hd.append(h)
+        Hdiag.append(h.diagonal().contiguous())
+        Hh.append(h.cpu().pin_memory())
+        del x
+    errs = torch.zeros(L, dtype=torch.float32, device=dev)
+
+    def step_device():
+        for i in range(L):
+            sc = scaling.search_scale_device(Wd[i], cb, Hdiag[i], 0.05, 1.0, GRID)
+            q = scaling.quantize_scaled_device(Wd[i], sc, cb, Hd[i], "diag", DAMP, 0)
+            errs[i] = ops.mean(ops.hweighted_error(Wd[i], q, Hd[i]))
+
+    Wnp = [w.numpy() for w in Wh]
+    Hnp = [h.numpy() for h in Hh]
+    e2e_out = {}
+
+    def step_e2e():
+        # the reference-facing call sequence of experiments/compare.py:84-95, host numpy in and out
+        for i in range(L):
+            sc = scaling.compute_min_mse_scaling(Wnp[i], cb, H=Hnp[i].diagonal(), grid_size=GRID)
+            q = scaling.quantize_with_scaling(Wnp[i], sc, cb, H=Hnp[i], damp=DAMP)
+            e2e_out[i] = (q, obq.quantization_error(Wnp[i], q, H=Hnp[i]))
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = 1e3 * (time.perf_counter() - t0)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall
+
+    # ---- warm-up, then a profiled pass to find the dominant kernel -------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    ops.PROFILE = {}
+    step_device()
+    torch.cuda.synchronize()
+    phases = ops.profile_totals_ms(ops.PROFILE)
+    ops.PROFILE = None
+    top = max(phases, key=lambda k: phases[k][0])
+
+    # ---- timed region (device resident) ------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
+    launches0 = ops.launch_count()
+    ms, wall = timed(step_device, args.steps)
+    launches = ops.launch_count() - launches0
+    top_ms, top_calls = ops.profile_totals_ms(ops.PROFILE).get(top, (0.0, 0))
+    ops.PROFILE, ops.PROFILE_ONLY = None, None
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    value = world * weights / (ms_per_step * 1e-3)
+    layer_err = float(errs.mean().item())
+
+    # ---- end to end through the numpy API (host buffers; H2D and D2H inside the timed region) ---
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        cv.H2D_BYTES = cv.D2H_BYTES = 0
+        ems, ewall = timed(step_e2e, args.steps)
+        e2e = {"value": world * weights / (ewall / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": cv.H2D_BYTES // args.steps, "d2h_bytes_per_step": cv.D2H_BYTES // args.steps,
+               "ms_per_step": ewall / args.steps,
+               "api": "compute_min_mse_scaling + quantize_with_scaling + quantization_error on host numpy arrays"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roofline = None
+    if top_calls:
+        per_launch_ms = top_ms / top_calls
+        if top == "scale_search":
+            # reference traffic model = one pass over W per grid point = 4*G bytes/weight
+            alg_bytes = 4.0 * GRID * weights / L
+            note = ("effective GB/s: algorithmic bytes = 4*G bytes per weight (the reference's G passes over W, "
+                    "scaling.py:127-133); the fused kernel reads W once (4 B/weight real DRAM) and is fp32-ALU bound")
+        elif top == "hinv":
+            alg_bytes = sum(8.0 * 3 * n * n for _, n in shapes) / L
+            note = "fp64 factor+inverse: algorithmic bytes = 3 passes over the n^2 fp64 matrix (lower bound)"
+        else:
+            alg_bytes = 8.0 * weights / L
+            note = "algorithmic bytes = one read + one write of W per launch"
+        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": per_launch_ms, "launches_timed": top_calls,
+                    "share_of_step": top_ms / ms if ms else None, "note": note}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world >= 1:
+        from oracle import sleekit_oracle as orc
+
+        est, bw, meas = cpu_sample(orc, wl, args.model, args.cpu_row_div)
+        cpu_baseline = {"value": bw / est, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": (f"one layer of each distinct shape of block 0, first 1/{args.cpu_row_div} of rows for the "
+                                   f"row-linear phases (extrapolated), fp64 factor in full; {meas:.1f} s of CPU work")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.model, L), "layers": L, "weights_per_rank": weights,
+                   "parallelism": f"independent layer sets x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs (W+H ~0.93 GB per rank) are larger than the 126 MB L2; no flush needed"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "layer_error_mean": layer_err,
+        "phases_ms_per_step": {k: round(v[0], 3) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
+        "xtx": {"tflops": xtx_flop / (xtx_ms * 1e-3) / 1e12 if xtx_ms else None, "ms_total": xtx_ms,
+                "note": "K1 X^T X over the 72 calibration matrices, algorithmic 2*S*n^2 flop, fp32 CUDA-core path"},
+        "wall_ms_per_step": wall / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

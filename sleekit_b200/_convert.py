@@ -30,10 +30,17 @@ def float_dtype_of(x):
     return np.dtype(np.float32) if dt in (np.float32, np.float16) else np.dtype(np.float64)
 
 
+H2D_BYTES = 0  # bytes copied host->device / device->host by this module (bench.py reads these)
+D2H_BYTES = 0
+
+
 def to_dev(x, dtype=None):
     """Contiguous CUDA tensor holding x (optionally cast)."""
+    global H2D_BYTES
     dev = ops.device()
     if is_tensor(x):
+        if not x.is_cuda:
+            H2D_BYTES += x.numel() * x.element_size()
         t = x if x.is_cuda else x.to(dev)
         if dtype is not None and t.dtype != dtype:
             t = t.to(dtype)
@@ -42,6 +49,7 @@ def to_dev(x, dtype=None):
     if a.dtype.kind not in "f" or a.dtype == np.float16:
         a = a.astype(np.float64 if a.dtype.kind in "iub" else np.float32)
     a = np.ascontiguousarray(a)
+    H2D_BYTES += a.nbytes
     t = torch.from_numpy(a).to(dev, non_blocking=False)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
@@ -49,6 +57,8 @@ def to_dev(x, dtype=None):
 
 
 def to_host(t):
+    global D2H_BYTES
+    D2H_BYTES += t.numel() * t.element_size()
     return t.detach().cpu().numpy()
 
 

@@ -21,6 +21,7 @@ NEAREST, UP, DOWN = 0, 1, 2
 # Optional per-call device timing (bench.py): set PROFILE to a dict and every wrapped entry
 # point records a CUDA event pair on the stream it launches on.  None = no overhead.
 PROFILE = None
+PROFILE_ONLY = None  # optional set of names: time only these
 
 
 def _timed(name):
@@ -29,7 +30,7 @@ def _timed(name):
 
         @functools.wraps(fn)
         def wrapper(*a, **k):
-            if PROFILE is None:
+            if PROFILE is None or (PROFILE_ONLY is not None and name not in PROFILE_ONLY):
                 return fn(*a, **k)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
