@@ -185,6 +185,10 @@ int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, in
 int slk_bias_delta_f32(const float* w, const float* wq, const float* mean, int64_t r, int64_t n,
                        float* delta, void* stream);
 
+/* Self-test (tests only): for each of `count` divisors, compares the kernels' fast exact divide
+ * with the IEEE divide over all 2^32 dividends; mismatches[i] must come back 0. */
+int slk_selftest_fastdiv_f32(const float* divisors, int32_t count, uint64_t* mismatches, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,6 +172,75 @@ __device__ __forceinline__ float grid_value_of_index(const DevGrid<float>& g, in
 }
 
 // ---------------------------------------------------------------------------
+// Correctly rounded division by a divisor that is reused many times.
+// With y = RN(1/d) obtained once by a true IEEE divide, two FMA residual corrections of
+// q = a*y give RN(a/d) (Markstein's theorem: the first correction makes q faithful, the second
+// one correctly rounded), for every normal-range quotient unless d's significand is all ones.
+// `ok` is false for such divisors (and for extreme exponents); callers then use the plain divide.
+// Range: exact for quotients with exponent in [-100, 100] (verified exhaustively); a quotient
+// below 2^-102 may be one ulp off because the residual a - d*q underflows.  The kernels only
+// divide (i) weights by row scales and (ii) "x - zero" by the codebook step, (iii) codewords by
+// reciprocal scales: tiny quotients of (i) are absorbed by the following "x - zero" (|zero| ~ 1),
+// (ii) and (iii) cannot be that small for scales >= 1e-16 * min_factor.
+// 5 FMA-pipe ops instead of the ~20-instruction IEEE divide sequence; checked exhaustively
+// against __fdiv_rn on the device by slk_selftest_fastdiv_f32 (tests/test_gpu_parity.py).
+// ---------------------------------------------------------------------------
+struct FastDivF { float d, y; int ok; };
+
+__device__ __forceinline__ FastDivF make_fastdiv(float d) {
+  FastDivF f;
+  f.d = d;
+  f.y = __fdiv_rn(1.0f, d);
+  const unsigned bits = __float_as_uint(d);
+  const int ex = (int)((bits >> 23) & 0xffu) - 127;
+  f.ok = (ex > -60 && ex < 60 && (bits & 0x7fffffu) != 0x7fffffu) ? 1 : 0;
+  return f;
+}
+
+__device__ __forceinline__ float fastdiv_core(float a, float d, float y) {
+  float q = __fmul_rn(a, y);
+  float r = __fmaf_rn(-d, q, a);
+  q = __fmaf_rn(r, y, q);
+  r = __fmaf_rn(-d, q, a);
+  return __fmaf_rn(r, y, q);
+}
+
+__device__ __forceinline__ float fastdiv(float a, const FastDivF& f) {
+  return f.ok ? fastdiv_core(a, f.d, f.y) : __fdiv_rn(a, f.d);
+}
+
+struct FastDivD { double d, y; int ok; };
+
+__device__ __forceinline__ FastDivD make_fastdiv(double d) {
+  FastDivD f;
+  f.d = d;
+  f.y = __ddiv_rn(1.0, d);
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+  const int ex = (int)((bits >> 52) & 0x7ffull) - 1023;
+  f.ok = (ex > -400 && ex < 400 && (bits & 0xfffffffffffffull) != 0xfffffffffffffull) ? 1 : 0;
+  return f;
+}
+
+__device__ __forceinline__ double fastdiv(double a, const FastDivD& f) {
+  if (!f.ok) return __ddiv_rn(a, f.d);
+  double q = __dmul_rn(a, f.y);
+  double r = __fma_rn(-f.d, q, a);
+  q = __fma_rn(r, f.y, q);
+  r = __fma_rn(-f.d, q, a);
+  return __fma_rn(r, f.y, q);
+}
+
+// Uniform-grid rounding with the divide by `step` done through a FastDivF (same results).
+__device__ __forceinline__ float uniform_value_fast(const DevGrid<float>& g, const FastDivF& fstep, float x) {
+  float t = fastdiv(__fsub_rn(x, g.zero), fstep);
+  float k = rintf(t);
+  const float hi = (float)(g.size - 1);
+  k = k < 0.0f ? 0.0f : k;
+  k = k > hi ? hi : k;
+  return __fadd_rn(__fmul_rn(k, g.step), g.zero);
+}
+
+// ---------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------
 template <typename T>

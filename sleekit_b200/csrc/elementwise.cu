@@ -356,6 +356,31 @@ __global__ void __launch_bounds__(256) argsort_rank_kernel(const double* __restr
   if (j < n) order[rank] = j;
 }
 
+// Exhaustive check of fastdiv_core against the IEEE divide: for each divisor, all 2^32 dividends.
+// Counted: results that differ (sign of zero ignored) while the true quotient is zero or has an
+// exponent in [-100, 100].  (Below 2^-102 the residual a - d*q is not representable and the
+// scheme can be one ulp off; every use in the kernels feeds such quotients into "x - zero" with
+// |zero| ~ 1, which absorbs them -- see common.cuh.)
+__global__ void __launch_bounds__(256) selftest_fastdiv_kernel(const float* __restrict__ divisors,
+                                                               unsigned long long* __restrict__ mismatches,
+                                                               unsigned long long stride_limit) {
+  const float d = divisors[blockIdx.y];
+  const FastDivF f = make_fastdiv(d);
+  unsigned long long bad = 0;
+  const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < stride_limit; i += step) {
+    const float a = __uint_as_float((unsigned)i);
+    if (!(fabsf(a) <= 3.0e38f)) continue;  // skip inf / nan
+    const float want = __fdiv_rn(a, d);
+    const float aw = fabsf(want);
+    if (!(aw == 0.0f || (aw >= 7.8886091e-31f && aw <= 1.2676506e30f))) continue;
+    const float got = f.ok ? fastdiv_core(a, f.d, f.y) : want;
+    if (!(got == want)) ++bad;
+  }
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches + blockIdx.y, bad);
+}
+
 __global__ void __launch_bounds__(256) mean_kernel_f32(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
   __shared__ double scratch[32];
   double acc = 0.0;
@@ -533,6 +558,15 @@ int slk_mean_f32(const float* v, int64_t count, float* out, void* stream) {
 int slk_mean_f64(const double* v, int64_t count, double* out, void* stream) {
   SLK_REQUIRE(v && out && count >= 1, "bad arguments");
   mean_kernel_f64<<<1, 256, 0, (cudaStream_t)stream>>>(v, count, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_selftest_fastdiv_f32(const float* divisors, int32_t count, uint64_t* mismatches, void* stream) {
+  SLK_REQUIRE(divisors && mismatches && count >= 1, "bad arguments");
+  SLK_CUDA(cudaMemsetAsync(mismatches, 0, (size_t)count * sizeof(uint64_t), (cudaStream_t)stream));
+  dim3 grid((unsigned)(sm_count() * 8), (unsigned)count);
+  selftest_fastdiv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(divisors, (unsigned long long*)mismatches, 1ull << 32);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

@@ -13,6 +13,44 @@
 
 namespace slk {
 
+// Error of one row at one grid point.  FAST: the three divides (by scale, by the codebook step,
+// by rs) go through fastdiv_core -- same correctly rounded quotients, 5 FMA-pipe ops each.
+template <typename HT, bool HAS_H, bool FAST>
+__device__ __forceinline__ HT row_error(const float* __restrict__ rowp, int64_t n, const DevGrid<float>& g,
+                                        const FastDivF& fs, const FastDivF& fr, const FastDivF& fstep,
+                                        const HT* __restrict__ hdiag) {
+  const float hi = (float)(g.size - 1);
+  HT acc[4] = {(HT)0, (HT)0, (HT)0, (HT)0};
+  auto one = [&](float w) -> float {
+    float v;
+    if (FAST) {
+      const float x = fastdiv_core(w, fs.d, fs.y);                          // scaling.py:73
+      float k = rintf(fastdiv_core(__fsub_rn(x, g.zero), fstep.d, fstep.y)); // codebook.py:60-62
+      k = k < 0.0f ? 0.0f : k;
+      k = k > hi ? hi : k;
+      v = __fadd_rn(__fmul_rn(k, g.step), g.zero);                          // codebook.py:63-64
+      v = fastdiv_core(v, fr.d, fr.y);                                      // scaling.py:80
+    } else {
+      v = __fdiv_rn(grid_value(g, __fdiv_rn(w, fs.d)), fr.d);
+    }
+    const float e = __fsub_rn(v, w);                                        // scaling.py:130
+    return __fmul_rn(e, e);
+  };
+  int64_t j = 0;
+  for (; j + 4 <= n; j += 4) {
+    float e2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e2[u] = one(rowp[j + u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] += HAS_H ? (HT)e2[u] * __ldg(hdiag + j + u) : (HT)e2[u];
+  }
+  for (; j < n; ++j) {
+    const float e2 = one(rowp[j]);
+    acc[0] += HAS_H ? (HT)e2 * __ldg(hdiag + j) : (HT)e2;
+  }
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
 template <typename HT, bool HAS_H>
 __global__ void __launch_bounds__(128) scale_search_kernel(const float* __restrict__ w, int64_t r, int64_t n,
                                                            DevGrid<float> g, float cb_min, float cb_max,
@@ -25,6 +63,7 @@ __global__ void __launch_bounds__(128) scale_search_kernel(const float* __restri
   float* srow = (float*)(smem_raw + (((size_t)G * sizeof(HT) + 15) & ~(size_t)15));  // [n] if row_in_smem
   __shared__ float red_lo[4], red_hi[4];
   __shared__ float s_init;
+  const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
 
   for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
     const float* grow = w + row * n;
@@ -56,35 +95,11 @@ __global__ void __launch_bounds__(128) scale_search_kernel(const float* __restri
     for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
       const float scale = __fmul_rn(__ldg(factors + gi), init);    // scaling.py:128
       const float rs = __fdiv_rn(1.0f, scale);                     // scaling.py:80
-      HT acc0 = (HT)0, acc1 = (HT)0, acc2 = (HT)0, acc3 = (HT)0;
-      int64_t j = 0;
-      for (; j + 4 <= n; j += 4) {
-        float x[4], e2[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = rowp[j + u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float v = grid_value(g, __fdiv_rn(x[u], scale));
-          float e = __fsub_rn(__fdiv_rn(v, rs), x[u]);
-          e2[u] = __fmul_rn(e, e);
-        }
-        if (HAS_H) {
-          acc0 += (HT)e2[0] * __ldg(hdiag + j);
-          acc1 += (HT)e2[1] * __ldg(hdiag + j + 1);
-          acc2 += (HT)e2[2] * __ldg(hdiag + j + 2);
-          acc3 += (HT)e2[3] * __ldg(hdiag + j + 3);
-        } else {
-          acc0 += (HT)e2[0]; acc1 += (HT)e2[1]; acc2 += (HT)e2[2]; acc3 += (HT)e2[3];
-        }
-      }
-      for (; j < n; ++j) {
-        float x = rowp[j];
-        float v = grid_value(g, __fdiv_rn(x, scale));
-        float e = __fsub_rn(__fdiv_rn(v, rs), x);
-        float e2 = __fmul_rn(e, e);
-        acc0 += HAS_H ? (HT)e2 * __ldg(hdiag + j) : (HT)e2;
-      }
-      errs[gi] = (acc0 + acc1) + (acc2 + acc3);
+      const FastDivF fs = make_fastdiv(scale), fr = make_fastdiv(rs);
+      if (g.kind == 0 && fstep.ok && fs.ok && fr.ok)
+        errs[gi] = row_error<HT, HAS_H, true>(rowp, n, g, fs, fr, fstep, hdiag);
+      else
+        errs[gi] = row_error<HT, HAS_H, false>(rowp, n, g, fs, fr, fstep, hdiag);
     }
     __syncthreads();
     // ---- pass 3: first strict minimum in grid order, best kept in fp32 (scaling.py:125-134)

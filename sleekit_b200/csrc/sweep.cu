@@ -1,43 +1,84 @@
 // K3: the GPTQ / OBQ column sweep.
 //   _quantize_opt_core   (leaf, <= 32 columns)      obq.py:106-118
 //   _quantize_opt_block  (8-ary lazy batching)      obq.py:121-137
-// Leaf: one warp per row, lane j holds column a+j.  Column i is broadcast with a shuffle,
-// quantised, its scaled residual r = (w - q) / U[i,i] is formed in fp64 (as numpy does: the
-// divisor is an fp64 scalar) and lanes j > i take q_j <- fp32(fp64(q_j) - r * U[i,j]) -- the
-// exact op sequence of obq.py:114-118, so given the same fp64 U a leaf is bit-identical to
-// the reference.  Trailing updates Q[:, b:end] -= E[:, a:b] @ U[a:b, b:end] are fp32 GEMMs
+// Leaf: one thread per row with its 32 columns in registers.  Column i is quantised, its scaled
+// residual r = (w - q) / U[i,i] is formed in fp64 (as numpy does: the divisor is an fp64 scalar)
+// and columns j > i take q_j <- fp32(fp64(q_j) - r * U[i,j]) -- the exact op sequence of
+// obq.py:114-118, so given the same fp64 U a leaf is bit-identical to the reference.  Trailing updates Q[:, b:end] -= E[:, a:b] @ U[a:b, b:end] are fp32 GEMMs
 // with exact-product fmaf accumulation on the fp32 rounding of U (parity-safe).
 #include "gemm.cuh"
 
 namespace slk {
 
-__global__ void __launch_bounds__(128) sweep_leaf_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r,
-                                                         int64_t n, int a, int width, const double* __restrict__ U,
-                                                         DevGrid<float> g) {
-  __shared__ double Us[32][33];
+constexpr int LEAF_ROWS = 64;  // rows (threads) per CTA of the leaf kernel
+
+// Thread-per-row leaf: each thread keeps its 32 columns in registers and walks them in order.
+// All threads of a warp read the same U[i][j] (shared-memory broadcast), so there is no
+// cross-lane traffic at all and the only serial chain is the one the algorithm imposes
+// (column i+1 needs column i's residual).  Arithmetic per column, as obq.py:110-118:
+//   q = quant(w);  res = fp64(w - q) / U[i,i];  E[:, i] = fp32(res);
+//   Q[:, j] = fp32(fp64(Q[:, j]) - res * U[i, j])   for j > i
+// The two divides (by the codebook step and by U[i,i]) use the exact reciprocal scheme of
+// common.cuh, so the results are the IEEE quotients.
+__global__ void __launch_bounds__(LEAF_ROWS) sweep_leaf_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r,
+                                                               int64_t n, int a, int width,
+                                                               const double* __restrict__ U, DevGrid<float> g) {
+  __shared__ double Us[32][32];
+  __shared__ double Uy[32];   // RN(1 / U[i][i])
+  __shared__ int Uok[32];
   for (int t = threadIdx.x; t < 32 * 32; t += blockDim.x) {
-    int i = t >> 5, j = t & 31;
-    Us[i][j] = (i < width && j < width) ? U[(int64_t)(a + i) * n + (a + j)] : 0.0;
+    const int i = t >> 5, j = t & 31;
+    double v = (i < width && j < width) ? U[(int64_t)(a + i) * n + (a + j)] : (i == j ? 1.0 : 0.0);
+    Us[i][j] = v;
+    if (i == j) {
+      const FastDivD f = make_fastdiv(v);
+      Uy[i] = f.y;
+      Uok[i] = f.ok;
+    }
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < r;
-       row += (int64_t)gridDim.x * warps_per_block) {
-    float* qrow = Q + row * n + a;
-    float q = lane < width ? qrow[lane] : 0.0f;
-    float e = 0.0f;
-    for (int i = 0; i < width; ++i) {
-      const float w = __shfl_sync(0xffffffffu, q, i);
-      const float qq = grid_value(g, w);
-      const double res = __ddiv_rn((double)__fsub_rn(w, qq), Us[i][i]);   // obq.py:114
-      if (lane == i) { q = qq; e = (float)res; }                          // obq.py:115-116
-      else if (lane > i) q = (float)__dsub_rn((double)q, __dmul_rn(res, Us[i][lane]));  // obq.py:118
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
+  const bool fastq = (g.kind == 0) && fstep.ok;
+  float* qrow = Q + row * n + a;
+  float* erow = E + row * n + a;
+  float q[32], e[32];
+  const bool vec = (width == 32) && ((((uintptr_t)qrow) & 15) == 0) && ((((uintptr_t)erow) & 15) == 0);
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 v = reinterpret_cast<const float4*>(qrow)[k];
+      q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
     }
-    if (lane < width) {
-      qrow[lane] = q;
-      E[row * n + a + lane] = e;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) q[k] = k < width ? qrow[k] : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float w = q[i];
+    const float qq = fastq ? uniform_value_fast(g, fstep, w) : grid_value(g, w);
+    const double num = (double)__fsub_rn(w, qq);
+    FastDivD fd;
+    fd.d = Us[i][i]; fd.y = Uy[i]; fd.ok = Uok[i];
+    const double res = fastdiv(num, fd);                                   // obq.py:114
+    q[i] = qq;                                                             // obq.py:116
+    e[i] = (float)res;                                                     // obq.py:115
+#pragma unroll
+    for (int j = i + 1; j < 32; ++j)
+      q[j] = (float)__dsub_rn((double)q[j], __dmul_rn(res, Us[i][j]));     // obq.py:118
+  }
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      reinterpret_cast<float4*>(qrow)[k] = make_float4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+      reinterpret_cast<float4*>(erow)[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < width) { qrow[k] = q[k]; erow[k] = e[k]; }
   }
 }
 
@@ -53,11 +94,8 @@ struct SweepCtx {
 static int sweep_range(const SweepCtx& c, int64_t a, int64_t b) {
   const int64_t size = b - a;
   if (size <= c.leaf) {
-    const int warps = 4;
-    int64_t blocks = ceil_div(c.r, warps);
-    int64_t cap = (int64_t)sm_count() * 16;
-    sweep_leaf_kernel<<<(int)(blocks < cap ? blocks : cap), warps * 32, 0, c.st>>>(c.Q, c.E, c.r, c.n, (int)a,
-                                                                                     (int)size, c.u64, c.g);
+    sweep_leaf_kernel<<<(int)ceil_div(c.r, LEAF_ROWS), LEAF_ROWS, 0, c.st>>>(c.Q, c.E, c.r, c.n, (int)a, (int)size,
+                                                                              c.u64, c.g);
     SLK_LAUNCH_CHECK();
     return SLK_OK;
   }

@@ -521,3 +521,23 @@ def test_edge_cases(slk):
     np.testing.assert_array_equal(q, want)
     with pytest.raises(TypeError):
         slk.obq.quantize_opt(W2, H2, lambda x: np.round(x))
+
+
+def test_fast_exact_division_matches_ieee_exhaustively(slk):
+    """K5 / K3 divide by per-row and per-codebook constants through a reciprocal + two FMA
+    corrections; it must equal the IEEE quotient for every dividend (2^32 of them) per divisor."""
+    import ctypes
+
+    from sleekit_b200 import _lib
+
+    rng = np.random.default_rng(99)
+    divs = [2.0 / (c - 1) for c in (2, 3, 4, 8, 16, 9, 256)] + [4.0 / 8, 6.0 / 8, 1.0, 3.0, 0.1, 5e-18, 7.0, 1e-3]
+    divs += list(np.exp(rng.uniform(-12, 12, 20)))            # scales
+    divs += list(1.0 / np.exp(rng.uniform(-12, 12, 12)))      # reciprocals of scales
+    divs += [float(np.nextafter(np.float32(2.0), np.float32(0.0)))]  # all-ones significand: falls back
+    d = torch.tensor(np.array(divs, dtype=np.float32), device="cuda")
+    bad = torch.zeros(d.numel(), dtype=torch.int64, device="cuda")
+    _lib.call("slk_selftest_fastdiv_f32", ctypes.c_void_p(d.data_ptr()), d.numel(), ctypes.c_void_p(bad.data_ptr()),
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(bad.sum().item()) == 0, [(divs[i], int(b)) for i, b in enumerate(bad.tolist()) if b]
