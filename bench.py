@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-row-div", type=int, default=4, help="CPU sample: 1/div of each layer's rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent layers are spread over")
+    ap.add_argument("--streams", type=int, default=24, help="CUDA streams the independent layers are spread over")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -265,8 +266,10 @@ def run_ours(args):
     lsq = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=DAMP, nb_ls_moves=0, grid_size=GRID,
                             streams=args.streams)
 
-    def step_device():
+    def step_eager():
         lsq(Wd, Hd, errs_out=errs, keep_outputs=False)
+
+    step_device = step_eager
 
     Wnp = [w.numpy() for w in Wh]
     Hnp = [h.numpy() for h in Hh]
@@ -312,13 +315,38 @@ def run_ours(args):
     ops.PROFILE = None
     top = max(phases, key=lambda k: phases[k][0])
 
+    graph = None
+    if not args.no_graph:
+        # one pass recorded as a CUDA graph: the streams become parallel branches, replay has no
+        # per-kernel CPU launch cost (the eager pass is bound by ~4 us of CPU per launch)
+        graph, gerrs, _ = lsq.capture(Wd, Hd)
+
+        def step_device():
+            graph.replay()
+
+        for _ in range(2):
+            step_device()
+        torch.cuda.synchronize()
+        errs = gerrs
+
     # ---- timed region (device resident) ------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
+    launches_per_step = None
+    if graph is None:
+        ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
     launches0 = ops.launch_count()
     ms, wall = timed(step_device, args.steps)
     launches = ops.launch_count() - launches0
+    if graph is not None:
+        # a replay launches the kernels recorded at capture time; count them with one eager pass,
+        # which also times the dominant kernel with events on the stream it runs on
+        ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
+        launches0 = ops.launch_count()
+        step_eager()
+        torch.cuda.synchronize()
+        launches_per_step = ops.launch_count() - launches0
+        launches = launches_per_step * args.steps
     top_ms, top_calls = ops.profile_totals_ms(ops.PROFILE).get(top, (0.0, 0))
     ops.PROFILE, ops.PROFILE_ONLY = None, None
     clocks = sampler.stop()
@@ -383,7 +411,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.model, L), "layers": L, "weights_per_rank": weights,
                    "parallelism": f"independent layer sets x{world}" if world > 1 else "single GPU",
-                   "streams": args.streams,
+                   "streams": args.streams, "cuda_graph": graph is not None,
                    "l2": "inputs (W+H ~0.93 GB per rank) are larger than the 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "layer_error_mean": layer_err,

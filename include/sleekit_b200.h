@@ -167,11 +167,13 @@ int slk_hinv_from_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, dou
 /* ---- K3: GPTQ / OBQ sweep ------------------------------------------------------
  * _quantize_opt_block / _quantize_opt_core                    obq.py:106-137
  * q: [r, n] in: scaled, column-permuted weights; out: quantized values.
- * e: [r, n] out: scaled residuals.  u64: fp64 factor (leaf arithmetic),
- * u32: its fp32 rounding (trailing updates).  leaf <= 32. */
+ * e: [r, n] out: scaled residuals.  u32: fp32 rounding of the factor.  leaf <= 32.
+ * exact_leaf = 0: all-fp32 leaf arithmetic (default, fast; u64 may be NULL);
+ * exact_leaf = 1: the leaf reproduces the reference's mixed fp64/fp32 op sequence bit for bit
+ *                 from the fp64 factor u64 (obq.py:114-118). */
 int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, const double* u64,
                        const float* u32, const slk_codebook* cb_host, int32_t leaf,
-                       int32_t fanout, void* stream);
+                       int32_t fanout, int32_t exact_leaf, void* stream);
 
 /* ---- K7: best-first local search ------------------------------------------------
  * quantize_local_search / LocalSearchQuantizer                obq.py:234-358

@@ -183,24 +183,43 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams<T> p) {
     }
     return;
   }
+  // Read-modify-write epilogues first gather every C element they need (all loads in flight at
+  // once -- interleaving each load with its store serialises 64 L2 round trips per thread), then
+  // compute and store.
 #pragma unroll
-  for (int i = 0; i < 2 * H; ++i) {
-    int64_t m = m0 + (i < H ? ty * H + i : 16 * H + ty * H + (i - H));
-    if (m >= M) continue;
+  for (int half = 0; half < 2; ++half) {
+    T old[H][2 * H];
+    if (EPI == EPI_ACCUM || EPI == EPI_HESS) {
 #pragma unroll
-    for (int j = 0; j < 2 * H; ++j) {
-      int64_t n = n0 + (j < H ? tx * H + j : 16 * H + tx * H + (j - H));
-      if (n >= N) continue;
-      T* c = C + m * p.ldc + n;
-      T v = acc[i][j];
-      if (EPI == EPI_STORE) *c = F::mul(p.alpha, v);
-      else if (EPI == EPI_ACCUM) *c = F::add(*c, F::mul(p.alpha, v));
-      else if (EPI == EPI_HESS) *c = F::add(F::mul(*c, p.keep), F::div(v, p.count));
-      else if (EPI == EPI_GAIN) {
-        T d = F::sub(__ldg(p.x0 + m * p.ldx + n), __ldg(p.x1 + m * p.ldx + n));
-        T t1 = F::mul(-F::mul(d, d), __ldg(p.x2 + n * p.x2_stride));
-        T t2 = F::mul(F::mul((T)2, v), d);
-        *c = F::sub(t1, t2);
+      for (int ii = 0; ii < H; ++ii) {
+        const int64_t m = m0 + half * 16 * H + ty * H + ii;
+#pragma unroll
+        for (int j = 0; j < 2 * H; ++j) {
+          const int64_t n = n0 + (j < H ? tx * H + j : 16 * H + tx * H + (j - H));
+          old[ii][j] = (m < M && n < N) ? __ldcg(C + m * p.ldc + n) : (T)0;
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < H; ++ii) {
+      const int i = half * H + ii;
+      const int64_t m = m0 + half * 16 * H + ty * H + ii;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 2 * H; ++j) {
+        const int64_t n = n0 + (j < H ? tx * H + j : 16 * H + tx * H + (j - H));
+        if (n >= N) continue;
+        T* c = C + m * p.ldc + n;
+        const T v = acc[i][j];
+        if (EPI == EPI_STORE) *c = F::mul(p.alpha, v);
+        else if (EPI == EPI_ACCUM) *c = F::add(old[ii][j], F::mul(p.alpha, v));
+        else if (EPI == EPI_HESS) *c = F::add(F::mul(old[ii][j], p.keep), F::div(v, p.count));
+        else if (EPI == EPI_GAIN) {
+          T d = F::sub(__ldg(p.x0 + m * p.ldx + n), __ldg(p.x1 + m * p.ldx + n));
+          T t1 = F::mul(-F::mul(d, d), __ldg(p.x2 + n * p.x2_stride));
+          T t2 = F::mul(F::mul((T)2, v), d);
+          *c = F::sub(t1, t2);
+        }
       }
     }
   }

@@ -41,56 +41,60 @@ __global__ void __launch_bounds__(256) hinv_gather_kernel(const TS* __restrict__
 
 // ---- 64x64 diagonal block: factor + inverse, warp-level ----------------------------------------
 // The block is split 2x2 into 32x32 tiles.  A 32x32 Cholesky and a 32x32 triangular inverse each
-// run in ONE warp with a row per lane held in registers and columns broadcast by shuffles (no
-// block barriers inside the 32 dependent steps); the four 32^3 products between them use all
-// 128 threads on shared memory.  ~8 us instead of ~90 us for the barrier-per-column version.
+// run in ONE warp with a row per lane and only __syncwarp between the 32 dependent steps (no
+// block barriers); the four 32^3 products between them use all 128 threads on shared memory.
 constexpr int HB = 32;
 constexpr int LDP = NB + 1;  // padded leading dimension of the smem blocks
 
 // Cholesky of the 32x32 tile at (r0, r0) of M (lower, in place) and its inverse into the same
-// tile of X.  Executed by one full warp.
-__device__ __forceinline__ void chol32_and_inverse(double (*M)[LDP], double (*X)[LDP], int r0, int lane,
-                                                   int32_t* info, int64_t gcol0) {
-  double a[HB];
-#pragma unroll
-  for (int k = 0; k < HB; ++k) a[k] = M[r0 + lane][r0 + k];
-#pragma unroll
+// tile of X.  Executed by one full warp; tiles stay in shared memory and every loop is a real
+// loop (a fully unrolled register version runs ~10^4 instructions exactly once and is
+// instruction-fetch bound; measured 150 us per panel).
+//  - factor: left-looking, lane i owns row i.  Step j: s_i = A[i][j] - sum_{k<j} L[i][k] L[j][k]
+//    (reads only, no shared-memory read-modify-write), lane j's s is the pivot, broadcast by
+//    shuffle; one __syncwarp per column.
+//  - inverse: lane j solves L x = e_j by forward substitution on its own column of X; lanes do
+//    not communicate at all.
+__device__ __noinline__ void chol32_and_inverse(double (*M)[LDP], double (*X)[LDP], int r0, int lane,
+                                                int32_t* info, int64_t gcol0) {
+  __shared__ double rdiag[HB];                 // 1 / L[j][j]
+  double* mrow = &M[r0 + lane][r0];
   for (int j = 0; j < HB; ++j) {
-    const double piv = __shfl_sync(0xffffffffu, a[j], j);
+    const double* jrow = &M[r0 + j][r0];
+    double s0 = mrow[j], s1 = 0.0;
+    int k = 0;
+    for (; k + 1 < j; k += 2) {
+      s0 = __fma_rn(-mrow[k], jrow[k], s0);
+      s1 = __fma_rn(-mrow[k + 1], jrow[k + 1], s1);
+    }
+    if (k < j) s0 = __fma_rn(-mrow[k], jrow[k], s0);
+    const double s = s0 + s1;
+    const double piv = __shfl_sync(0xffffffffu, s, j);
     if (lane == 0 && !(piv > 0.0)) atomicCAS(info, 0, (int32_t)(gcol0 + j + 1));
     const double y = rsqrt(piv);
-    a[j] = lane == j ? piv * y : a[j] * y;   // L[j][j] = sqrt(piv); L[i][j] = a[i][j] / sqrt(piv)
-    const double li = a[j];
-#pragma unroll
-    for (int k = j + 1; k < HB; ++k) {
-      const double lk = __shfl_sync(0xffffffffu, li, k);
-      a[k] = __fma_rn(-li, lk, a[k]);          // rows above k only touch their unused upper part
-    }
+    __syncwarp();
+    if (lane == j) { mrow[j] = piv * y; rdiag[j] = y; }   // sqrt(piv) and its reciprocal
+    else if (lane > j) mrow[j] = s * y;
+    else mrow[j] = 0.0;                        // upper part of L
+    __syncwarp();
   }
-  double dinv = 0.0;
-#pragma unroll
-  for (int k = 0; k < HB; ++k) {
-    if (k == lane) dinv = 1.0 / a[k];
-    M[r0 + lane][r0 + k] = k <= lane ? a[k] : 0.0;
-  }
-  // X = inv(L): lane i owns row i.  Before step k, x[j] holds sum_{m<k} L[i][m] X[m][j].
-  double x[HB];
-#pragma unroll
-  for (int k = 0; k < HB; ++k) x[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < HB; ++k) {
-    if (lane == k) {
-#pragma unroll
-      for (int j = 0; j <= k; ++j) x[j] = ((j == k ? 1.0 : 0.0) - x[j]) * dinv;
+  // X = inv(L): lane c owns column c.  x_i = (delta_ic - sum_{k<i} L[i][k] x_k) / L[i][i], with
+  // x_k = 0 for k < c, so the sum may start at k = c.
+  double* xcol = &X[r0][r0 + lane];            // element i of this lane's column: xcol[i * LDP]
+  for (int i = 0; i < HB; ++i) {
+    const double* irow = &M[r0 + i][r0];
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+    if (i > lane) {
+      int k = lane;
+      for (; k + 1 < i; k += 2) {
+        s0 = __fma_rn(-irow[k], xcol[k * LDP], s0);
+        s1 = __fma_rn(-irow[k + 1], xcol[(k + 1) * LDP], s1);
+      }
+      if (k < i) s0 = __fma_rn(-irow[k], xcol[k * LDP], s0);
     }
-#pragma unroll
-    for (int j = 0; j <= k; ++j) {
-      const double xkj = __shfl_sync(0xffffffffu, x[j], k);
-      if (lane > k) x[j] = __fma_rn(a[k], xkj, x[j]);
-    }
+    xcol[i * LDP] = i >= lane ? (s0 + s1) * rdiag[i] : 0.0;
   }
-#pragma unroll
-  for (int k = 0; k < HB; ++k) X[r0 + lane][r0 + k] = k <= lane ? x[k] : 0.0;
+  __syncwarp();
 }
 
 // C(32x32 at cr,cc) = beta*C + alpha * A(32x32 at ar,ac) * op(B)(32x32), op = transpose if TB.
@@ -152,27 +156,47 @@ __global__ void __launch_bounds__(128) hinv_panel_kernel(double* __restrict__ A,
   double (*L)[LDP] = (double (*)[LDP])diag_smem;
   double (*X)[LDP] = (double (*)[LDP])(diag_smem + NB * LDP);
   const int tid = threadIdx.x;
-  for (int t = tid; t < NB * NB; t += 128) {
-    const int i = t / NB, j = t % NB;
-    L[i][j] = A[(k0 + i) * ld + k0 + j];
+  // All global loads are issued up front, 32 per thread in flight (one memory latency instead of
+  // 32 in a row): the diagonal block, and for slab CTAs the slab too, which then sits in registers
+  // while the block is factored.
+  const double* D = A + k0 * ld + k0;
+  double* S = A + (k0 + (int64_t)blockIdx.x * NB) * ld + k0;   // blockIdx.x == 0: the diagonal block itself
+  double dv[32], sv[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int t = tid + k * 128;
+    dv[k] = D[(t >> 6) * ld + (t & 63)];
+  }
+  if (blockIdx.x != 0) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int t = tid + k * 128;
+      sv[k] = S[(t >> 6) * ld + (t & 63)];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int t = tid + k * 128;
+    L[t >> 6][t & 63] = dv[k];
   }
   __syncthreads();
   factor64(L, X, tid, info, k0);
   if (blockIdx.x == 0) {
-    for (int t = tid; t < NB * NB; t += 128) {
-      const int i = t / NB, j = t % NB;
-      // L_kk itself is never needed again (the other CTAs of this launch are still reading the
-      // unfactored block, so it must not be overwritten here); only its inverse is kept.
-      Li[(k0 + i) * ld + k0 + j] = X[i][j];
+    // L_kk itself is never needed again (the other CTAs of this launch are still reading the
+    // unfactored block, so it must not be overwritten here); only its inverse is kept.
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int t = tid + k * 128;
+      Li[(k0 + (t >> 6)) * ld + k0 + (t & 63)] = X[t >> 6][t & 63];
     }
     return;
   }
-  // slab solve: S <- S @ X^T, X lower triangular (only k <= j contributes)
-  double* S = A + (k0 + (int64_t)blockIdx.x * NB) * ld + k0;
+  // slab solve: S <- S @ X^T, X lower triangular
   __syncthreads();
-  for (int t = tid; t < NB * NB; t += 128) {
-    const int i = t / NB, j = t % NB;
-    L[i][j] = S[i * ld + j];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int t = tid + k * 128;
+    L[t >> 6][t & 63] = sv[k];
   }
   __syncthreads();
   const int ri = (tid >> 3) * 4, cj = (tid & 7) * 8;

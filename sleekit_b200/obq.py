@@ -141,11 +141,13 @@ def _quantize_opt_block(Q, E, Hinv, quantizer, min_block_size, num_blocks):
     blocking does not matter)."""
     if cv.is_tensor(Q):
         u64 = cv.to_dev(Hinv, torch.float64)
-        ops.gptq_sweep(Q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks, e=E)
+        ops.gptq_sweep(Q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks, e=E,
+                       exact_leaf=True)
         return
     q = cv.to_dev(Q, torch.float32)
     u64 = cv.to_dev(Hinv, torch.float64)
-    q, e = ops.gptq_sweep(q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks)
+    q, e = ops.gptq_sweep(q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks,
+                          exact_leaf=True)
     Q[...] = cv.to_host(q)
     E[...] = cv.to_host(e)
 

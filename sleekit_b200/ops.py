@@ -368,7 +368,7 @@ def permute_cols(src, idx, scatter=False):
 
 
 @_timed("hinv")
-def hinv(h, order=None, dampval=None, want64=True, want32=True):
+def hinv(h, order=None, dampval=None, want64=False, want32=True):
     """Upper factor U of the inverse of (h + dampval*I)[order][:, order]; returns (u64, u32, info)."""
     _chk(h)
     n = h.shape[0]
@@ -390,16 +390,18 @@ def hinv(h, order=None, dampval=None, want64=True, want32=True):
 
 
 @_timed("gptq_sweep")
-def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None):
-    """In place on q ([rows, n] scaled, permuted weights -> quantized values); returns (q, e)."""
+def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None, exact_leaf=False):
+    """In place on q ([rows, n] scaled, permuted weights -> quantized values); returns (q, e).
+    exact_leaf=True reproduces the reference's fp64/fp32 leaf arithmetic bit for bit from u64."""
     cb = device_codebook(cb)
     _chk(q, torch.float32)
-    _chk(u64, torch.float64)
     _chk(u32, torch.float32)
+    if exact_leaf:
+        _chk(u64, torch.float64)
     if e is None:
         e = torch.empty_like(q)
-    _lib.call("slk_gptq_sweep_f32", _ptr(q), _ptr(e), q.shape[0], q.shape[1], _ptr(u64), _ptr(u32), cb.ref,
-              int(leaf), int(fanout), _stream())
+    _lib.call("slk_gptq_sweep_f32", _ptr(q), _ptr(e), q.shape[0], q.shape[1], _ptr(u64) if exact_leaf else None,
+              _ptr(u32), cb.ref, int(leaf), int(fanout), 1 if exact_leaf else 0, _stream())
     return q, e
 
 

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .scaling import quantize_scaled_device, search_scale_device
+from .scaling import quantize_scaled_device
 from .statistics import _device_scaling
 
 
@@ -34,7 +34,7 @@ class LayerSetQuantizer:
         err = ops.mean(ops.hweighted_error(W, q, H))
         return q, sc, err
 
-    def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True):
+    def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True, _in_capture=False):
         """Ws[i] [r_i, n_i] fp32, Hs[i] [n_i, n_i] fp32 on the device.  Returns (quantized
         weights, scales, errors) -- errors as one fp32 device vector.  Nothing synchronises."""
         L = len(Ws)
@@ -54,10 +54,23 @@ class LayerSetQuantizer:
                 errs[i:i + 1].copy_(e.reshape(1))
                 if keep_outputs:
                     outs[i], scales[i] = q, sc
-                    q.record_stream(main)
-                    sc.record_stream(main)
+                    if not _in_capture:
+                        q.record_stream(main)
+                        sc.record_stream(main)
         for st in self.streams[: min(S, L)]:
             done = torch.cuda.Event()
             done.record(st)
             main.wait_event(done)
         return outs, scales, errs
+
+    def capture(self, Ws, Hs):
+        """Record one pass over the layer set into a CUDA graph (the side streams become parallel
+        branches) and return (graph, errors, quantized weights).  graph.replay() re-runs the whole
+        pass on the current contents of Ws / Hs with no per-kernel CPU launch cost; outputs are
+        rewritten in place at every replay.  Call once after a warm-up pass."""
+        L = len(Ws)
+        errs = torch.empty(L, dtype=torch.float32, device=Ws[0].device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs, _, _ = self(Ws, Hs, errs_out=errs, keep_outputs=True, _in_capture=True)
+        return graph, errs, outs

@@ -123,9 +123,18 @@ def _compute_mse(H, E):
     return cv.back(out, E)
 
 
+_FACTOR_CACHE = {}
+
+
 def _factors(min_factor, max_factor, grid_size, dev):
-    grid = np.linspace(min_factor, max_factor, grid_size, dtype=np.float32)  # scaling.py:124
-    return torch.from_numpy(grid).to(dev)
+    """The fp32 grid of scaling.py:124 on the device (cached: a few hundred bytes per setting, and
+    no host->device copy is then needed inside a CUDA-graph capture)."""
+    key = (float(min_factor), float(max_factor), int(grid_size), str(dev))
+    t = _FACTOR_CACHE.get(key)
+    if t is None:
+        grid = np.linspace(min_factor, max_factor, grid_size, dtype=np.float32)  # scaling.py:124
+        t = _FACTOR_CACHE[key] = torch.from_numpy(grid).to(dev)
+    return t
 
 
 def search_scale_device(Wd, codebook, Hd=None, min_factor=0.05, max_factor=1.0, grid_size=100):

@@ -39,7 +39,7 @@ def test_argument_errors_are_reported_not_crashed():
     rc = lib.slk_round_f32(None, 4, ctypes.byref(cb), 0, None, None, None)
     assert rc == -1
     assert b"codebook" in lib.slk_last_error() or b"size" in lib.slk_last_error()
-    rc = lib.slk_gptq_sweep_f32(None, None, 4, 4, None, None, ctypes.byref(_lib.SlkCodebook(0, 4, -1.0, 1.0, 2 / 3, None, None)), 64, 8, None)
+    rc = lib.slk_gptq_sweep_f32(None, None, 4, 4, None, None, ctypes.byref(_lib.SlkCodebook(0, 4, -1.0, 1.0, 2 / 3, None, None)), 64, 8, 0, None)
     assert rc == -1 and b"leaf" in lib.slk_last_error()
 
 
