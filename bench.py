@@ -30,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# independent layers run as parallel graph branches / streams: give them distinct hardware queues
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "gptq_weights_quantized_per_s"
 UNIT = "weights/s"
@@ -50,7 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-row-div", type=int, default=4, help="CPU sample: 1/div of each layer's rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=24, help="CUDA streams the independent layers are spread over")
+    ap.add_argument("--streams", type=int, default=72, help="CUDA streams the independent layers are spread over")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 

@@ -187,6 +187,19 @@ int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, in
 int slk_bias_delta_f32(const float* w, const float* wq, const float* mean, int64_t r, int64_t n,
                        float* delta, void* stream);
 
+/* ---- tensor-core GEMM core (tcgen05 + TMEM + TMA, 3xTF32 split, fp32-faithful) -----------------
+ * D[M, N] = (A [- A2])[M, K] * B[N, K]^T, both operands fp32 K-major with pitches lda / ldb.
+ * epilogue 0: C = alpha*D        1: C += alpha*D (obq.py:137 with alpha = -1)
+ *          2: C = C*keep + D/count (statistics.py:82-87)
+ *          3: C[m, tile] = sum_n D[m, n] * rowdot[m, n] over each 128-column tile (obq.py:95)
+ * Used internally by the K1 / K3 / K6 / K7 entry points when shapes and alignment allow
+ * (pitches multiple of 4, 16-byte aligned bases); exported for tests and benchmarks. */
+size_t slk_tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K);
+int slk_tc_gemm_f32(int32_t epilogue, const float* a, const float* a2, int64_t lda, const float* b,
+                    int64_t ldb, float* c, int64_t ldc, const float* rowdot, int64_t ldr, int64_t M,
+                    int64_t N, int64_t K, float alpha, float keep, float count, void* ws,
+                    size_t ws_bytes, int32_t* error_flag, void* stream);
+
 /* Self-test (tests only): for each of `count` divisors, compares the kernels' fast exact divide
  * with the IEEE divide over all 2^32 dividends; mismatches[i] must come back 0. */
 int slk_selftest_fastdiv_f32(const float* divisors, int32_t count, uint64_t* mismatches, void* stream);

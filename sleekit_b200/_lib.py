@@ -76,6 +76,9 @@ SIGNATURES = {
     "slk_local_search_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _P]),
     "slk_bias_delta_f32": (_INT, [_P, _P, _P, _I64, _I64, _P, _P]),
     "slk_selftest_fastdiv_f32": (_INT, [_P, _I32, _P, _P]),
+    "slk_tc_gemm_ws_bytes": (_SZ, [_I64, _I64, _I64]),
+    "slk_tc_gemm_f32": (_INT, [_I32, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, C.c_float, C.c_float,
+                               C.c_float, _P, _SZ, _P, _P]),
 }
 
 
