@@ -128,8 +128,10 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
  * x: [S, n] with row stride ldx (samples are rows).  Updates, in place,
  *   mean = mean*keep + colsum(x)/new_count ;  hess = hess*keep + x^T x/new_count
  * keep = old_count/(old_count+S), new_count = old_count+S (both given by caller). */
+size_t slk_hessian_accum_ws_bytes(int64_t S, int64_t n);
 int slk_hessian_accum_f32(const float* x, int64_t S, int64_t n, int64_t ldx, float* hess,
-                          float* mean, double keep, double new_count, void* stream);
+                          float* mean, double keep, double new_count, void* ws, size_t ws_bytes,
+                          void* stream);
 /* remove_input_bias  H - outer(m, m)                        obq.py:14-25 */
 int slk_remove_input_bias_f32(const float* h, const float* m, int64_t n, float* out, void* stream);
 int slk_remove_input_bias_f64(const double* h, const double* m, int64_t n, double* out, void* stream);

@@ -4,6 +4,7 @@
 //   slk_gain_*                 compute_gain                      obq.py:220-231
 //   slk_scale_search_fullh_f32 compute_min_mse_scaling, 2-D H    scaling.py:98-134
 #include "gemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace slk {
 
@@ -128,12 +129,30 @@ extern "C" {
 
 size_t slk_hweighted_error_ws_bytes(int64_t r, int64_t n, int32_t elem_bytes) {
   int64_t tiles = elem_bytes == 8 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
-  return (size_t)(r * tiles) * (size_t)elem_bytes + 256;
+  size_t bytes = align256((size_t)(r * tiles) * (size_t)elem_bytes + 256);
+  if (elem_bytes == 4) bytes += tc_gemm_ws_bytes(r, n, n);   // hi/lo operand copies of the tensor-core path
+  return bytes;
 }
 
 int slk_hweighted_error_f32(const float* w, const float* q, const float* h, int64_t r, int64_t n, void* ws,
                             size_t ws_bytes, float* out, void* stream) {
-  return hweighted_error_impl<float>(w, q, h, r, n, ws, ws_bytes, out, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (r >= 1 && n >= 32 && w && h && out && ws && tc_gemm_usable(w, n, h, n) && (!q || (uintptr_t)q % 16 == 0) &&
+      ws_bytes >= slk_hweighted_error_ws_bytes(r, n, 4)) {
+    // tensor-core path: ((W-Q) @ H) via tcgen05 (H symmetric: H is its own K-major B operand),
+    // the row dot with (W-Q) fused in the epilogue, then the fixed-order reduce over column tiles
+    const int64_t tiles = ceil_div(n, TC_TILE_N);
+    const size_t part_bytes = align256((size_t)(r * rowdot_tiles<float>(n)) * 4 + 256);
+    TcParams p;
+    p.C = (float*)ws; p.ldc = tiles; p.R = w; p.R2 = q; p.ldr = n; p.M = r; p.N = n; p.K = n;
+    p.alpha = 1.0f; p.keep = 0.0f; p.count = 1.0f; p.error_flag = nullptr;
+    int rc = tc_gemm_f32(TC_ROWDOT, w, q, n, h, n, p, (char*)ws + part_bytes, ws_bytes - part_bytes, st);
+    if (rc) return rc;
+    rowdot_reduce_kernel<float><<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)ws, r, tiles, out);
+    SLK_LAUNCH_CHECK();
+    return SLK_OK;
+  }
+  return hweighted_error_impl<float>(w, q, h, r, n, ws, ws_bytes, out, st);
 }
 int slk_hweighted_error_f64(const double* w, const double* q, const double* h, int64_t r, int64_t n, void* ws,
                             size_t ws_bytes, double* out, void* stream) {
@@ -149,12 +168,22 @@ int slk_gain_f64(const double* w, const double* q, const double* h, const double
   return gain_impl<double>(w, q, h, cand, r, n, out, (cudaStream_t)stream);
 }
 
+size_t slk_hessian_accum_ws_bytes(int64_t S, int64_t n) { return tc_gemm_at_ws_bytes(n, S) + 256; }
+
 int slk_hessian_accum_f32(const float* x, int64_t S, int64_t n, int64_t ldx, float* hess, float* mean, double keep,
-                          double new_count, void* stream) {
+                          double new_count, void* ws, size_t ws_bytes, void* stream) {
   SLK_REQUIRE(x && hess && mean && S >= 1 && n >= 1 && ldx >= n, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   colsum_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(x, S, n, ldx, mean, (float)keep, (float)new_count);
   SLK_LAUNCH_CHECK();
+  if (n >= 64 && S >= 32 && ws && ws_bytes >= slk_hessian_accum_ws_bytes(S, n) && tc_gemm_usable(hess, 4, hess, 4)) {
+    // tensor-core path: X is split and transposed once into K-major hi/lo [n, S]; both operands of
+    // X^T X read that same copy; H = H*keep + D/count fused in the epilogue (statistics.py:82-87)
+    TcParams p;
+    p.C = hess; p.ldc = n; p.R = nullptr; p.R2 = nullptr; p.ldr = 0; p.M = n; p.N = n; p.K = S;
+    p.alpha = 1.0f; p.keep = (float)keep; p.count = (float)new_count; p.error_flag = nullptr;
+    return tc_gemm_at_f32(TC_HESS_SYM, x, ldx, p, ws, ws_bytes, st);
+  }
   // H = H*keep + X^T X / count : A = X^T (stored [K=S, M=n]), B = X ([K=S, N=n])
   GemmParams<float> p = gemm_params<float>(x, ldx, x, ldx, hess, n, n, n, S);
   p.keep = (float)keep;

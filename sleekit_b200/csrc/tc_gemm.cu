@@ -18,9 +18,10 @@
 // Pipeline: STAGES-deep ring of {full, empty} mbarriers between TMA and MMA; a 2-deep ring of
 // {hi_full, hi_empty} between MMA and epilogue (see TC_KC).  TMEM: 2 x BN columns of hi*hi
 // accumulators + BN columns of cross terms, 128 lanes each.
-#include "common.cuh"
+#include "tc_gemm.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace slk {
 
@@ -29,15 +30,6 @@ constexpr int TC_BK = 32;            // 32 fp32 = 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 8;         // kind::tf32: 32 bytes of K per instruction
 constexpr int TC_THREADS = 192;
 
-enum TcEpilogue { TC_STORE = 0, TC_ACCUM = 1, TC_HESS = 2, TC_ROWDOT = 3 };
-
-struct TcParams {
-  float* C; int64_t ldc;         // TC_STORE / TC_ACCUM / TC_HESS: [M, N]; TC_ROWDOT: partials [M, tiles_n]
-  const float* R; int64_t ldr;   // TC_ROWDOT: the matrix whose rows are dotted with the product rows
-  int64_t M, N, K;
-  float alpha, keep, count;
-  int* error_flag;               // set (and the kernel traps) if a barrier wait exceeds its budget
-};
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,6 +148,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  if (EPI == TC_HESS_SYM && n0 + BN <= m0) return;   // strictly-lower tile of a symmetric product
   const int num_kb = (int)((p.K + TC_BK - 1) / TC_BK);
   const int num_chunks = (num_kb + TC_KC - 1) / TC_KC;
 
@@ -253,11 +246,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (!row_ok || col >= p.N) continue;
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(run[c0 + j], v[j]);
-      if (EPI == TC_ROWDOT) {
+      if (EPI == TC_HESS_SYM) {
+        // symmetric accumulate: only n >= m is computed here; each value is written to (m, n) and
+        // mirrored to (n, m) (coalesced: consecutive lanes are consecutive m), so H stays
+        // symmetric to the bit and the tiles below the diagonal are never launched
+        float* cc = p.C + row * p.ldc + col;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t n = col + j;
+          if (n < p.N && n >= row) {
+            const float o = __fadd_rn(__fmul_rn(cc[j], p.keep), __fdiv_rn(v[j], p.count));
+            cc[j] = o;
+            p.C[n * p.ldc + row] = o;
+          }
+        }
+      } else if (EPI == TC_ROWDOT) {
         const float* rr = p.R + row * p.ldr + col;
+        const float* r2 = p.R2 ? p.R2 + row * p.ldr + col : nullptr;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (col + j < p.N) dot = __fmaf_rn(v[j], __ldg(rr + j), dot);
+          if (col + j < p.N) {
+            float e = __ldg(rr + j);
+            if (r2) e = __fsub_rn(e, __ldg(r2 + j));
+            dot = __fmaf_rn(v[j], e, dot);
+          }
       } else {
         float* cc = p.C + row * p.ldc + col;
         const bool vec = (col + 16 <= p.N) && ((((uintptr_t)cc) & 15) == 0);
@@ -378,6 +390,12 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }
 
 bool tc_gemm_usable(const void* a, int64_t lda, const void* b, int64_t ldb) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("SLK_DISABLE_TC");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (disabled) return false;
   return ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && encode_fn() != nullptr;
 }
 
@@ -438,6 +456,31 @@ size_t tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K) {
   return (size_t)(2 * M * Kp + 2 * N * Kp) * sizeof(float) + 1024;
 }
 
+// D = At^T * At (M = N = columns of At): one transposing split feeds both operands.
+int tc_gemm_at_f32(int epi, const float* At, int64_t ldat, TcParams p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t Kp = (p.K + 3) / 4 * 4;
+  const size_t elems = (size_t)p.M * Kp;
+  SLK_REQUIRE(p.M == p.N, "tc_gemm_at: square output expected");
+  SLK_REQUIRE(ws && ws_bytes >= 2 * elems * sizeof(float) + 1024, "tc_gemm_at workspace too small");
+  float* hi = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  float* lo = hi + elems;
+  dim3 grid((unsigned)ceil_div(p.M, 32), (unsigned)ceil_div(p.K, 32));
+  split_tf32_transpose_kernel<<<grid, 256, 0, st>>>(At, p.K, p.M, ldat, Kp, hi, lo);
+  SLK_LAUNCH_CHECK();
+  switch (epi) {
+    case TC_STORE: return tc_launch<128, TC_STORE>(hi, lo, Kp, hi, lo, Kp, p, st);
+    case TC_HESS: return tc_launch<128, TC_HESS>(hi, lo, Kp, hi, lo, Kp, p, st);
+    case TC_HESS_SYM: return tc_launch<128, TC_HESS_SYM>(hi, lo, Kp, hi, lo, Kp, p, st);
+  }
+  SLK_REQUIRE(false, "tc_gemm_at: unsupported epilogue %d", epi);
+  return SLK_ERR_ARG;
+}
+
+size_t tc_gemm_at_ws_bytes(int64_t M, int64_t K) {
+  const int64_t Kp = (K + 3) / 4 * 4;
+  return (size_t)(2 * M * Kp) * sizeof(float) + 1024;
+}
+
 }  // namespace slk
 
 using namespace slk;
@@ -456,7 +499,7 @@ int slk_tc_gemm_f32(int32_t epilogue, const float* a, const float* a2, int64_t l
   SLK_REQUIRE(epilogue != TC_ROWDOT || rowdot != nullptr, "row-dot epilogue needs the row matrix");
   SLK_REQUIRE(encode_fn() != nullptr, "TMA descriptors unavailable (driver too old?)");
   TcParams p;
-  p.C = c; p.ldc = ldc; p.R = rowdot; p.ldr = ldr; p.M = M; p.N = N; p.K = K;
+  p.C = c; p.ldc = ldc; p.R = rowdot; p.R2 = nullptr; p.ldr = ldr; p.M = M; p.N = N; p.K = K;
   p.alpha = alpha; p.keep = keep; p.count = count; p.error_flag = error_flag;
   return tc_gemm_f32(epilogue, a, a2, lda, b, ldb, p, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -1,0 +1,31 @@
+// Interface of the tcgen05 GEMM core (tc_gemm.cu) for the other translation units.
+#pragma once
+
+#include "common.cuh"
+
+namespace slk {
+
+enum TcEpilogue { TC_STORE = 0, TC_ACCUM = 1, TC_HESS = 2, TC_ROWDOT = 3, TC_HESS_SYM = 4 };
+
+struct TcParams {
+  float* C; int64_t ldc;         // TC_STORE / TC_ACCUM / TC_HESS: [M, N]; TC_ROWDOT: partials [M, tiles_n]
+  const float* R; const float* R2; int64_t ldr;   // TC_ROWDOT: rows of (R - R2) are dotted with the product rows
+  int64_t M, N, K;
+  float alpha, keep, count;
+  int* error_flag;               // set (and the kernel traps) if a barrier wait exceeds its budget
+};
+
+constexpr int TC_TILE_N = 128;
+
+// true when the tensor-core path can take these operands (16-byte aligned, pitches multiple of 4,
+// driver exposes cuTensorMapEncodeTiled, not disabled by SLK_DISABLE_TC=1)
+bool tc_gemm_usable(const void* a, int64_t lda, const void* b, int64_t ldb);
+size_t tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K);
+// D = (A [- A2]) * B^T; A [M, K], B [N, K] fp32 K-major
+int tc_gemm_f32(int epi, const float* A, const float* A2, int64_t lda, const float* B, int64_t ldb, TcParams p,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+// same with A given transposed: At [K, M] (pitch ldat); used by K1 (X^T X with X [S, n])
+int tc_gemm_at_f32(int epi, const float* At, int64_t ldat, TcParams p, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_gemm_at_ws_bytes(int64_t M, int64_t K);
+
+}  // namespace slk

@@ -301,8 +301,10 @@ def hessian_accum(x, hess, mean_vec, keep, new_count):
     _chk(mean_vec, torch.float32)
     S, n = x.shape
     assert hess.shape == (n, n) and mean_vec.shape == (n,)
+    nbytes = _lib.load().slk_hessian_accum_ws_bytes(S, n)
+    ws = _ws(nbytes, x.device)
     _lib.call("slk_hessian_accum_f32", _ptr(x), S, n, n, _ptr(hess), _ptr(mean_vec), float(keep), float(new_count),
-              _stream())
+              _ptr(ws), nbytes, _stream())
 
 
 @_timed("remove_input_bias")
