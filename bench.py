@@ -49,9 +49,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="opt-125m")
     ap.add_argument("--layers", type=int, default=0, help="debug: only the first L layers")
-    ap.add_argument("--cpu-row-div", type=int, default=4, help="CPU sample: 1/div of each layer's rows")
+    ap.add_argument("--cpu-row-div", type=int, default=1,
+                    help="CPU sample: 1/div of each layer's rows for the row-linear phases (1 = every row, no extrapolation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--only", default="", choices=["", "big", "small"], help="debug: only layers with n >= 2048 / n < 2048")
     ap.add_argument("--streams", type=int, default=72, help="CUDA streams the independent layers are spread over")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -135,9 +137,11 @@ def run_reference(args):
         meas.append(m)
     wall = time.perf_counter() - t0
     value = weights / (sum(ests) / len(ests))
-    sample = (f"per step: one layer of each distinct shape of block 0 ({sorted(set(shapes[:6]))}), first 1/{args.cpu_row_div} "
-              f"of the rows for the row-linear phases (scale search, sweep, error; scaled back by {args.cpu_row_div}x), "
-              f"damp+order+fp64 factor in full; whole-block time = sum over its 6 layers; numpy/OpenBLAS on all host cores")
+    sample = (f"per step: block 0 of the workload (6 layers, 7 077 888 weights): one layer of each distinct shape "
+              f"({sorted(set(shapes[:6]))}) is timed"
+              + (" in full (every row)" if args.cpu_row_div == 1 else
+                 f" on the first 1/{args.cpu_row_div} of its rows for the row-linear phases (scaled back), fp64 factor in full")
+              + "; the 4 identical [768,768] layers count 4x; numpy/OpenBLAS on all host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
@@ -232,6 +236,8 @@ def run_ours(args):
     shapes = wl.layer_shapes(args.model)
     if args.layers:
         shapes = shapes[: args.layers]
+    if args.only:
+        shapes = [sh for sh in shapes if (sh[1] >= 2048) == (args.only == "big")]
     L = len(shapes)
     weights = sum(r * n for r, n in shapes)
     cb = codebook.UniformCodebook(CODEBOOK, -1, 1)
@@ -310,12 +316,19 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
+    # per-operation device time from a SERIAL eager pass (one stream: event pairs then bracket
+    # exactly one operation's kernels; on overlapping streams they would include each other)
+    serial = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=DAMP, nb_ls_moves=0, grid_size=GRID,
+                               streams=1)
+    serial(Wd, Hd, errs_out=errs, keep_outputs=False)
+    torch.cuda.synchronize()
     ops.PROFILE = {}
-    step_device()
+    serial(Wd, Hd, errs_out=errs, keep_outputs=False)
     torch.cuda.synchronize()
     phases = ops.profile_totals_ms(ops.PROFILE)
     ops.PROFILE = None
     top = max(phases, key=lambda k: phases[k][0])
+    serial_total_ms = sum(v[0] for v in phases.values())
 
     graph = None
     if not args.no_graph:
@@ -345,7 +358,7 @@ def run_ours(args):
         # which also times the dominant kernel with events on the stream it runs on
         ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
         launches0 = ops.launch_count()
-        step_eager()
+        serial(Wd, Hd, errs_out=errs, keep_outputs=False)
         torch.cuda.synchronize()
         launches_per_step = ops.launch_count() - launches0
         launches = launches_per_step * args.steps
@@ -381,31 +394,56 @@ def run_ours(args):
     roofline = None
     if top_calls:
         per_launch_ms = top_ms / top_calls
+        share = phases[top][0] / serial_total_ms if serial_total_ms else None
+        common = {"kernel": top, "avg_launch_ms": per_launch_ms, "launches_timed": top_calls, "traffic": None,
+                  "share_of_serial_device_time": share}
         if top == "scale_search":
             # reference traffic model = one pass over W per grid point = 4*G bytes/weight
-            alg_bytes = 4.0 * GRID * weights / L
-            note = ("effective GB/s: algorithmic bytes = 4*G bytes per weight (the reference's G passes over W, "
-                    "scaling.py:127-133); the fused kernel reads W once (4 B/weight real DRAM) and is fp32-ALU bound")
-        elif top == "hinv":
-            alg_bytes = sum(8.0 * 3 * n * n for _, n in shapes) / L
-            note = "fp64 factor+inverse: algorithmic bytes = 3 passes over the n^2 fp64 matrix (lower bound)"
+            achieved = 4.0 * GRID * weights / L / (per_launch_ms * 1e-3) / 1e9
+            roofline = dict(common, bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
+                            peak_source=peak_src,
+                            note=("effective GB/s: algorithmic bytes = 4*G bytes per weight (the reference's G passes "
+                                  "over W, scaling.py:127-133); the fused kernel reads W once (4 B/weight of real DRAM "
+                                  "traffic) and is bound by the fp32 pipe"))
+        elif top in ("hinv", "gptq_sweep", "hweighted_error"):
+            if top == "hinv":
+                flop = sum(2.0 * n ** 3 / 3.0 for _, n in shapes) / L     # n^3/3 factor + n^3/3 inverse, fp64
+                a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+                torch.matmul(a, a)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    torch.matmul(a, a)
+                e1.record()
+                torch.cuda.synchronize()
+                peak = 3 * 2.0 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+                psrc = "cuBLAS fp64 GEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)"
+                note = ("fp64 damp+permute+factor+inverse (K2): algorithmic 2n^3/3 fp64 flop per layer; small layers "
+                        "are bound by the latency of n/64 dependent panels, not by the FP64 pipe")
+            else:
+                flop = (sum(float(r) * n * n for r, n in shapes) if top == "gptq_sweep"
+                        else sum(2.0 * r * n * n for r, n in shapes)) / L
+                peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+                psrc = "half of the measured bf16 peak (dense TF32 = bf16/2)"
+                note = "algorithmic fp32 flop of the GEMM phase per launch"
+            achieved = flop / (per_launch_ms * 1e-3) / 1e12
+            roofline = dict(common, bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                            peak_source=psrc, note=note)
         else:
-            alg_bytes = 8.0 * weights / L
-            note = "algorithmic bytes = one read + one write of W per launch"
-        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": per_launch_ms, "launches_timed": top_calls,
-                    "share_of_step": top_ms / ms if ms else None, "note": note}
+            achieved = 8.0 * weights / L / (per_launch_ms * 1e-3) / 1e9
+            roofline = dict(common, bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
+                            peak_source=peak_src, note="algorithmic bytes = one read + one write of W per launch")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world >= 1:
         from oracle import sleekit_oracle as orc
 
-        est, bw, meas = cpu_sample(orc, wl, args.model, args.cpu_row_div)
+        est, bw, meas = cpu_sample(orc, wl, args.model, 1)
         cpu_baseline = {"value": bw / est, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                        "sample": (f"one layer of each distinct shape of block 0, first 1/{args.cpu_row_div} of rows for the "
-                                   f"row-linear phases (extrapolated), fp64 factor in full; {meas:.1f} s of CPU work")}
+                        "sample": (f"block 0 of the workload in full (every row): one layer of each of its 3 distinct "
+                                   f"shapes timed, the 4 identical [768,768] layers counted 4x; {meas:.1f} s of CPU work, "
+                                   f"numpy/OpenBLAS on all host cores")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -417,9 +455,10 @@ def run_ours(args):
                    "l2": "inputs (W+H ~0.93 GB per rank) are larger than the 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "layer_error_mean": layer_err,
-        "phases_ms_per_step": {k: round(v[0], 3) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
+        "serial_phases_ms_per_step": {k: round(v[0], 3) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
         "xtx": {"tflops": xtx_flop / (xtx_ms * 1e-3) / 1e12 if xtx_ms else None, "ms_total": xtx_ms,
-                "note": "K1 X^T X over the 72 calibration matrices, algorithmic 2*S*n^2 flop, fp32 CUDA-core path"},
+                "note": ("K1 X^T X over the 72 calibration matrices (S=2048), algorithmic 2*S*n^2 flop; tcgen05 3xTF32, "
+                         "upper tiles only, incl. the hi/lo split+transpose pass; n=768 layers are launch-bound")},
         "wall_ms_per_step": wall / args.steps,
     }
     print(json.dumps(line), flush=True)

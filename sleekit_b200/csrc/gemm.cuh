@@ -48,9 +48,8 @@ template <typename T> struct GemmTile { };
 template <> struct GemmTile<float> { static constexpr int H = 4; static constexpr int PAD = 4; };
 template <> struct GemmTile<double> { static constexpr int H = 2; static constexpr int PAD = 4; };
 
-template <typename T, bool A_T, bool B_T, int EPI>
+template <typename T, int H, bool A_T, bool B_T, int EPI>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmParams<T> p) {
-  constexpr int H = GemmTile<T>::H;
   constexpr int BM = 32 * H, BN = 32 * H, BK = 8;
   constexpr int LDS_ = BM + GemmTile<T>::PAD;
   constexpr int PER = BM * BK / 256;  // elements of each operand tile per thread
@@ -242,9 +241,17 @@ template <typename T> static inline int gemm_bm() { return 32 * GemmTile<T>::H; 
 template <typename T, bool A_T, bool B_T, int EPI>
 static inline int gemm_launch(const GemmParams<T>& p, int batch, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return SLK_OK;
-  const int bm = gemm_bm<T>();
-  dim3 grid((unsigned)ceil_div(p.N, bm), (unsigned)ceil_div(p.M, bm), (unsigned)batch);
-  gemm_kernel<T, A_T, B_T, EPI><<<grid, 256, 0, st>>>(p);
+  // fp64: 8x8 register tiles (128x128 CTA tile, 4 DFMA per shared-memory load) once the problem is
+  // large enough to fill the GPU with such tiles; 4x4 (64x64) otherwise.  fp32 always 8x8.
+  constexpr int HS = GemmTile<T>::H;
+  if (false && sizeof(T) == 8 && EPI != EPI_ROWDOT && p.M >= 1024 && p.N >= 1024) {  // measured slower on B200 (1 CTA/SM)
+    constexpr int HL = 4;
+    dim3 grid((unsigned)ceil_div(p.N, 32 * HL), (unsigned)ceil_div(p.M, 32 * HL), (unsigned)batch);
+    gemm_kernel<T, HL, A_T, B_T, EPI><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)ceil_div(p.N, 32 * HS), (unsigned)ceil_div(p.M, 32 * HS), (unsigned)batch);
+    gemm_kernel<T, HS, A_T, B_T, EPI><<<grid, 256, 0, st>>>(p);
+  }
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

@@ -8,6 +8,8 @@
 // with exact-product fmaf accumulation on the fp32 rounding of U (parity-safe).
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 namespace slk {
 
 constexpr int LEAF_ROWS = 64;  // rows (threads) per CTA of the leaf kernel
@@ -181,6 +183,128 @@ __global__ void __launch_bounds__(LEAF_ROWS) sweep_leaf32_kernel(float* __restri
   leaf_phase32<8>(q, sh, 24, width, g, fstep, fastq, qrow, erow);
 }
 
+// ---- fused sweep: one launch per layer --------------------------------------------------------
+// Rows never interact, so a CTA that owns 32 rows can walk all columns by itself: for every
+// 32-column block it (1) forms the block left-looking, Qb = W[:, blk] - E[:, :a] @ U[:a, blk]
+// (all 256 threads; E and U stream through a 4-stage cp.async ring, E being this CTA's own rows
+// written earlier and read back through L2), (2) sweeps the block with one thread per row (the
+// fp32 leaf above).  No trailing read-modify-write of Q, no dependent launches: 1 launch instead
+// of the 47 (n = 768) to 255 (n = 3072) of the recursion.  Same algebra as obq.py:121-137 -- the
+// propagated terms are summed per block instead of per recursion level.
+constexpr int FR = 32;     // rows per CTA
+constexpr int FT = 256;    // threads per CTA
+constexpr int FST = 4;     // cp.async stages
+
+struct FusedSmem {
+  float E[FST][32][36];    // [row][k], rows padded to 36 floats: 16-byte aligned, bank-conflict free
+  float U[FST][32][32];    // [k][col]
+  float Qs[32][33];
+  LeafShared32 leaf;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r, int64_t n,
+                                                         const float* __restrict__ U, DevGrid<float> g) {
+  __shared__ __align__(16) FusedSmem sm;
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * FR;
+  const int lrow = tid >> 3, seg = tid & 7;          // GEMM phase: thread -> (row, 4 columns) and (k, 4 columns)
+  const int64_t grow = row0 + lrow;
+  const bool aligned = (n % 4 == 0) && ((((uintptr_t)E) & 15) == 0) && ((((uintptr_t)U) & 15) == 0);
+  const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
+  const bool fastq = (g.kind == 0) && fstep.ok;
+
+  for (int64_t a = 0; a < n; a += 32) {
+    const int width = (int)((n - a) < 32 ? (n - a) : 32);
+    const bool fullw = aligned && width == 32;
+    // ---- (1) Qb = W[:, a:a+32] - E[:, :a] @ U[:a, a:a+32] -----------------------------------
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nchunks = (int)(a / 32);
+    auto load_chunk = [&](int c) {
+      const int st = c % FST;
+      const int64_t k0 = (int64_t)c * 32;
+      // E chunk: row lrow, k0 + 4*seg .. +3
+      float* de = &sm.E[st][lrow][seg * 4];
+      if (aligned && grow < r) cp_async16(de, E + grow * n + k0 + seg * 4);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) de[j] = grow < r ? __ldcg(E + grow * n + k0 + seg * 4 + j) : 0.0f;
+      }
+      // U chunk: row k0 + lrow, columns a + 4*seg .. +3
+      float* du = &sm.U[st][lrow][seg * 4];
+      const float* su = U + (k0 + lrow) * n + a + seg * 4;
+      if (fullw) cp_async16(du, su);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) du[j] = (seg * 4 + j < width) ? __ldg(su + j) : 0.0f;
+      }
+    };
+    for (int c = 0; c < FST - 1; ++c) {
+      if (c < nchunks) load_chunk(c);
+      cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      cp_async_wait<FST - 2>();
+      __syncthreads();
+      if (c + FST - 1 < nchunks) load_chunk(c + FST - 1);
+      cp_async_commit();
+      const int st = c % FST;
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        const float e = sm.E[st][lrow][kk];
+        const float4 u = *reinterpret_cast<const float4*>(&sm.U[st][kk][seg * 4]);
+        acc[0] = __fmaf_rn(e, u.x, acc[0]);
+        acc[1] = __fmaf_rn(e, u.y, acc[1]);
+        acc[2] = __fmaf_rn(e, u.z, acc[2]);
+        acc[3] = __fmaf_rn(e, u.w, acc[3]);
+      }
+    }
+    cp_async_wait<0>();
+    // diagonal block of U for the leaf (zero padded to 64 columns), and the block itself
+    {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = tid + k * FT, i = t >> 5, j = t & 31;
+        sm.leaf.U[i][j] = (i < width && j < width) ? __ldg(U + (a + i) * n + (a + j)) : ((i == j) ? 1.0f : 0.0f);
+        sm.leaf.U[i][32 + j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = seg * 4 + j;
+        float w = (grow < r && col < width) ? __ldcg(Q + grow * n + a + col) : 0.0f;
+        sm.Qs[lrow][col] = __fsub_rn(w, acc[j]);
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const FastDivF f = make_fastdiv(sm.leaf.U[tid][tid]);
+      sm.leaf.Uy[tid] = f.y;
+      sm.leaf.Uok[tid] = f.ok;
+    }
+    __syncwarp();
+    // ---- (2) leaf: warp 0, one thread per row ------------------------------------------------
+    if (tid < 32 && row0 + tid < r) {
+      float q[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) q[k] = sm.Qs[tid][k];
+      float* qrow = Q + (row0 + tid) * n + a;
+      float* erow = E + (row0 + tid) * n + a;
+      leaf_phase32<32>(q, sm.leaf, 0, width, g, fstep, fastq, qrow, erow);
+      leaf_phase32<24>(q, sm.leaf, 8, width, g, fstep, fastq, qrow, erow);
+      leaf_phase32<16>(q, sm.leaf, 16, width, g, fstep, fastq, qrow, erow);
+      leaf_phase32<8>(q, sm.leaf, 24, width, g, fstep, fastq, qrow, erow);
+    }
+    __syncthreads();   // E of this block is visible to the whole CTA before the next block reads it
+  }
+}
+
 struct SweepCtx {
   float* Q; float* E; int64_t r, n;
   const double* u64; const float* u32;
@@ -234,6 +358,16 @@ extern "C" int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, cons
   SLK_REQUIRE(fanout >= 2, "fanout %d < 2", fanout);
   if (r == 0) return SLK_OK;
   SLK_REQUIRE(q && e && u32 && (u64 || !exact_leaf), "NULL pointer");
+  static int fused_mode = -1;   // SLK_SWEEP_FUSED=0 forces the multi-launch recursion (A/B testing)
+  if (fused_mode < 0) {
+    const char* ev = getenv("SLK_SWEEP_FUSED");
+    fused_mode = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  if (!exact_leaf && leaf == 32 && fused_mode) {
+    sweep_fused_kernel<<<(unsigned)ceil_div(r, FR), FT, 0, (cudaStream_t)stream>>>(q, e, r, n, u32, make_grid<float>(cb));
+    SLK_LAUNCH_CHECK();
+    return SLK_OK;
+  }
   SweepCtx c;
   c.Q = q; c.E = e; c.r = r; c.n = n; c.u64 = u64; c.u32 = u32;
   c.g = make_grid<float>(cb);
