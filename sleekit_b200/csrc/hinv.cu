@@ -10,11 +10,19 @@
 // Steps: gather -> for every 64-wide panel { diag block factor+inverse (1 CTA, smem) ; panel
 // solve as a GEMM with the block inverse ; trailing symmetric update (lower tiles only) }
 // -> log2(npad/64) levels of batched triangular products -> flip + (fp64|fp32) store.
-#include "gemm.cuh"
+#include "dgemm_mma.cuh"
 
 namespace slk {
 
 constexpr int NB = 64;
+
+// fp64 products of K2: FP64 tensor path (DMMA) when the operands qualify (always inside K2: all
+// extents are multiples of 64), DFMA tiles otherwise.
+template <bool B_T, int EPI>
+static int dgemm(const GemmParams<double>& p, int batch, cudaStream_t st) {
+  if (dgemm_mma_ok(p)) return dgemm_mma_launch<B_T, EPI>(p, batch, st);
+  return gemm_launch<double, false, B_T, EPI>(p, batch, st);
+}
 
 // A[i, j] = flip(H_opt[order][:, order])[i, j], identity outside n
 template <typename TS>
@@ -263,7 +271,7 @@ static int hinv_factor_and_invert(double* A, double* Li, double* T, int64_t n, i
       GemmParams<double> p = gemm_params<double>(P, ld, P, ld, A + (k0 + NB) * ld + (k0 + NB), ld, rest, rest, NB);
       p.alpha = -1.0;
       p.lower_only = 1;
-      int rc = gemm_launch<double, false, true, EPI_ACCUM>(p, 1, st);
+      int rc = dgemm<true, EPI_ACCUM>(p, 1, st);
       if (rc) return rc;
     }
   }
@@ -279,7 +287,7 @@ static int hinv_factor_and_invert(double* A, double* Li, double* T, int64_t n, i
       p.strideA = p.strideB = p.strideC = stride;
       p.M_last = m_last; p.K_last = s;
       p.k_lo_from_n = 1;
-      int rc = gemm_launch<double, false, false, EPI_STORE>(p, (int)pairs, st);
+      int rc = dgemm<false, EPI_STORE>(p, (int)pairs, st);
       if (rc) return rc;
     }
     {
@@ -288,7 +296,7 @@ static int hinv_factor_and_invert(double* A, double* Li, double* T, int64_t n, i
       p.M_last = m_last; p.K_last = m_last;
       p.alpha = -1.0;
       p.k_hi_from_m = 1;
-      int rc = gemm_launch<double, false, false, EPI_STORE>(p, (int)pairs, st);
+      int rc = dgemm<false, EPI_STORE>(p, (int)pairs, st);
       if (rc) return rc;
     }
   }
