@@ -184,21 +184,25 @@ __global__ void __launch_bounds__(LEAF_ROWS) sweep_leaf32_kernel(float* __restri
 }
 
 // ---- fused sweep: one launch per layer --------------------------------------------------------
-// Rows never interact, so a CTA that owns 32 rows can walk all columns by itself: for every
+// Rows never interact, so a CTA that owns R rows can walk all columns by itself: for every
 // 32-column block it (1) forms the block left-looking, Qb = W[:, blk] - E[:, :a] @ U[:a, blk]
 // (all 256 threads; E and U stream through a 4-stage cp.async ring, E being this CTA's own rows
 // written earlier and read back through L2), (2) sweeps the block with one thread per row (the
 // fp32 leaf above).  No trailing read-modify-write of Q, no dependent launches: 1 launch instead
 // of the 47 (n = 768) to 255 (n = 3072) of the recursion.  Same algebra as obq.py:121-137 -- the
 // propagated terms are summed per block instead of per recursion level.
-constexpr int FR = 32;     // rows per CTA
+// R (8, 16 or 32 rows per CTA) is chosen so that the grid covers the SMs; the 256 threads are
+// R x 8 column groups x KG = 32/R k-groups (split-K inside the CTA, reduced through shared memory).
 constexpr int FT = 256;    // threads per CTA
 constexpr int FST = 4;     // cp.async stages
 
+template <int R>
 struct FusedSmem {
-  float E[FST][32][36];    // [row][k], rows padded to 36 floats: 16-byte aligned, bank-conflict free
-  float U[FST][32][32];    // [k][col]
-  float Qs[32][33];
+  static constexpr int KG = 32 / R;
+  float E[FST][KG][R][36];    // [k-group][row][k], rows padded to 36 floats (16-byte aligned, conflict free)
+  float U[FST][KG][32][32];   // [k-group][k][col]
+  float red[KG][R][33];       // split-K partial sums
+  float Qs[R][33];
   LeafShared32 leaf;
 };
 
@@ -210,12 +214,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int R>
 __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r, int64_t n,
                                                          const float* __restrict__ U, DevGrid<float> g) {
-  __shared__ __align__(16) FusedSmem sm;
+  typedef FusedSmem<R> SM;
+  constexpr int KG = SM::KG;
+  constexpr int KSUP = 32 * KG;                       // k covered by one ring stage
+  extern __shared__ __align__(16) unsigned char fused_raw[];
+  SM& sm = *reinterpret_cast<SM*>(fused_raw);
   const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * FR;
-  const int lrow = tid >> 3, seg = tid & 7;          // GEMM phase: thread -> (row, 4 columns) and (k, 4 columns)
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int kg = tid / (R * 8), lt = tid % (R * 8);
+  const int lrow = lt >> 3, seg = lt & 7;
   const int64_t grow = row0 + lrow;
   const bool aligned = (n % 4 == 0) && ((((uintptr_t)E) & 15) == 0) && ((((uintptr_t)U) & 15) == 0);
   const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
@@ -224,73 +234,97 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
   for (int64_t a = 0; a < n; a += 32) {
     const int width = (int)((n - a) < 32 ? (n - a) : 32);
     const bool fullw = aligned && width == 32;
+    // operands of the leaf are requested now and parked in registers: their latency hides
+    // behind the product loop
+    float ud[4], wq[4];
+    {
+      const int i = tid >> 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = seg * 4 + j;
+        ud[j] = (i < width && c < width) ? __ldg(U + (a + i) * n + (a + c)) : ((i == c) ? 1.0f : 0.0f);
+        wq[j] = (kg == 0 && grow < r && c < width) ? __ldcg(Q + grow * n + a + c) : 0.0f;
+      }
+    }
     // ---- (1) Qb = W[:, a:a+32] - E[:, :a] @ U[:a, a:a+32] -----------------------------------
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int nchunks = (int)(a / 32);
-    auto load_chunk = [&](int c) {
+    const int nsup = (int)((a + KSUP - 1) / KSUP);
+    auto load_stage = [&](int c) {
       const int st = c % FST;
-      const int64_t k0 = (int64_t)c * 32;
-      // E chunk: row lrow, k0 + 4*seg .. +3
-      float* de = &sm.E[st][lrow][seg * 4];
-      if (aligned && grow < r) cp_async16(de, E + grow * n + k0 + seg * 4);
-      else {
+      const int64_t k0 = (int64_t)c * KSUP;
+      const int64_t ke = k0 + 32 * kg;               // this thread's k-group for the E piece
+      float* de = &sm.E[st][kg][lrow][seg * 4];
+      if (ke < a) {
+        if (aligned && grow < r) cp_async16(de, E + grow * n + ke + seg * 4);
+        else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) de[j] = grow < r ? __ldcg(E + grow * n + k0 + seg * 4 + j) : 0.0f;
+          for (int j = 0; j < 4; ++j) de[j] = grow < r ? __ldcg(E + grow * n + ke + seg * 4 + j) : 0.0f;
+        }
       }
-      // U chunk: row k0 + lrow, columns a + 4*seg .. +3
-      float* du = &sm.U[st][lrow][seg * 4];
-      const float* su = U + (k0 + lrow) * n + a + seg * 4;
-      if (fullw) cp_async16(du, su);
-      else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) du[j] = (seg * 4 + j < width) ? __ldg(su + j) : 0.0f;
+      for (int j = 0; j < KG; ++j) {                  // U: KG pieces per thread, k-row tid/8 of group j
+        const int64_t ku = k0 + 32 * j;
+        if (ku < a) {
+          float* du = &sm.U[st][j][tid >> 3][seg * 4];
+          const float* su = U + (ku + (tid >> 3)) * n + a + seg * 4;
+          if (fullw) cp_async16(du, su);
+          else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) du[q4] = (seg * 4 + q4 < width) ? __ldg(su + q4) : 0.0f;
+          }
+        }
       }
     };
     for (int c = 0; c < FST - 1; ++c) {
-      if (c < nchunks) load_chunk(c);
+      if (c < nsup) load_stage(c);
       cp_async_commit();
     }
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = 0; c < nsup; ++c) {
       cp_async_wait<FST - 2>();
       __syncthreads();
-      if (c + FST - 1 < nchunks) load_chunk(c + FST - 1);
+      if (c + FST - 1 < nsup) load_stage(c + FST - 1);
       cp_async_commit();
       const int st = c % FST;
+      if ((int64_t)c * KSUP + 32 * kg < a) {
 #pragma unroll
-      for (int kk = 0; kk < 32; ++kk) {
-        const float e = sm.E[st][lrow][kk];
-        const float4 u = *reinterpret_cast<const float4*>(&sm.U[st][kk][seg * 4]);
-        acc[0] = __fmaf_rn(e, u.x, acc[0]);
-        acc[1] = __fmaf_rn(e, u.y, acc[1]);
-        acc[2] = __fmaf_rn(e, u.z, acc[2]);
-        acc[3] = __fmaf_rn(e, u.w, acc[3]);
+        for (int kk = 0; kk < 32; ++kk) {
+          const float e = sm.E[st][kg][lrow][kk];
+          const float4 u = *reinterpret_cast<const float4*>(&sm.U[st][kg][kk][seg * 4]);
+          acc[0] = __fmaf_rn(e, u.x, acc[0]);
+          acc[1] = __fmaf_rn(e, u.y, acc[1]);
+          acc[2] = __fmaf_rn(e, u.z, acc[2]);
+          acc[3] = __fmaf_rn(e, u.w, acc[3]);
+        }
       }
     }
     cp_async_wait<0>();
-    // diagonal block of U for the leaf (zero padded to 64 columns), and the block itself
     {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int t = tid + k * FT, i = t >> 5, j = t & 31;
-        sm.leaf.U[i][j] = (i < width && j < width) ? __ldg(U + (a + i) * n + (a + j)) : ((i == j) ? 1.0f : 0.0f);
-        sm.leaf.U[i][32 + j] = 0.0f;
-      }
+      const int i = tid >> 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int col = seg * 4 + j;
-        float w = (grow < r && col < width) ? __ldcg(Q + grow * n + a + col) : 0.0f;
-        sm.Qs[lrow][col] = __fsub_rn(w, acc[j]);
+        sm.leaf.U[i][seg * 4 + j] = ud[j];
+        sm.leaf.U[i][32 + seg * 4 + j] = 0.0f;
+        sm.red[kg][lrow][seg * 4 + j] = acc[j];
       }
     }
     __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = sm.red[0][lrow][seg * 4 + j];
+#pragma unroll
+        for (int q = 1; q < KG; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
+        sm.Qs[lrow][seg * 4 + j] = __fsub_rn(wq[j], t);
+      }
+    }
     if (tid < 32) {
       const FastDivF f = make_fastdiv(sm.leaf.U[tid][tid]);
       sm.leaf.Uy[tid] = f.y;
       sm.leaf.Uok[tid] = f.ok;
     }
-    __syncwarp();
-    // ---- (2) leaf: warp 0, one thread per row ------------------------------------------------
-    if (tid < 32 && row0 + tid < r) {
+    __syncthreads();
+    // ---- (2) leaf: one thread per row ----------------------------------------------------------
+    if (tid < R && row0 + tid < r) {
       float q[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) q[k] = sm.Qs[tid][k];
@@ -303,6 +337,20 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
     }
     __syncthreads();   // E of this block is visible to the whole CTA before the next block reads it
   }
+}
+
+template <int R>
+static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u32, const DevGrid<float>& g,
+                        cudaStream_t st) {
+  auto kern = sweep_fused_kernel<R>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<R>)));
+    attr_done = true;
+  }
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, g);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
 }
 
 struct SweepCtx {
@@ -364,9 +412,12 @@ extern "C" int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, cons
     fused_mode = (ev && ev[0] == '0') ? 0 : 1;
   }
   if (!exact_leaf && leaf == 32 && fused_mode) {
-    sweep_fused_kernel<<<(unsigned)ceil_div(r, FR), FT, 0, (cudaStream_t)stream>>>(q, e, r, n, u32, make_grid<float>(cb));
-    SLK_LAUNCH_CHECK();
-    return SLK_OK;
+    // rows per CTA: as many as still give every SM about two CTAs
+    const DevGrid<float> g = make_grid<float>(cb);
+    const int64_t want = 2 * (int64_t)sm_count();
+    if (r >= 32 * want) return launch_fused<32>(q, e, r, n, u32, g, (cudaStream_t)stream);
+    if (r >= 16 * want) return launch_fused<16>(q, e, r, n, u32, g, (cudaStream_t)stream);
+    return launch_fused<8>(q, e, r, n, u32, g, (cudaStream_t)stream);
   }
   SweepCtx c;
   c.Q = q; c.E = e; c.r = r; c.n = n; c.u64 = u64; c.u32 = u32;
