@@ -369,16 +369,36 @@ def run_ours(args):
     value = world * weights / (ms_per_step * 1e-3)
     layer_err = float(errs.mean().item())
 
-    # ---- end to end through the numpy API (host buffers; H2D and D2H inside the timed region) ---
+    # ---- end to end with HOST buffers: H2D and D2H inside the timed region -----------------------
+    # (a) the layer-set plan: inputs in page-locked host memory, every layer a graph branch
+    #     H2D(W, H) -> hot path -> D2H(Q, err), so the copy engines run under other layers' kernels
+    # (b) the reference's per-call numpy API on pageable arrays (experiments/compare.py:84-95):
+    #     every call uploads its own operands (W three times, H twice) -- reported beside (a)
     e2e = None
+    e2e_numpy = None
     if not args.no_e2e:
+        plan = lsq.host_plan(shapes)
+        for i in range(L):
+            plan.W[i][...] = Wnp[i]
+            plan.H[i][...] = Hnp[i]
+        plan.run()
+        plan.run()
+        ems, ewall = timed(lambda: plan.run(sync=True), args.steps)
+        e2e_err = float(plan.err.mean())
+        e2e = {"value": world * weights / (ewall / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": plan.h2d_bytes, "d2h_bytes_per_step": plan.d2h_bytes,
+               "ms_per_step": ewall / args.steps, "layer_error_mean": e2e_err,
+               "api": ("LayerSetQuantizer.host_plan(shapes).run(): W and H of all layers in pinned host buffers -> "
+                       "quantized weights and layer errors in pinned host buffers; wall clock, synchronised every step")}
+        del plan
         step_e2e()
         cv.H2D_BYTES = cv.D2H_BYTES = 0
-        ems, ewall = timed(step_e2e, args.steps)
-        e2e = {"value": world * weights / (ewall / args.steps * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": cv.H2D_BYTES // args.steps, "d2h_bytes_per_step": cv.D2H_BYTES // args.steps,
-               "ms_per_step": ewall / args.steps,
-               "api": "compute_min_mse_scaling + quantize_with_scaling + quantization_error on host numpy arrays"}
+        nsteps = max(1, min(args.steps, 2))
+        ems, ewall = timed(step_e2e, nsteps)
+        e2e_numpy = {"value": world * weights / (ewall / nsteps * 1e-3), "unit": UNIT,
+                     "h2d_bytes_per_step": cv.H2D_BYTES // nsteps, "d2h_bytes_per_step": cv.D2H_BYTES // nsteps,
+                     "ms_per_step": ewall / nsteps, "steps": nsteps,
+                     "api": "compute_min_mse_scaling + quantize_with_scaling + quantization_error on pageable numpy arrays"}
 
     if rank != 0:
         return
@@ -453,7 +473,7 @@ def run_ours(args):
                    "parallelism": f"independent layer sets x{world}" if world > 1 else "single GPU",
                    "streams": args.streams, "cuda_graph": graph is not None,
                    "l2": "inputs (W+H ~0.93 GB per rank) are larger than the 126 MB L2; no flush needed"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "e2e": e2e, "e2e_numpy_api": e2e_numpy, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "layer_error_mean": layer_err,
         "serial_phases_ms_per_step": {k: round(v[0], 3) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
         "xtx": {"tflops": xtx_flop / (xtx_ms * 1e-3) / 1e12 if xtx_ms else None, "ms_total": xtx_ms,

@@ -34,9 +34,11 @@ class LayerSetQuantizer:
         err = ops.mean(ops.hweighted_error(W, q, H))
         return q, sc, err
 
-    def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True, _in_capture=False):
+    def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True, _in_capture=False, _pre=None, _post=None):
         """Ws[i] [r_i, n_i] fp32, Hs[i] [n_i, n_i] fp32 on the device.  Returns (quantized
-        weights, scales, errors) -- errors as one fp32 device vector.  Nothing synchronises."""
+        weights, scales, errors) -- errors as one fp32 device vector.  Nothing synchronises.
+        _pre(i) / _post(i, q) run on layer i's stream before / after its kernels (HostPlan uses
+        them for the host<->device copies)."""
         L = len(Ws)
         dev = Ws[0].device
         errs = errs_out if errs_out is not None else torch.empty(L, dtype=torch.float32, device=dev)
@@ -50,8 +52,12 @@ class LayerSetQuantizer:
             if i < S:
                 st.wait_event(start)
             with torch.cuda.stream(st):
+                if _pre is not None:
+                    _pre(i)
                 q, sc, e = self._one(Ws[i], Hs[i])
                 errs[i:i + 1].copy_(e.reshape(1))
+                if _post is not None:
+                    _post(i, q)
                 if keep_outputs:
                     outs[i], scales[i] = q, sc
                     if not _in_capture:
@@ -74,3 +80,68 @@ class LayerSetQuantizer:
         with torch.cuda.graph(graph):
             outs, _, _ = self(Ws, Hs, errs_out=errs, keep_outputs=True, _in_capture=True)
         return graph, errs, outs
+
+    def host_plan(self, shapes):
+        """Pinned host buffers + device buffers + one CUDA graph for a fixed list of layer shapes
+        [(r, n), ...]; see HostPlan."""
+        return HostPlan(self, shapes)
+
+
+class HostPlan:
+    """Host-buffer entry point of the layer-set driver (the experiments' per-layer loop,
+    experiments/compare.py:50-135, over host arrays).
+
+    The plan owns page-locked host buffers ``W[i]``, ``H[i]`` (inputs, numpy views the caller
+    fills) and ``Q[i]``, ``err`` (outputs).  ``run()`` replays ONE CUDA graph in which every layer
+    is a branch: H2D copy of its W and H -> scale search -> GPTQ -> layer error -> D2H copy of
+    the quantized weights; the copy engines therefore work under the kernels of the other
+    layers.  Same kernels and results as the device-tensor path."""
+
+    def __init__(self, lsq, shapes):
+        ops.require_cuda()
+        self.lsq = lsq
+        self.shapes = [(int(r), int(n)) for r, n in shapes]
+        dev = ops.device()
+        f32 = torch.float32
+        self._Wp = [torch.empty((r, n), dtype=f32).pin_memory() for r, n in self.shapes]
+        self._Hp = [torch.empty((n, n), dtype=f32).pin_memory() for r, n in self.shapes]
+        self._Qp = [torch.empty((r, n), dtype=f32).pin_memory() for r, n in self.shapes]
+        self._errp = torch.empty(len(self.shapes), dtype=f32).pin_memory()
+        self.W = [t.numpy() for t in self._Wp]
+        self.H = [t.numpy() for t in self._Hp]
+        self.Q = [t.numpy() for t in self._Qp]
+        self.err = self._errp.numpy()
+        self._Wd = [torch.empty((r, n), dtype=f32, device=dev) for r, n in self.shapes]
+        self._Hd = [torch.empty((n, n), dtype=f32, device=dev) for r, n in self.shapes]
+        self._errd = torch.empty(len(self.shapes), dtype=f32, device=dev)
+        self._graph = None
+        self.h2d_bytes = sum(4 * (r * n + n * n) for r, n in self.shapes)
+        self.d2h_bytes = sum(4 * r * n for r, n in self.shapes) + 4 * len(self.shapes)
+
+    def _pre(self, i):
+        self._Wd[i].copy_(self._Wp[i], non_blocking=True)
+        self._Hd[i].copy_(self._Hp[i], non_blocking=True)
+
+    def _post(self, i, q):
+        self._Qp[i].copy_(q, non_blocking=True)
+
+    def _pass(self, in_capture):
+        self.lsq(self._Wd, self._Hd, errs_out=self._errd, keep_outputs=False, _in_capture=in_capture,
+                 _pre=self._pre, _post=self._post)
+        self._errp.copy_(self._errd, non_blocking=True)
+
+    def run(self, sync=True):
+        """One pass over the layer set from the current contents of W / H; fills Q and err."""
+        if self._graph is None:
+            # first call: identity Hessians would do as well -- the caller's data is used so that
+            # the warm-up pass is already a valid result; then record the graph
+            self._pass(False)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._pass(True)
+            self._graph = g
+        self._graph.replay()
+        if sync:
+            torch.cuda.current_stream().synchronize()
+        return self.Q, self.err

@@ -496,6 +496,28 @@ def test_device_tensors_pass_through(slk):
     assert isinstance(e, torch.Tensor) and rel(e.item(), slk.obq.quantization_error(W, host, H)) < 1e-6
 
 
+def test_host_plan_equals_per_layer_api(slk):
+    """The pinned-host layer-set plan (H2D -> hot path -> D2H as graph branches) returns exactly
+    what the per-layer numpy API returns, on every replay and after the inputs change."""
+    from sleekit_b200.pipeline import LayerSetQuantizer
+
+    shapes = [(64, 256), (96, 128), (32, 320), (64, 256)]
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    lsq = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=0.01, streams=3)
+    plan = lsq.host_plan(shapes)
+    for rep in range(3):
+        layers = [wl.synthetic_layer(r, n, 10 * rep + i, samples=512) for i, (r, n) in enumerate(shapes)]
+        for i, (W, H, m) in enumerate(layers):
+            plan.W[i][...] = W
+            plan.H[i][...] = H
+        Q, err = plan.run()
+        for i, (W, H, m) in enumerate(layers):
+            sc = slk.scaling.compute_min_mse_scaling(W, cb, 0, H=H.diagonal())
+            want = slk.scaling.quantize_with_scaling(W, sc, cb, H=H)
+            np.testing.assert_array_equal(Q[i], want)
+            assert rel(err[i], slk.obq.quantization_error(W, want, H)) < 1e-6
+
+
 def test_edge_cases(slk):
     cb = slk.codebook.UniformCodebook(4, -1, 1)
     W = np.zeros((3, 40), np.float32)
