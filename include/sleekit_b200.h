@@ -166,6 +166,16 @@ int slk_hinv_from_f32(const float* h, int64_t n, const int64_t* order, const flo
 int slk_hinv_from_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, double* u64,
                       float* u32, int32_t* info, void* stream);
 
+/* K2 without the triangular inverse (the form the fused quantize_opt path uses):
+ * R = flip(cholesky(flip(H_opt[order][:, order]))) in fp64 (obq.py:46-50), i.e. H_opt = R R^T and
+ * compute_hessian_chol's U = R^-1.  Outputs: r32 [n, n] fp32 rounding of R (upper, zeros below) and
+ * ud32 [ceil(n/32), 32, 32] fp32: the inverses of R's 32x32 diagonal blocks (= diagonal blocks of
+ * U; identity-padded for a ragged last block).  One tile-task kernel, no dependent launches. */
+size_t slk_chol_factor_ws_bytes(int64_t n);
+int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const float* dampval,
+                        void* ws, size_t ws_bytes, float* r32, float* ud32, int32_t* info,
+                        void* stream);
+
 /* ---- K3: GPTQ / OBQ sweep ------------------------------------------------------
  * _quantize_opt_block / _quantize_opt_core                    obq.py:106-137
  * q: [r, n] in: scaled, column-permuted weights; out: quantized values.
@@ -176,6 +186,12 @@ int slk_hinv_from_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, dou
 int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, const double* u64,
                        const float* u32, const slk_codebook* cb_host, int32_t leaf,
                        int32_t fanout, int32_t exact_leaf, void* stream);
+
+/* Same sweep from the Cholesky factor (slk_chol_factor_f32) instead of the inverse factor:
+ * block J is formed as W[:, J] + ((W-Q)[:, :a] R[:a, J]) U_JJ, which equals obq.py:137's
+ * W[:, J] - E[:, :a] U[:a, J].  q in/out as above; d [r, n] out: W - Q (scaled, permuted domain). */
+int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32,
+                         const float* ud32, const slk_codebook* cb_host, void* stream);
 
 /* ---- K7: best-first local search ------------------------------------------------
  * quantize_local_search / LocalSearchQuantizer                obq.py:234-358

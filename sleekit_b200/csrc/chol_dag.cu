@@ -1,0 +1,462 @@
+// K2 (fused-path form): dampening + column permutation + fp64 Cholesky factor, WITHOUT the n^3/3
+// triangular inverse.
+//   H_opt = H + damp*mean(diag H)*I ; H_opt[order][:, order]                  obq.py:198-204
+//   compute_hessian_chol builds U = flip(inv(cholesky(flip(H_opt))))            obq.py:38-55
+// With L = cholesky(flip(H_opt)) and R = flip(L) (upper, H_opt = R R^T) one has U = R^-1, and the
+// sweep's propagated term is  E[:, :a] U[:a, J] = -(W-Q)[:, :a] R[:a, J] U_JJ  with U_JJ the inverse
+// of the 32x32 diagonal block R_JJ (verified against the reference's own loop).  The
+// sweep (sweep.cu, R form) therefore needs only R (fp32) and the diagonal-block inverses; the
+// public compute_hessian_chol keeps the full inverse (hinv.cu).
+//
+// The factorisation is ONE launch: a tile Cholesky (64x64 tiles, left-looking) whose tile tasks are
+// handed out by an atomic ticket in column-major order.  Task (i, j), i >= j:
+//     S = A(i,j) - sum_{k<j} L(i,k) L(j,k)^T        DMMA m8n8k4, operands through a cp.async ring
+//     i == j:  L(j,j) = chol(S), X_j = L(j,j)^-1     in shared memory (8-column register panels,
+//                                                     DMMA trailing updates, inverse by doubling)
+//     i >  j:  L(i,j) = S X_j^T                      DMMA
+// and publishes a per-tile ready flag (release); consumers poll the flags of the tiles they read
+// (acquire).  A task only ever waits for tasks with a SMALLER ticket, and a ticket is only taken by
+// a CTA that is already running, so the scheme cannot deadlock whatever else shares the GPU and
+// however few CTAs are resident (the decoupled look-back argument).  No dependent launches: the
+// n/64-panel launch chain of the right-looking version (hinv.cu) becomes in-kernel flag latency.
+#include "common.cuh"
+
+namespace slk {
+
+constexpr int CT = 64;            // tile edge
+constexpr int CP = 68;            // shared-memory pitch (doubles): 68 = 4 (mod 16) makes every DMMA fragment
+                                  // access touch each 8-byte bank pair at most twice (the minimum)
+constexpr int CBK = 16;           // k per ring stage
+constexpr int CLD = CBK + 4;      // ring pitch
+constexpr int CST = 4;            // ring stages
+constexpr int CTH = 256;          // threads per CTA (8 warps: 2 x 4 warp tiles of 32 x 16)
+
+struct CholSmem {
+  union {
+    struct { double A[CST][CT * CLD]; double B[CST][CT * CLD]; } ring;          // 80 KB
+    struct { double M[CT * CP]; double X[CT * CP]; double T[32 * CP]; } f;      // 85 KB
+  };
+  double rd[CT];                  // 1 / L[c][c]
+  int ticket;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_ready(const int* flag) {
+  while (ld_acquire_gpu(flag) == 0) __nanosleep(32);
+}
+__device__ __forceinline__ void cd_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cd_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// A[i, j] (tiles on and below the diagonal) of flip(H_opt[order][:, order]) with the identity padding in FRONT:
+// flipped index i <-> sweep column npad-1-i, so that 32-column sweep blocks coincide with 32-row
+// blocks of the factor for every n.  Also clears the flags, the ticket and info.
+template <typename TS>
+__global__ void __launch_bounds__(256) chol_gather_kernel(const TS* __restrict__ h, int64_t n, int64_t npad,
+                                                          const int64_t* __restrict__ order,
+                                                          const float* __restrict__ dampval, double* __restrict__ A,
+                                                          int* __restrict__ flags, int64_t nflags,
+                                                          int32_t* __restrict__ info) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t t = t0; t < nflags; t += stride) flags[t] = 0;
+  if (t0 == 0) *info = 0;
+  const double damp = dampval ? (double)dampval[0] : 0.0;
+  const int64_t total = npad * npad;
+  for (int64_t t = t0; t < total; t += stride) {
+    const int64_t i = t / npad, j = t - i * npad;
+    if (j / CT > i / CT) continue;             // tiles above the diagonal are never read
+    const int64_t a = npad - 1 - i, b = npad - 1 - j;
+    double v;
+    if (a < n && b < n) {
+      const int64_t sa = order ? __ldg(order + a) : a, sb = order ? __ldg(order + b) : b;
+      v = (double)h[sa * n + sb];
+      if (i == j) v = __dadd_rn(v, damp);      // obq.py:198: fp32 H promoted, fp64 add
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    A[t] = v;
+  }
+}
+
+// ---- 64x64 diagonal tile: factor + inverse in shared memory ---------------------------------------
+// M holds the lower triangle column-major (M[c*CP + r] = S[r][c], r >= c) so that a lane that owns
+// a row reads consecutive addresses.
+
+// Panel of 8 columns, one warp, rows lane and lane+32 in registers; right-looking inside the panel.
+// The dependent chain per column is shuffle -> rsqrt -> multiply -> shuffle -> fma.
+__device__ __forceinline__ void chol_panel8(double* M, double* rd, int b, int lane, int32_t* info, int64_t gcol0) {
+  const int c0 = 8 * b;
+  const bool hi = c0 >= 32;
+  double v0[8], v1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    v0[c] = M[(c0 + c) * CP + lane];
+    v1[c] = M[(c0 + c) * CP + lane + 32];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int prow = c0 + j;
+    const double piv = __shfl_sync(0xffffffffu, hi ? v1[j] : v0[j], prow & 31);
+    if (lane == 0 && !(piv > 0.0)) atomicCAS(info, 0, (int32_t)(gcol0 + prow + 1));
+    const double y = rsqrt(piv);
+    v0[j] = __dmul_rn(v0[j], y);               // the pivot row's own entry becomes piv*y = sqrt(piv)
+    v1[j] = __dmul_rn(v1[j], y);
+    if (lane == (prow & 31)) rd[prow] = y;
+    const double mine = hi ? v1[j] : v0[j];
+#pragma unroll
+    for (int c = j + 1; c < 8; ++c) {
+      const double l = __shfl_sync(0xffffffffu, mine, (c0 + c) & 31);   // L[c0+c][c0+j]
+      v0[c] = __fma_rn(-v0[j], l, v0[c]);
+      v1[c] = __fma_rn(-v1[j], l, v1[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    M[(c0 + c) * CP + lane] = v0[c];
+    M[(c0 + c) * CP + lane + 32] = v1[c];
+  }
+}
+
+// Rank-8 update of the 8x8 tiles (ti, tk), b < tk <= ti, by the panel b just factored.
+__device__ __forceinline__ void chol_trailing8(double* M, int b, int warp, int lane) {
+  const int fr = lane >> 2, fk = lane & 3;
+  int cnt = 0;
+  for (int ti = b + 1; ti < 8; ++ti) {
+    for (int tk = b + 1; tk <= ti; ++tk, ++cnt) {
+      if ((cnt & 7) != warp) continue;
+      double* c0p = &M[(8 * tk + 2 * fk) * CP + 8 * ti + fr];
+      double c[2] = {c0p[0], c0p[CP]};
+#pragma unroll
+      for (int ks = 0; ks < 8; ks += 4) {
+        const double a = M[(8 * b + ks + fk) * CP + 8 * ti + fr];
+        const double bb = M[(8 * b + ks + fk) * CP + 8 * tk + fr];
+        cd_dmma(c, -a, bb);
+      }
+      c0p[0] = c[0];
+      c0p[CP] = c[1];
+    }
+  }
+}
+
+// C(i, n) = alpha * sum_k A(i, k) B(k, n) on 8x8 DMMA tiles in shared memory, `nprob` independent
+// problems of size s x s x s laid out with the given strides; tiles are dealt to the 8 warps.
+__device__ __forceinline__ void smem_mm_batched(double* C, int sci, int scn, int spc, const double* A, int sai, int sak,
+                                                int spa, const double* B, int sbk, int sbn, int spb, int s, int nprob,
+                                                double alpha, int warp, int lane) {
+  const int fr = lane >> 2, fk = lane & 3;
+  const int tn = s >> 3, tiles = tn * tn;
+  for (int t = warp; t < tiles * nprob; t += CTH / 32) {
+    const int p = t / tiles, tt = t - p * tiles;
+    const int i0 = (tt / tn) * 8, n0 = (tt % tn) * 8;
+    const double* Ap = A + p * spa;
+    const double* Bp = B + p * spb;
+    double c[2] = {0.0, 0.0};
+    for (int k0 = 0; k0 < s; k0 += 4) {
+      const double a = Ap[(i0 + fr) * sai + (k0 + fk) * sak];
+      const double bb = Bp[(k0 + fk) * sbk + (n0 + fr) * sbn];
+      cd_dmma(c, a, bb);
+    }
+    double* cp = C + p * spc + (i0 + fr) * sci + (n0 + 2 * fk) * scn;
+    cp[0] = __dmul_rn(alpha, c[0]);
+    cp[scn] = __dmul_rn(alpha, c[1]);
+  }
+}
+
+// In: sm.f.M lower triangle (column-major).  Out: L in sm.f.M (same layout, entries with r < c are
+// garbage), X = L^-1 row-major in sm.f.X (upper part zero).  All 256 threads.
+__device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t* info, int64_t gcol0) {
+  const int warp = tid >> 5, lane = tid & 31;
+  double* M = sm.f.M;
+  double* X = sm.f.X;
+  for (int t = tid; t < CT * CP; t += CTH) X[t] = 0.0;
+  for (int b = 0; b < 8; ++b) {
+    if (warp == 0) chol_panel8(M, sm.rd, b, lane, info, gcol0);
+    __syncthreads();
+    if (b < 7) {
+      chol_trailing8(M, b, warp, lane);
+      __syncthreads();
+    }
+  }
+  // inverses of the 8x8 diagonal blocks: thread c solves L_bb x = e_cc by forward substitution
+  if (tid < CT) {
+    const int b8 = tid & ~7, cc = tid & 7;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double s = (i == cc) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) s = __fma_rn(-M[(b8 + k) * CP + b8 + i], x[k], s);
+      x[i] = (i >= cc) ? __dmul_rn(s, sm.rd[b8 + i]) : 0.0;
+      X[(b8 + i) * CP + b8 + cc] = x[i];
+    }
+  }
+  __syncthreads();
+  // doubling: inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]]
+  for (int s = 8; s < CT; s *= 2) {
+    const int pairs = CT / (2 * s);
+    // T_p = L21 X11
+    smem_mm_batched(sm.f.T, CP, 1, s * CP, M + s, 1, CP, 2 * s * (CP + 1), X, CP, 1, 2 * s * (CP + 1), s, pairs, 1.0,
+                    warp, lane);
+    __syncthreads();
+    // X21 = -X22 T_p
+    smem_mm_batched(X + s * CP, CP, 1, 2 * s * (CP + 1), X + s * (CP + 1), CP, 1, 2 * s * (CP + 1), sm.f.T, CP, 1, s * CP,
+                    s, pairs, -1.0, warp, lane);
+    __syncthreads();
+  }
+}
+
+// ---- the tile-task kernel ----------------------------------------------------------------------------
+// A: [T*64, ld] fp64, lower triangle in, L out.  Dinv: [T, 64, 64] inverses of the diagonal tiles.
+// sync: [T*T] ready flags followed by the ticket counter.
+__global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A, int64_t ld, int T,
+                                                          double* __restrict__ Dinv, int* __restrict__ sync,
+                                                          int32_t* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char chol_raw[];
+  CholSmem& sm = *reinterpret_cast<CholSmem*>(chol_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+  int* ready = sync;
+  int* ticket = sync + (int64_t)T * T;
+  const int ntasks = T * (T + 1) / 2;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int t = sm.ticket;
+    if (t >= ntasks) return;
+    int j = 0, rem = t;
+    while (rem >= T - j) { rem -= T - j; ++j; }
+    const int i = j + rem;
+    const bool diag = (i == j);
+    const double* Ai = A + (int64_t)i * CT * ld;
+    const double* Aj = A + (int64_t)j * CT * ld;
+    double* Cij = A + (int64_t)i * CT * ld + (int64_t)j * CT;
+
+    // the tile itself, in accumulator-fragment layout (rows wm+8ii+fr, columns wn+8jj+2fk, +1)
+    double2 cij[4][2];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+        cij[ii][jj] = *reinterpret_cast<const double2*>(Cij + (int64_t)row * ld + col);
+      }
+    double acc[4][2][2];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
+
+    const int nt = 4 * j;   // ring steps: 64-wide k tiles split in 4
+    auto load = [&](int s) {
+      const int st = s % CST;
+      const int64_t k0 = (int64_t)(s >> 2) * CT + (s & 3) * CBK;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int idx = tid + q * CTH, row = idx >> 3, piece = idx & 7;
+        cd_cp16(&sm.ring.A[st][row * CLD + piece * 2], Ai + (int64_t)row * ld + k0 + piece * 2);
+        if (!diag) cd_cp16(&sm.ring.B[st][row * CLD + piece * 2], Aj + (int64_t)row * ld + k0 + piece * 2);
+      }
+    };
+    if (nt > 0) {
+      if (tid == 0) {
+        wait_ready(ready + (int64_t)i * T);
+        if (!diag) wait_ready(ready + (int64_t)j * T);
+      }
+      __syncthreads();
+    }
+    for (int s = 0; s < CST - 1; ++s) {
+      if (s < nt) load(s);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int s = 0; s < nt; ++s) {
+      const int sn = s + CST - 1;
+      if (tid == 0 && sn < nt && (sn & 3) == 0) {
+        wait_ready(ready + (int64_t)i * T + (sn >> 2));
+        if (!diag) wait_ready(ready + (int64_t)j * T + (sn >> 2));
+      }
+      asm volatile("cp.async.wait_group %0;" ::"n"(CST - 2) : "memory");
+      __syncthreads();
+      if (sn < nt) load(sn);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const double* As = sm.ring.A[s % CST];
+      const double* Bs = diag ? As : sm.ring.B[s % CST];
+#pragma unroll
+      for (int ks = 0; ks < CBK; ks += 4) {
+        double a[4], b[2];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) a[ii] = As[(wm + 8 * ii + fr) * CLD + ks + fk];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) b[jj] = Bs[(wn + 8 * jj + fr) * CLD + ks + fk];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) cd_dmma(acc[ii][jj], a[ii], b[jj]);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // the ring is dead: its storage becomes M / X / T
+
+    if (diag) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+          sm.f.M[col * CP + row] = __dsub_rn(cij[ii][jj].x, acc[ii][jj][0]);
+          sm.f.M[(col + 1) * CP + row] = __dsub_rn(cij[ii][jj].y, acc[ii][jj][1]);
+        }
+      __syncthreads();
+      chol_factor_tile(sm, tid, info, (int64_t)j * CT);
+      double* Xg = Dinv + (int64_t)j * CT * CT;
+      for (int e = tid; e < CT * CT; e += CTH) {
+        const int r = e >> 6, c = e & 63;
+        Cij[(int64_t)r * ld + c] = (r >= c) ? sm.f.M[c * CP + r] : 0.0;
+        Xg[e] = sm.f.X[r * CP + c];
+      }
+    } else {
+      // S row-major into M, X_j into X, L(i,j) = S X_j^T
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+          double2 v;
+          v.x = __dsub_rn(cij[ii][jj].x, acc[ii][jj][0]);
+          v.y = __dsub_rn(cij[ii][jj].y, acc[ii][jj][1]);
+          *reinterpret_cast<double2*>(&sm.f.M[row * CP + col]) = v;
+        }
+      if (tid == 0) wait_ready(ready + (int64_t)j * T + j);
+      __syncthreads();
+      const double* Xg = Dinv + (int64_t)j * CT * CT;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int idx = tid + q * CTH, row = idx >> 5, piece = idx & 31;
+        cd_cp16(&sm.f.X[row * CP + piece * 2], Xg + row * CT + piece * 2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      double out[4][2][2];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) out[ii][jj][0] = out[ii][jj][1] = 0.0;
+      // X_j is lower triangular: column tile wn..wn+15 only needs k < wn + 16
+      for (int ks = 0; ks < wn + 16; ks += 4) {
+        double a[4], b[2];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) a[ii] = sm.f.M[(wm + 8 * ii + fr) * CP + ks + fk];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) b[jj] = sm.f.X[(wn + 8 * jj + fr) * CP + ks + fk];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) cd_dmma(out[ii][jj], a[ii], b[jj]);
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+          *reinterpret_cast<double2*>(Cij + (int64_t)row * ld + col) = make_double2(out[ii][jj][0], out[ii][jj][1]);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
+  }
+}
+
+// R32[a, b] = L[npad-1-a, npad-1-b] for b >= a (0 below); Ud[blk][p][q] = inverse of the 32x32
+// diagonal block R[32blk.., 32blk..] = flip of the matching diagonal block of the tile inverses.
+__global__ void __launch_bounds__(256) chol_export_kernel(const double* __restrict__ A, int64_t n, int64_t npad,
+                                                          const double* __restrict__ Dinv, float* __restrict__ r32,
+                                                          float* __restrict__ ud32) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = n * n;
+  for (int64_t t = t0; t < total; t += stride) {
+    const int64_t a = t / n, b = t - a * n;
+    r32[t] = (b >= a) ? (float)A[(npad - 1 - a) * npad + (npad - 1 - b)] : 0.0f;
+  }
+  const int64_t nblk = (n + 31) / 32;
+  for (int64_t t = t0; t < nblk * 1024; t += stride) {
+    const int64_t blk = t >> 10;
+    const int p = (int)((t >> 5) & 31), q = (int)(t & 31);
+    const int64_t fb = npad / 32 - 1 - blk;          // 32-block index in factor order
+    const int64_t tile = fb >> 1;
+    const int sub = (int)(fb & 1) * 32;
+    ud32[t] = (float)Dinv[tile * CT * CT + (int64_t)(sub + 31 - p) * CT + (sub + 31 - q)];
+  }
+}
+
+static inline int64_t cpad64(int64_t n) { return (n + CT - 1) / CT * CT; }
+
+template <typename TS>
+static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const float* dampval, void* ws, size_t ws_bytes,
+                            float* r32, float* ud32, int32_t* info, cudaStream_t st) {
+  SLK_REQUIRE(h && info && r32 && ud32 && n >= 1, "bad arguments");
+  SLK_REQUIRE(ws && ws_bytes >= slk_chol_factor_ws_bytes(n), "workspace too small");
+  const int64_t npad = cpad64(n);
+  const int T = (int)(npad / CT);
+  double* A = (double*)ws;
+  double* Dinv = A + npad * npad;
+  int* sync = (int*)(Dinv + (int64_t)T * CT * CT);
+  const int64_t nflags = (int64_t)T * T + 1;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  int64_t blocks = ceil_div(npad * npad, 256);
+  chol_gather_kernel<TS><<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(h, n, npad, order, dampval, A, sync,
+                                                                              nflags, info);
+  SLK_LAUNCH_CHECK();
+  static bool attr_done = false;
+  if (!attr_done) {
+    SLK_CUDA(cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
+    attr_done = true;
+  }
+  const int64_t ntasks = (int64_t)T * (T + 1) / 2;
+  int64_t grid = 2 * (int64_t)T + 2;
+  if (grid > ntasks) grid = ntasks;
+  if (grid > 2 * (int64_t)sm_count()) grid = 2 * (int64_t)sm_count();
+  chol_dag_kernel<<<(unsigned)grid, CTH, sizeof(CholSmem), st>>>(A, npad, T, Dinv, sync, info);
+  SLK_LAUNCH_CHECK();
+  blocks = ceil_div(n * n, 256);
+  chol_export_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(A, n, npad, Dinv, r32, ud32);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+}  // namespace slk
+
+using namespace slk;
+
+extern "C" {
+
+size_t slk_chol_factor_ws_bytes(int64_t n) {
+  const int64_t npad = cpad64(n);
+  const int64_t T = npad / CT;
+  return (size_t)(npad * npad + T * CT * CT) * sizeof(double) + (size_t)(T * T + 1) * sizeof(int) + 256;
+}
+
+int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const float* dampval, void* ws,
+                        size_t ws_bytes, float* r32, float* ud32, int32_t* info, void* stream) {
+  return chol_factor_impl<float>(h, n, order, dampval, ws, ws_bytes, r32, ud32, info, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -115,7 +115,8 @@ struct LeafShared32 {
 template <int WIN>
 __device__ __forceinline__ void leaf_phase32(float (&q)[32], const LeafShared32& sh, int i0, int width,
                                              const DevGrid<float>& g, const FastDivF& fstep, bool fastq,
-                                             float* __restrict__ qrow, float* __restrict__ erow) {
+                                             float* __restrict__ qrow, float* __restrict__ erow,
+                                             const float* __restrict__ w0 = nullptr) {
 #pragma unroll 1
   for (int t = 0; t < 8; ++t) {
     const int i = i0 + t;
@@ -126,7 +127,7 @@ __device__ __forceinline__ void leaf_phase32(float (&q)[32], const LeafShared32&
     fd.d = sh.U[i][i]; fd.y = sh.Uy[i]; fd.ok = sh.Uok[i];
     const float res = fastdiv(__fsub_rn(w, qq), fd);
     qrow[i] = qq;
-    erow[i] = res;
+    erow[i] = w0 ? __fsub_rn(w0[i], qq) : res;   // R form: D = W - Q of the ORIGINAL weight
     const float* urow = &sh.U[i][i];
 #pragma unroll
     for (int j = 1; j < WIN; ++j) q[j - 1] = __fmaf_rn(-res, urow[j], q[j]);
@@ -203,6 +204,7 @@ struct FusedSmem {
   float U[FST][KG][32][32];   // [k-group][k][col]
   float red[KG][R][33];       // split-K partial sums
   float Qs[R][33];
+  float W0[R][33];            // R form: the original weights of the block
   LeafShared32 leaf;
 };
 
@@ -214,9 +216,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int R>
+// RFORM = false: E holds the scaled residuals and U the inverse factor (obq.py:121-137 as written).
+// RFORM = true : U is the Cholesky factor R (H_opt = R R^T), Ud the 32x32 diagonal-block inverses
+//                (chol_dag.cu), E holds D = W - Q, and the block is formed as
+//                W[:, J] + (D[:, :a] R[:a, J]) Ud_J  -- same algebra, no full inverse.
+template <int R, bool RFORM>
 __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r, int64_t n,
-                                                         const float* __restrict__ U, DevGrid<float> g) {
+                                                         const float* __restrict__ U, const float* __restrict__ Ud,
+                                                         DevGrid<float> g) {
   typedef FusedSmem<R> SM;
   constexpr int KG = SM::KG;
   constexpr int KSUP = 32 * KG;                       // k covered by one ring stage
@@ -242,7 +249,8 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = seg * 4 + j;
-        ud[j] = (i < width && c < width) ? __ldg(U + (a + i) * n + (a + c)) : ((i == c) ? 1.0f : 0.0f);
+        if (RFORM) ud[j] = __ldg(Ud + (a / 32) * 1024 + i * 32 + c);
+        else ud[j] = (i < width && c < width) ? __ldg(U + (a + i) * n + (a + c)) : ((i == c) ? 1.0f : 0.0f);
         wq[j] = (kg == 0 && grow < r && c < width) ? __ldcg(Q + grow * n + a + c) : 0.0f;
       }
     }
@@ -314,7 +322,32 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
         float t = sm.red[0][lrow][seg * 4 + j];
 #pragma unroll
         for (int q = 1; q < KG; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
-        sm.Qs[lrow][seg * 4 + j] = __fsub_rn(wq[j], t);
+        if (RFORM) {
+          sm.Qs[lrow][seg * 4 + j] = t;            // P = D[:, :a] R[:a, J], multiplied by Ud_J below
+          sm.W0[lrow][seg * 4 + j] = wq[j];
+        } else {
+          sm.Qs[lrow][seg * 4 + j] = __fsub_rn(wq[j], t);
+        }
+      }
+    }
+    if (RFORM) {
+      __syncthreads();
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kg == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float pv = sm.Qs[lrow][c];
+          const float4 u = *reinterpret_cast<const float4*>(&sm.leaf.U[c][seg * 4]);
+          s4[0] = __fmaf_rn(pv, u.x, s4[0]);
+          s4[1] = __fmaf_rn(pv, u.y, s4[1]);
+          s4[2] = __fmaf_rn(pv, u.z, s4[2]);
+          s4[3] = __fmaf_rn(pv, u.w, s4[3]);
+        }
+      }
+      __syncthreads();
+      if (kg == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm.Qs[lrow][seg * 4 + j] = __fadd_rn(wq[j], s4[j]);
       }
     }
     if (tid < 32) {
@@ -330,25 +363,26 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
       for (int k = 0; k < 32; ++k) q[k] = sm.Qs[tid][k];
       float* qrow = Q + (row0 + tid) * n + a;
       float* erow = E + (row0 + tid) * n + a;
-      leaf_phase32<32>(q, sm.leaf, 0, width, g, fstep, fastq, qrow, erow);
-      leaf_phase32<24>(q, sm.leaf, 8, width, g, fstep, fastq, qrow, erow);
-      leaf_phase32<16>(q, sm.leaf, 16, width, g, fstep, fastq, qrow, erow);
-      leaf_phase32<8>(q, sm.leaf, 24, width, g, fstep, fastq, qrow, erow);
+      const float* w0 = RFORM ? &sm.W0[tid][0] : nullptr;
+      leaf_phase32<32>(q, sm.leaf, 0, width, g, fstep, fastq, qrow, erow, w0);
+      leaf_phase32<24>(q, sm.leaf, 8, width, g, fstep, fastq, qrow, erow, w0);
+      leaf_phase32<16>(q, sm.leaf, 16, width, g, fstep, fastq, qrow, erow, w0);
+      leaf_phase32<8>(q, sm.leaf, 24, width, g, fstep, fastq, qrow, erow, w0);
     }
     __syncthreads();   // E of this block is visible to the whole CTA before the next block reads it
   }
 }
 
-template <int R>
-static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u32, const DevGrid<float>& g,
+template <int R, bool RFORM>
+static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u32, const float* ud, const DevGrid<float>& g,
                         cudaStream_t st) {
-  auto kern = sweep_fused_kernel<R>;
+  auto kern = sweep_fused_kernel<R, RFORM>;
   static bool attr_done = false;
   if (!attr_done) {
     SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<R>)));
     attr_done = true;
   }
-  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, g);
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, ud, g);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -415,13 +449,29 @@ extern "C" int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, cons
     // rows per CTA: as many as still give every SM about two CTAs
     const DevGrid<float> g = make_grid<float>(cb);
     const int64_t want = 2 * (int64_t)sm_count();
-    if (r >= 32 * want) return launch_fused<32>(q, e, r, n, u32, g, (cudaStream_t)stream);
-    if (r >= 16 * want) return launch_fused<16>(q, e, r, n, u32, g, (cudaStream_t)stream);
-    return launch_fused<8>(q, e, r, n, u32, g, (cudaStream_t)stream);
+    if (r >= 32 * want) return launch_fused<32, false>(q, e, r, n, u32, nullptr, g, (cudaStream_t)stream);
+    if (r >= 16 * want) return launch_fused<16, false>(q, e, r, n, u32, nullptr, g, (cudaStream_t)stream);
+    return launch_fused<8, false>(q, e, r, n, u32, nullptr, g, (cudaStream_t)stream);
   }
   SweepCtx c;
   c.Q = q; c.E = e; c.r = r; c.n = n; c.u64 = u64; c.u32 = u32;
   c.g = make_grid<float>(cb);
   c.leaf = leaf; c.fanout = fanout; c.exact_leaf = exact_leaf; c.st = (cudaStream_t)stream;
   return sweep_range(c, 0, n);
+}
+
+// R form of the sweep: r32 = Cholesky factor R (upper, H_opt = R R^T), ud32 = [ceil(n/32), 32, 32]
+// inverses of its diagonal blocks (slk_chol_factor_f32).  d receives W - Q.
+extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud32,
+                                    const slk_codebook* cb, void* stream) {
+  int rc = check_codebook(cb);
+  if (rc) return rc;
+  SLK_REQUIRE(r >= 0 && n >= 1, "bad shape");
+  if (r == 0) return SLK_OK;
+  SLK_REQUIRE(q && d && r32 && ud32, "NULL pointer");
+  const DevGrid<float> g = make_grid<float>(cb);
+  const int64_t want = 2 * (int64_t)sm_count();
+  if (r >= 32 * want) return launch_fused<32, true>(q, d, r, n, r32, ud32, g, (cudaStream_t)stream);
+  if (r >= 16 * want) return launch_fused<16, true>(q, d, r, n, r32, ud32, g, (cudaStream_t)stream);
+  return launch_fused<8, true>(q, d, r, n, r32, ud32, g, (cudaStream_t)stream);
 }

@@ -18,6 +18,10 @@ __all__ = [
 ]
 
 MAX_LEAF = 32  # widest column block the leaf kernel sweeps (one lane per column)
+# quantize_opt's fused path: Cholesky factor + R-form sweep (True) or full inverse factor + U-form sweep
+import os as _os
+
+USE_CHOL_FORM = _os.environ.get("SLK_CHOL_FORM", "1") != "0"
 
 
 def random_psd_matrix(size, rank, damp=0.0):
@@ -176,8 +180,13 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
         hopt.diagonal().add_(dampval.to(torch.float64))
         order = _device_order(Wd, hopt, quantizer, act_order, hopt_diag)
     Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
-    u64, u32, info = ops.hinv(Hd, order, dampval)                         # obq.py:204-205
-    ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209
+    if _sweep_leaf(min_block_size) == MAX_LEAF and USE_CHOL_FORM:
+        # factor only (no triangular inverse): H_opt = R R^T, sweep from R
+        r32, ud32, info = ops.chol_factor(Hd, order, dampval)             # obq.py:204 (dpotrf part)
+        ops.gptq_sweep_r(Q, r32, ud32, quantizer)                         # obq.py:208-209
+    else:
+        u64, u32, info = ops.hinv(Hd, order, dampval)                     # obq.py:204-205
+        ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209
     if order is not None:
         Q = ops.permute_cols(Q, order, scatter=True)                      # obq.py:212-213
     if check:

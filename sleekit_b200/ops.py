@@ -391,6 +391,38 @@ def hinv(h, order=None, dampval=None, want64=False, want32=True):
     return u64, u32, info
 
 
+@_timed("chol_factor")
+def chol_factor(h, order=None, dampval=None):
+    """fp64 Cholesky of (h + dampval*I)[order][:, order] in the sweep's orientation: returns
+    (r32 [n,n] upper with H_opt = R R^T, ud32 [ceil(n/32),32,32] diagonal-block inverses, info)."""
+    _chk(h, torch.float32)
+    n = h.shape[0]
+    lib = _lib.load()
+    nbytes = lib.slk_chol_factor_ws_bytes(n)
+    ws = _ws(nbytes, h.device)
+    r32 = torch.empty((n, n), dtype=torch.float32, device=h.device)
+    ud32 = torch.empty(((n + 31) // 32, 32, 32), dtype=torch.float32, device=h.device)
+    info = torch.empty(1, dtype=torch.int32, device=h.device)
+    if order is not None:
+        _chk(order, torch.int64)
+    _lib.call("slk_chol_factor_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(r32), _ptr(ud32),
+              _ptr(info), _stream())
+    return r32, ud32, info
+
+
+@_timed("gptq_sweep")
+def gptq_sweep_r(q, r32, ud32, cb, d=None):
+    """In place on q; the sweep from the Cholesky factor (chol_factor); returns (q, d = W - Q)."""
+    cb = device_codebook(cb)
+    _chk(q, torch.float32)
+    _chk(r32, torch.float32)
+    _chk(ud32, torch.float32)
+    if d is None:
+        d = torch.empty_like(q)
+    _lib.call("slk_gptq_sweep_r_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32), _ptr(ud32), cb.ref, _stream())
+    return q, d
+
+
 @_timed("gptq_sweep")
 def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None, exact_leaf=False):
     """In place on q ([rows, n] scaled, permuted weights -> quantized values); returns (q, e).

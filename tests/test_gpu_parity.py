@@ -226,6 +226,56 @@ def test_factor_vs_oracle(slk, n):
     np.testing.assert_allclose(U.T @ U @ Hd, np.eye(n), atol=1e-7)
 
 
+@pytest.mark.parametrize("n,perm,damp", [(50, False, 0.01), (64, True, 0.01), (200, True, 0.03), (768, True, 0.01),
+                                         (1000, True, 0.01), (3072, True, 0.01)])
+def test_cholesky_form_vs_oracle(slk, n, perm, damp):
+    """K2 without the inverse (tile-task Cholesky): R = flip(chol(flip(H_opt))) = inv(U) and the
+    32x32 diagonal blocks of U, against the oracle's factor (obq.py:38-55) -- fp64 work, fp32 out."""
+    from sleekit_b200 import ops
+
+    _, H, _ = wl.synthetic_layer(4, n, 13, samples=max(min(2 * n, 4096), 256))
+    dampval = np.float32(damp) * H.diagonal().mean()
+    order = np.argsort(-H.diagonal().astype(np.float64), kind="stable") if perm else np.arange(n)
+    Hd = (H.astype(np.float64) + np.float64(dampval) * np.eye(n))[order][:, order]
+    U = orc.inverse_upper_factor(Hd)
+    L = np.linalg.cholesky(Hd[::-1, ::-1])
+    R = np.ascontiguousarray(L[::-1, ::-1])           # upper, Hd = R R^T, U = inv(R)
+    Hdev = torch.from_numpy(H).cuda()
+    r32, ud32, info = ops.chol_factor(Hdev, torch.from_numpy(order).cuda() if perm else None,
+                                      torch.tensor([dampval], dtype=torch.float32, device="cuda"))
+    assert int(info.item()) == 0
+    r32, ud32 = r32.cpu().numpy(), ud32.cpu().numpy()
+    np.testing.assert_array_equal(np.tril(r32, -1), 0)
+    assert np.abs(r32 - R).max() <= 2e-7 * np.abs(R).max()
+    for b in range((n + 31) // 32):
+        w = min(32, n - 32 * b)
+        want = np.eye(32)
+        want[:w, :w] = U[32 * b:32 * b + w, 32 * b:32 * b + w]
+        assert np.abs(ud32[b] - want).max() <= 2e-7 * np.abs(want).max(), b
+    # the factor reproduces H_opt to fp32 round-off of R
+    Rd = r32.astype(np.float64)
+    assert np.abs(Rd @ Rd.T - Hd).max() <= 1e-6 * np.abs(Hd).max()
+
+
+def test_cholesky_form_sweep_equals_inverse_form(slk):
+    """quantize_opt through (Cholesky factor, R-form sweep) and through (inverse factor, U-form
+    sweep): the same algebra in different fp32 rounding -- codes agree to the GPTQ noise floor."""
+    W, H, m = wl.synthetic_layer(256, 1024, 5)
+    cb, grid = slk.codebook.UniformCodebook(8, -1, 1), orc.UniformGrid(8, -1, 1)
+    sc = orc.search_scale(W, grid, 0, H=H.diagonal())
+    outs = []
+    for flag in (True, False):
+        old, slk.obq.USE_CHOL_FORM = slk.obq.USE_CHOL_FORM, flag
+        try:
+            outs.append(slk.scaling.quantize_with_scaling(W, sc, cb, H=H))
+        finally:
+            slk.obq.USE_CHOL_FORM = old
+    a = agree(grid.index(orc.divide_rows(outs[0], sc, 0)), grid.index(orc.divide_rows(outs[1], sc, 0)))
+    e0, e1 = orc.mean_error(W, outs[0], H), orc.mean_error(W, outs[1], H)
+    print(f"chol form vs inverse form: code agreement {a:.6f}, errors {e0:.6e} {e1:.6e}")
+    assert a >= 0.999 and rel(e0, e1) <= 1e-3
+
+
 def test_factor_not_positive_definite_raises(slk):
     H = np.eye(70)
     H[40, 40] = -1.0

@@ -73,7 +73,7 @@ def main():
 
             print(f"leaf r={r}: {timeit(f) - timeit(g):8.1f} us")
     if what in ("sweep", "hinv", "all"):
-        for r, n in ((768, 768), (3072, 768), (768, 3072)):
+        for r, n in ((768, 768), (3072, 768), (768, 3072), (1024, 4096)):
             W, H, _ = wl.synthetic_layer(r, n, 0, samples=2048 if n <= 1024 else 4096)
             Wd, Hd = torch.from_numpy(W).to(dev), torch.from_numpy(H).to(dev)
             damp = ops.damp_value(Hd, 0.01)
@@ -84,7 +84,11 @@ def main():
             Ws = ops.scale_rows(Wd, sc, 0)
             t_s = timeit(lambda: ops.gptq_sweep(Ws.clone(), u64, u32, cb), reps=5)
             t_a = timeit(lambda: ops.argsort(ops.order_keys(Hd, damp, None)), reps=5)
-            print(f"[{r}x{n}] hinv {t_h:9.1f} us   sweep {t_s:9.1f} us   argsort {t_a:7.1f} us  info={int(info.item())}")
+            t_c = timeit(lambda: ops.chol_factor(Hd, order, damp), reps=5)
+            r32, ud32, info2 = ops.chol_factor(Hd, order, damp)
+            t_r = timeit(lambda: ops.gptq_sweep_r(Ws.clone(), r32, ud32, cb), reps=5)
+            print(f"[{r}x{n}] hinv {t_h:9.1f} us   sweep {t_s:9.1f} us   argsort {t_a:7.1f} us  info={int(info.item())}"
+                  f"   chol {t_c:9.1f} us  sweep_r {t_r:9.1f} us  info={int(info2.item())}")
     if what in ("search", "all"):
         for r, n in ((768, 768), (3072, 768), (768, 3072)):
             W, H, _ = wl.synthetic_layer(r, n, 0, samples=256)
