@@ -96,6 +96,10 @@ int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const slk_codeboo
                          const float* factors, int32_t G, const void* hdiag, int32_t h_dtype,
                          float* out_scale, float* out_err, float* out_init, void* stream);
 
+/* Tests / A-B runs: 1 forces the direct op-chain kernel of slk_scale_search_f32, 0 restores the
+ * default (exact threshold tables for uniform codebooks of <= 16 entries; identical results). */
+int slk_debug_scale_search_direct(int on);
+
 /* ---- K6: H-weighted error ---------------------------------------------------
  * channelwise_error  ((W-Q) @ H * (W-Q)).sum(-1)            obq.py:89-95
  * _compute_mse with a 2-D H                                 scaling.py:91-95
@@ -175,6 +179,9 @@ size_t slk_chol_factor_ws_bytes(int64_t n);
 int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const float* dampval,
                         void* ws, size_t ws_bytes, float* r32, float* ud32, int32_t* info,
                         void* stream);
+
+/* Development aid: per-tile-task trace of the Cholesky kernel (8 int64 per task); NULL disables. */
+int slk_debug_chol_trace(void* buf);
 
 /* ---- K3: GPTQ / OBQ sweep ------------------------------------------------------
  * _quantize_opt_block / _quantize_opt_core                    obq.py:106-137

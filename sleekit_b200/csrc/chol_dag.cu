@@ -219,6 +219,15 @@ __device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t*
   }
 }
 
+// Optional per-task trace (development aid, tools/chol_trace.py): 8 int64 per task --
+// i, j, globaltimer at start / end, clock64 after the ticket / k loop / tile math / publish.
+__device__ long long* g_chol_trace = nullptr;
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---- the tile-task kernel ----------------------------------------------------------------------------
 // A: [T*64, ld] fp64, lower triangle in, L out.  Dinv: [T, 64, 64] inverses of the diagonal tiles.
 // sync: [T*T] ready flags followed by the ticket counter.
@@ -244,6 +253,8 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
     while (rem >= T - j) { rem -= T - j; ++j; }
     const int i = j + rem;
     const bool diag = (i == j);
+    long long* tr = (g_chol_trace && tid == 0) ? g_chol_trace + (int64_t)t * 8 : nullptr;
+    if (tr) { tr[0] = i; tr[1] = j; tr[2] = gtimer(); tr[4] = clock64(); }
     const double* Ai = A + (int64_t)i * CT * ld;
     const double* Aj = A + (int64_t)j * CT * ld;
     double* Cij = A + (int64_t)i * CT * ld + (int64_t)j * CT;
@@ -312,6 +323,7 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();   // the ring is dead: its storage becomes M / X / T
+    if (tr) tr[5] = clock64();
 
     if (diag) {
 #pragma unroll
@@ -378,9 +390,11 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
           *reinterpret_cast<double2*>(Cij + (int64_t)row * ld + col) = make_double2(out[ii][jj][0], out[ii][jj][1]);
         }
     }
+    if (tr) tr[6] = clock64();
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
+    if (tr) { tr[7] = clock64(); tr[3] = gtimer(); }
   }
 }
 
@@ -447,6 +461,13 @@ static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const 
 using namespace slk;
 
 extern "C" {
+
+/* development aid: per-task trace buffer (8 int64 per tile task), NULL disables */
+int slk_debug_chol_trace(void* buf) {
+  long long* p = (long long*)buf;
+  SLK_CUDA(cudaMemcpyToSymbol(g_chol_trace, &p, sizeof(p)));
+  return SLK_OK;
+}
 
 size_t slk_chol_factor_ws_bytes(int64_t n) {
   const int64_t npad = cpad64(n);

@@ -327,33 +327,29 @@ __global__ void __launch_bounds__(256) order_keys_kernel(const float* __restrict
 }
 
 // Stable rank sort: order[rank(j)] = j with rank = #{i : key_i < key_j or (== and i < j)}.
-// O(n^2) compares spread over the grid; n <= a few 10^4 here, so this is microseconds and
-// needs no scratch.  NaN keys sort last (as numpy does).
+// One WARP per key: the lanes split the n candidates and a shuffle reduction adds the counts, so
+// the serial chain is n/32 compares (n = 3072: 96) and the grid has n/8 CTAs.  Keys are mapped to
+// order-preserving unsigned integers first (-0 = +0, NaN last, as numpy sorts).  No scratch.
+__device__ __forceinline__ unsigned long long sortable_key(double k) {
+  if (k != k) return ~0ull;
+  k = __dadd_rn(k, 0.0);                                   // -0.0 -> +0.0
+  const unsigned long long b = (unsigned long long)__double_as_longlong(k);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
 __global__ void __launch_bounds__(256) argsort_rank_kernel(const double* __restrict__ keys, int64_t n,
                                                            int64_t* __restrict__ order) {
-  __shared__ double tile[1024];
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const double kj = j < n ? keys[j] : 0.0;
-  const bool nanj = kj != kj;
-  int64_t rank = 0;
-  for (int64_t base = 0; base < n; base += 1024) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < 1024; t += blockDim.x) tile[t] = base + t < n ? keys[base + t] : 0.0;
-    __syncthreads();
-    int lim = (int)((n - base) < 1024 ? (n - base) : 1024);
-    if (j < n) {
-      for (int t = 0; t < lim; ++t) {
-        double ki = tile[t];
-        int64_t i = base + t;
-        bool nani = ki != ki;
-        bool before;
-        if (nanj) before = !nani || i < j;
-        else before = !nani && (ki < kj || (ki == kj && i < j));
-        rank += before ? 1 : 0;
-      }
-    }
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const unsigned long long uj = sortable_key(__ldg(keys + j));
+  int cnt = 0;
+  for (int64_t i = lane; i < n; i += 32) {
+    const unsigned long long ui = sortable_key(__ldg(keys + i));
+    cnt += (ui < uj || (ui == uj && i < j)) ? 1 : 0;
   }
-  if (j < n) order[rank] = j;
+  cnt = warp_sum(cnt);
+  if (lane == 0) order[cnt] = j;
 }
 
 // Exhaustive check of fastdiv_core against the IEEE divide: for each divisor, all 2^32 dividends.
@@ -535,7 +531,7 @@ int slk_order_keys(const float* h, int64_t n, const float* dampval, const float*
 
 int slk_argsort_f64(const double* keys, int64_t n, int64_t* order, void* stream) {
   SLK_REQUIRE(keys && order && n >= 1, "bad arguments");
-  argsort_rank_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, order);
+  argsort_rank_kernel<<<(int)ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(keys, n, order);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

@@ -1,9 +1,12 @@
-set -x
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests -m gpu -x -q -k "cholesky_form" > gpurun_out/pytest_s2b.log 2>&1; echo "pytest rc=$?" 
-tail -30 gpurun_out/pytest_s2b.log
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2b_all.log 2>&1; echo "pytest all rc=$?"
-tail -5 gpurun_out/pytest_s2b_all.log
-timeout 300 python tools/microbench.py sweep > gpurun_out/micro_s2b.log 2>&1; tail -20 gpurun_out/micro_s2b.log
-timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_s2b.log 2>&1; echo "bench rc=$?"
-tail -c 1500 gpurun_out/bench_s2b.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_s2d.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_s2d.log
+timeout 300 python tools/microbench.py search > gpurun_out/micro_s2d.log 2>&1; tail -5 gpurun_out/micro_s2d.log
+SLK_SEARCH_TABLE=0 timeout 300 python tools/microbench.py search 2>&1 | tail -3
+timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_s2d.log 2>&1; echo "bench rc=$?"
+python - <<'PY'
+import json
+for ln in open("gpurun_out/bench_s2d.log"):
+    if ln.startswith("{"):
+        d=json.loads(ln); print(d["ms_per_step"], d["serial_phases_ms_per_step"], d["layer_error_mean"])
+PY
