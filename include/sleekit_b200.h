@@ -172,16 +172,21 @@ int slk_hinv_from_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, dou
 
 /* K2 without the triangular inverse (the form the fused quantize_opt path uses):
  * R = flip(cholesky(flip(H_opt[order][:, order]))) in fp64 (obq.py:46-50), i.e. H_opt = R R^T and
- * compute_hessian_chol's U = R^-1.  Outputs: r32 [n, n] fp32 rounding of R (upper, zeros below) and
- * ud32 [ceil(n/32), 32, 32] fp32: the inverses of R's 32x32 diagonal blocks (= diagonal blocks of
- * U; identity-padded for a ragged last block).  One tile-task kernel, no dependent launches. */
+ * compute_hessian_chol's U = R^-1.  Outputs: r32 [n, n] fp32 rounding of R (upper, zeros below),
+ * rt_hi / rt_lo [n, n] (may both be NULL) its transpose split into TF32 parts, hi + lo = R^T
+ * (only the part on and below the diagonal is written: the K-major operand of the sweep's
+ * tensor-core GEMMs) and ud32 [ceil(n/32), 32, 32] fp32: the
+ * inverses of R's 32x32 diagonal blocks (= diagonal blocks of U; identity-padded for a ragged last
+ * block).  One tile-task kernel, no dependent launches. */
 size_t slk_chol_factor_ws_bytes(int64_t n);
 int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const float* dampval,
-                        void* ws, size_t ws_bytes, float* r32, float* ud32, int32_t* info,
-                        void* stream);
+                        void* ws, size_t ws_bytes, float* r32, float* rt_hi, float* rt_lo,
+                        float* ud32, int32_t* info, void* stream);
 
 /* Development aid: per-tile-task trace of the Cholesky kernel (8 int64 per task); NULL disables. */
 int slk_debug_chol_trace(void* buf);
+/* Same for the macro-block sweep kernel: 8 int64 phase clocks per 32-column block of CTA 0. */
+int slk_debug_sweep_trace(void* buf);
 
 /* ---- K3: GPTQ / OBQ sweep ------------------------------------------------------
  * _quantize_opt_block / _quantize_opt_core                    obq.py:106-137
@@ -197,8 +202,14 @@ int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, const double* u
 /* Same sweep from the Cholesky factor (slk_chol_factor_f32) instead of the inverse factor:
  * block J is formed as W[:, J] + ((W-Q)[:, :a] R[:a, J]) U_JJ, which equals obq.py:137's
  * W[:, J] - E[:, :a] U[:a, J].  q in/out as above; d [r, n] out: W - Q (scaled, permuted domain). */
+/* Columns are cut into macro blocks of 256; inside one the fused kernel propagates locally,
+ * between them one tcgen05 GEMM (fp32-faithful 3xTF32) accumulates D[:, s:e] R[s:e, e:] for all
+ * later columns (needs rt_hi / rt_lo and the workspace; without them, or for n < 512, one fused
+ * launch).  The leaf writes D already split into TF32 parts, so a macro block costs two launches. */
+size_t slk_gptq_sweep_r_ws_bytes(int64_t r, int64_t n);
 int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32,
-                         const float* ud32, const slk_codebook* cb_host, void* stream);
+                         const float* rt_hi, const float* rt_lo, const float* ud32,
+                         const slk_codebook* cb_host, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K7: best-first local search ------------------------------------------------
  * quantize_local_search / LocalSearchQuantizer                obq.py:234-358

@@ -73,10 +73,12 @@ SIGNATURES = {
     "slk_hinv_from_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P, _P, _P]),
     "slk_hinv_from_f64": (_INT, [_P, _I64, _P, _SZ, _P, _P, _P, _P]),
     "slk_chol_factor_ws_bytes": (_SZ, [_I64]),
-    "slk_chol_factor_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P, _P, _P]),
+    "slk_chol_factor_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
+    "slk_gptq_sweep_r_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_debug_chol_trace": (_INT, [_P]),
+    "slk_debug_sweep_trace": (_INT, [_P]),
     "slk_debug_scale_search_direct": (_INT, [_INT]),
-    "slk_gptq_sweep_r_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _CB, _P]),
+    "slk_gptq_sweep_r_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _P, _CB, _P, _SZ, _P]),
     "slk_gptq_sweep_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _CB, _I32, _I32, _I32, _P]),
     "slk_local_search_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_local_search_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _P]),

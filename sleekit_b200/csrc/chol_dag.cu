@@ -20,6 +20,7 @@
 // however few CTAs are resident (the decoupled look-back argument).  No dependent launches: the
 // n/64-panel launch chain of the right-looking version (hinv.cu) becomes in-kernel flag latency.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace slk {
 
@@ -398,26 +399,52 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
   }
 }
 
-// R32[a, b] = L[npad-1-a, npad-1-b] for b >= a (0 below); Ud[blk][p][q] = inverse of the 32x32
-// diagonal block R[32blk.., 32blk..] = flip of the matching diagonal block of the tile inverses.
+// R32[a, b] = L[npad-1-a, npad-1-b] for b >= a (0 below); rt_hi + rt_lo = R32^T on and below its
+// diagonal, split into TF32 parts (the part above is never read and left untouched); Ud[blk][p][q] = inverse of the 32x32 diagonal
+// block R[32blk.., 32blk..] = flip of the matching diagonal block of the tile inverses.
+// One CTA per 32x32 tile pair (ta <= tb); the transpose goes through shared memory so that all
+// global accesses are coalesced.
 __global__ void __launch_bounds__(256) chol_export_kernel(const double* __restrict__ A, int64_t n, int64_t npad,
                                                           const double* __restrict__ Dinv, float* __restrict__ r32,
+                                                          float* __restrict__ rt_hi, float* __restrict__ rt_lo,
                                                           float* __restrict__ ud32) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = n * n;
-  for (int64_t t = t0; t < total; t += stride) {
-    const int64_t a = t / n, b = t - a * n;
-    r32[t] = (b >= a) ? (float)A[(npad - 1 - a) * npad + (npad - 1 - b)] : 0.0f;
+  __shared__ float tile[32][33];
+  const int64_t nt = (n + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // linear block id -> (ta, tb), tb >= ta
+  int64_t ta = 0, rem = blockIdx.x;
+  while (rem >= nt - ta) { rem -= nt - ta; ++ta; }
+  const int64_t tb = ta + rem;
+  const int64_t a0 = ta * 32, b0 = tb * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t a = a0 + i, b = b0 + tx;
+    float v = 0.0f;
+    if (a < n && b < n && b >= a) v = (float)A[(npad - 1 - a) * npad + (npad - 1 - b)];
+    tile[i][tx] = v;
+    if (a < n && b < n) r32[a * n + b] = v;
+    if (tb > ta) {                                   // mirror tile of R32 is all zeros
+      const int64_t a2 = b0 + i, b2 = a0 + tx;
+      if (a2 < n && b2 < n) r32[a2 * n + b2] = 0.0f;
+    }
   }
-  const int64_t nblk = (n + 31) / 32;
-  for (int64_t t = t0; t < nblk * 1024; t += stride) {
-    const int64_t blk = t >> 10;
-    const int p = (int)((t >> 5) & 31), q = (int)(t & 31);
-    const int64_t fb = npad / 32 - 1 - blk;          // 32-block index in factor order
-    const int64_t tile = fb >> 1;
+  __syncthreads();
+  if (rt_hi) {
+    for (int i = ty; i < 32; i += 8) {
+      const int64_t row = b0 + i, col = a0 + tx;     // RT[b][a] = R[a][b], already split for the tensor path
+      if (row < n && col < n) {
+        float h, l;
+        split_tf32(tile[tx][i], h, l);
+        rt_hi[row * n + col] = h;
+        rt_lo[row * n + col] = l;
+      }
+    }
+  }
+  if (ta == tb) {
+    const int64_t fb = npad / 32 - 1 - ta;           // 32-block index in factor order
+    const int64_t tl = fb >> 1;
     const int sub = (int)(fb & 1) * 32;
-    ud32[t] = (float)Dinv[tile * CT * CT + (int64_t)(sub + 31 - p) * CT + (sub + 31 - q)];
+    for (int i = ty; i < 32; i += 8)
+      ud32[ta * 1024 + i * 32 + tx] = (float)Dinv[tl * CT * CT + (int64_t)(sub + 31 - i) * CT + (sub + 31 - tx)];
   }
 }
 
@@ -425,7 +452,7 @@ static inline int64_t cpad64(int64_t n) { return (n + CT - 1) / CT * CT; }
 
 template <typename TS>
 static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const float* dampval, void* ws, size_t ws_bytes,
-                            float* r32, float* ud32, int32_t* info, cudaStream_t st) {
+                            float* r32, float* rt_hi, float* rt_lo, float* ud32, int32_t* info, cudaStream_t st) {
   SLK_REQUIRE(h && info && r32 && ud32 && n >= 1, "bad arguments");
   SLK_REQUIRE(ws && ws_bytes >= slk_chol_factor_ws_bytes(n), "workspace too small");
   const int64_t npad = cpad64(n);
@@ -450,8 +477,8 @@ static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const 
   if (grid > 2 * (int64_t)sm_count()) grid = 2 * (int64_t)sm_count();
   chol_dag_kernel<<<(unsigned)grid, CTH, sizeof(CholSmem), st>>>(A, npad, T, Dinv, sync, info);
   SLK_LAUNCH_CHECK();
-  blocks = ceil_div(n * n, 256);
-  chol_export_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(A, n, npad, Dinv, r32, ud32);
+  const int64_t nt32 = (n + 31) / 32;
+  chol_export_kernel<<<(unsigned)(nt32 * (nt32 + 1) / 2), 256, 0, st>>>(A, n, npad, Dinv, r32, rt_lo ? rt_hi : nullptr, rt_lo, ud32);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -476,8 +503,9 @@ size_t slk_chol_factor_ws_bytes(int64_t n) {
 }
 
 int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const float* dampval, void* ws,
-                        size_t ws_bytes, float* r32, float* ud32, int32_t* info, void* stream) {
-  return chol_factor_impl<float>(h, n, order, dampval, ws, ws_bytes, r32, ud32, info, (cudaStream_t)stream);
+                        size_t ws_bytes, float* r32, float* rt_hi, float* rt_lo, float* ud32, int32_t* info,
+                        void* stream) {
+  return chol_factor_impl<float>(h, n, order, dampval, ws, ws_bytes, r32, rt_hi, rt_lo, ud32, info, (cudaStream_t)stream);
 }
 
 }  // extern "C"

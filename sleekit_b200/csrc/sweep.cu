@@ -7,6 +7,7 @@
 // obq.py:114-118, so given the same fp64 U a leaf is bit-identical to the reference.  Trailing updates Q[:, b:end] -= E[:, a:b] @ U[a:b, b:end] are fp32 GEMMs
 // with exact-product fmaf accumulation on the fp32 rounding of U (parity-safe).
 #include "gemm.cuh"
+#include "tc_gemm.cuh"
 
 #include <stdlib.h>
 
@@ -116,18 +117,25 @@ template <int WIN>
 __device__ __forceinline__ void leaf_phase32(float (&q)[32], const LeafShared32& sh, int i0, int width,
                                              const DevGrid<float>& g, const FastDivF& fstep, bool fastq,
                                              float* __restrict__ qrow, float* __restrict__ erow,
-                                             const float* __restrict__ w0 = nullptr) {
+                                             const float* __restrict__ w0 = nullptr, float* dsm = nullptr) {
 #pragma unroll 1
   for (int t = 0; t < 8; ++t) {
     const int i = i0 + t;
     if (i >= width) return;
     const float w = q[0];
     const float qq = fastq ? uniform_value_fast(g, fstep, w) : grid_value(g, w);
-    FastDivF fd;
-    fd.d = sh.U[i][i]; fd.y = sh.Uy[i]; fd.ok = sh.Uok[i];
-    const float res = fastdiv(__fsub_rn(w, qq), fd);
+    float res;
+    if (w0) {
+      res = __fmul_rn(__fsub_rn(w, qq), sh.Uy[i]);   // R form: Uy = R[i][i] = 1 / U[i][i]
+    } else {
+      FastDivF fd;
+      fd.d = sh.U[i][i]; fd.y = sh.Uy[i]; fd.ok = sh.Uok[i];
+      res = fastdiv(__fsub_rn(w, qq), fd);
+    }
     qrow[i] = qq;
-    erow[i] = w0 ? __fsub_rn(w0[i], qq) : res;   // R form: D = W - Q of the ORIGINAL weight
+    const float dv = w0 ? __fsub_rn(w0[i], qq) : res;   // R form: D = W - Q of the ORIGINAL weight
+    erow[i] = dv;
+    if (dsm) dsm[i] = dv;
     const float* urow = &sh.U[i][i];
 #pragma unroll
     for (int j = 1; j < WIN; ++j) q[j - 1] = __fmaf_rn(-res, urow[j], q[j]);
@@ -220,10 +228,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // RFORM = true : U is the Cholesky factor R (H_opt = R R^T), Ud the 32x32 diagonal-block inverses
 //                (chol_dag.cu), E holds D = W - Q, and the block is formed as
 //                W[:, J] + (D[:, :a] R[:a, J]) Ud_J  -- same algebra, no full inverse.
+// The kernel sweeps the column range [c0, c1) (c0 a multiple of 32) and forms the propagated term
+// from the columns [c0, a) only; what the columns before c0 contribute arrives in Pacc (R form:
+// Pacc[:, J] = D[:, :c0] R[:c0, J], accumulated by tensor-core GEMMs between macro blocks).
 template <int R, bool RFORM>
 __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r, int64_t n,
                                                          const float* __restrict__ U, const float* __restrict__ Ud,
-                                                         DevGrid<float> g) {
+                                                         DevGrid<float> g, int64_t c0, int64_t c1,
+                                                         const float* __restrict__ Pacc) {
   typedef FusedSmem<R> SM;
   constexpr int KG = SM::KG;
   constexpr int KSUP = 32 * KG;                       // k covered by one ring stage
@@ -238,12 +250,14 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
   const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
   const bool fastq = (g.kind == 0) && fstep.ok;
 
-  for (int64_t a = 0; a < n; a += 32) {
-    const int width = (int)((n - a) < 32 ? (n - a) : 32);
+  for (int64_t a = c0; a < c1; a += 32) {
+    const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
     const bool fullw = aligned && width == 32;
     // operands of the leaf are requested now and parked in registers: their latency hides
     // behind the product loop
-    float ud[4], wq[4];
+    float ud[4], wq[4], pa[4] = {0.f, 0.f, 0.f, 0.f};
+    float rdiag = 1.0f;
+    if (RFORM && tid < 32) rdiag = (tid < width) ? __ldg(U + (a + tid) * n + (a + tid)) : 1.0f;
     {
       const int i = tid >> 3;
 #pragma unroll
@@ -252,14 +266,15 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
         if (RFORM) ud[j] = __ldg(Ud + (a / 32) * 1024 + i * 32 + c);
         else ud[j] = (i < width && c < width) ? __ldg(U + (a + i) * n + (a + c)) : ((i == c) ? 1.0f : 0.0f);
         wq[j] = (kg == 0 && grow < r && c < width) ? __ldcg(Q + grow * n + a + c) : 0.0f;
+        if (RFORM && Pacc) pa[j] = (kg == 0 && grow < r && c < width) ? __ldcg(Pacc + grow * n + a + c) : 0.0f;
       }
     }
     // ---- (1) Qb = W[:, a:a+32] - E[:, :a] @ U[:a, a:a+32] -----------------------------------
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int nsup = (int)((a + KSUP - 1) / KSUP);
+    const int nsup = (int)((a - c0 + KSUP - 1) / KSUP);
     auto load_stage = [&](int c) {
       const int st = c % FST;
-      const int64_t k0 = (int64_t)c * KSUP;
+      const int64_t k0 = c0 + (int64_t)c * KSUP;
       const int64_t ke = k0 + 32 * kg;               // this thread's k-group for the E piece
       float* de = &sm.E[st][kg][lrow][seg * 4];
       if (ke < a) {
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
       if (c + FST - 1 < nsup) load_stage(c + FST - 1);
       cp_async_commit();
       const int st = c % FST;
-      if ((int64_t)c * KSUP + 32 * kg < a) {
+      if (c0 + (int64_t)c * KSUP + 32 * kg < a) {
 #pragma unroll
         for (int kk = 0; kk < 32; ++kk) {
           const float e = sm.E[st][kg][lrow][kk];
@@ -323,6 +338,7 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
 #pragma unroll
         for (int q = 1; q < KG; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
         if (RFORM) {
+          t = __fadd_rn(t, pa[j]);                 // + what the columns before c0 contribute
           sm.Qs[lrow][seg * 4 + j] = t;            // P = D[:, :a] R[:a, J], multiplied by Ud_J below
           sm.W0[lrow][seg * 4 + j] = wq[j];
         } else {
@@ -351,9 +367,13 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
       }
     }
     if (tid < 32) {
-      const FastDivF f = make_fastdiv(sm.leaf.U[tid][tid]);
-      sm.leaf.Uy[tid] = f.y;
-      sm.leaf.Uok[tid] = f.ok;
+      if (RFORM) {
+        sm.leaf.Uy[tid] = rdiag;
+      } else {
+        const FastDivF f = make_fastdiv(sm.leaf.U[tid][tid]);
+        sm.leaf.Uy[tid] = f.y;
+        sm.leaf.Uok[tid] = f.ok;
+      }
     }
     __syncthreads();
     // ---- (2) leaf: one thread per row ----------------------------------------------------------
@@ -375,14 +395,15 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
 
 template <int R, bool RFORM>
 static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u32, const float* ud, const DevGrid<float>& g,
-                        cudaStream_t st) {
+                        cudaStream_t st, int64_t c0 = 0, int64_t c1 = -1, const float* pacc = nullptr) {
+  if (c1 < 0) c1 = n;
   auto kern = sweep_fused_kernel<R, RFORM>;
   static bool attr_done = false;
   if (!attr_done) {
     SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<R>)));
     attr_done = true;
   }
-  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, ud, g);
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, ud, g, c0, c1, pacc);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -460,18 +481,337 @@ extern "C" int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, cons
   return sweep_range(c, 0, n);
 }
 
-// R form of the sweep: r32 = Cholesky factor R (upper, H_opt = R R^T), ud32 = [ceil(n/32), 32, 32]
-// inverses of its diagonal blocks (slk_chol_factor_f32).  d receives W - Q.
-extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud32,
-                                    const slk_codebook* cb, void* stream) {
+// ---- macro-block kernel (R form) ------------------------------------------------------------------
+// Sweeps ONE macro block [c0, c1), c1 - c0 <= MB_COLS, with everything the dependent chain touches
+// resident in shared memory: the block's D (written by the leaf, read by the products), and the
+// R panel R[c0:a, J] of the NEXT 32-column block, prefetched with cp.async while the current block
+// is being swept; the leaf operands of the next block (W, Pacc, Ud, diag R) are prefetched into
+// registers the same way.  Per 32 columns the chain is: local product from shared memory ->
+// 32x32 multiply by Ud_J -> leaf.  No global-memory latency sits on it.
+// Leaf of the macro kernel: FOUR lanes per row, 8 columns each.  For every group of 8 columns
+// (A) the owning lane walks its 8 columns alone -- round, residual res = (w - q) * R[i][i], update
+// of its remaining columns -- so the dependent chain never crosses a lane; (B) the 8 residuals are
+// shuffled to the row's lanes and the lanes that own later columns apply them (64 independent
+// FMAs).  obq.py:110-118 in the R form; D = W - q goes to shared memory and to HBM.
+template <bool FASTQ>
+__device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh, const DevGrid<float>& g,
+                                           const FastDivF& fstep, int width, int part, int lane, bool rowok,
+                                           float* __restrict__ qrow, float* __restrict__ drow,
+                                           float* __restrict__ dhi, float* __restrict__ dlo,
+                                           const float (&w0)[8], float* __restrict__ dsm) {
+  const float top = (float)(g.size - 1);
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    if (p * 8 >= width) break;
+    float resv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (part == p) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int i = p * 8 + t;
+        const float w = q[t];
+        float qq;
+        if (FASTQ) {
+          // codebook.py:60-64 with the divide by the step through the exact reciprocal scheme and
+          // rint through the 1.5*2^23 constant (identical after the clip for every finite input)
+          const float tt = fastdiv_core(__fsub_rn(w, g.zero), fstep.d, fstep.y);
+          float k = __fsub_rn(__fadd_rn(tt, 12582912.0f), 12582912.0f);
+          k = fminf(fmaxf(k, 0.0f), top);
+          qq = __fadd_rn(__fmul_rn(k, g.step), g.zero);
+        } else {
+          qq = grid_value(g, w);
+        }
+        const float res = __fmul_rn(__fsub_rn(w, qq), sh.Uy[i]);
+        resv[t] = res;
+        if (t < 7) {
+          const float4 ua = *reinterpret_cast<const float4*>(&sh.U[i][p * 8]);
+          const float4 ub = *reinterpret_cast<const float4*>(&sh.U[i][p * 8 + 4]);
+          const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+          for (int c = t + 1; c < 8; ++c) q[c] = __fmaf_rn(-res, u[c], q[c]);
+        }
+        const float dv = __fsub_rn(w0[t], qq);
+        const bool in = i < width;
+        dsm[i] = in ? dv : 0.0f;
+        if (rowok && in) {
+          qrow[i] = qq;
+          drow[i] = dv;
+          if (dhi) {                                   // TF32 parts for the macro-block GEMM
+            float h, l;
+            split_tf32(dv, h, l);
+            dhi[i] = h;
+            dlo[i] = l;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int owner_lane = (lane & ~3) | p;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) resv[t] = __shfl_sync(0xffffffffu, resv[t], owner_lane);
+    if (part > p) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float4 ua = *reinterpret_cast<const float4*>(&sh.U[p * 8 + t][part * 8]);
+        const float4 ub = *reinterpret_cast<const float4*>(&sh.U[p * 8 + t][part * 8 + 4]);
+        const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = __fmaf_rn(-resv[t], u[c], q[c]);
+      }
+    }
+  }
+}
+
+constexpr int MB_COLS = 256;
+constexpr int MB_PITCH = MB_COLS + 4;
+__device__ long long* g_sweep_trace = nullptr;   // development aid: per-block phase clocks of CTA 0
+
+template <int R>
+struct MacroSmem {
+  static constexpr int KG = 32 / R;
+  float Dm[R][MB_PITCH];                    // D = W - Q of this macro block
+  float Rs[2][MB_COLS - 32][32];            // R[c0 + k][a + col], k < a - c0
+  float red[KG][R][33];
+  float Qs[R][33];
+  float W0[R][33];
+  LeafShared32 leaf;
+};
+
+template <int R>
+__global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int64_t n,
+                                                         const float* __restrict__ Rf, const float* __restrict__ Ud,
+                                                         DevGrid<float> g, int64_t c0, int64_t c1,
+                                                         const float* __restrict__ Pacc, float* __restrict__ Dhi,
+                                                         float* __restrict__ Dlo) {
+  typedef MacroSmem<R> SM;
+  constexpr int KG = SM::KG;
+  extern __shared__ __align__(16) unsigned char macro_raw[];
+  SM& sm = *reinterpret_cast<SM*>(macro_raw);
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int kg = tid / (R * 8), lt = tid % (R * 8);
+  const int lrow = lt >> 3, seg = lt & 7;
+  const int64_t grow = row0 + lrow;
+  const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
+  const bool fastq = (g.kind == 0) && fstep.ok;
+
+  // leaf operands of a block, fetched one block ahead
+  struct Pre { float ud[4], wq[4], pa[4], rdiag; };
+  auto fetch = [&](int64_t a, Pre& p) {
+    const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
+    const int i = tid >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = seg * 4 + j;
+      p.ud[j] = __ldg(Ud + (a / 32) * 1024 + i * 32 + c);
+      const bool in = (kg == 0 && grow < r && c < width);
+      p.wq[j] = in ? __ldcg(Q + grow * n + a + c) : 0.0f;
+      p.pa[j] = (in && Pacc) ? __ldcg(Pacc + grow * n + a + c) : 0.0f;
+    }
+    p.rdiag = (tid < width) ? __ldg(Rf + (a + tid) * n + (a + tid)) : 1.0f;
+  };
+  // R panel of block a: rows c0 .. a-1, columns a .. a+31 (zero beyond c1)
+  auto prefetch_panel = [&](int64_t a, int buf) {
+    const int rows = (int)(a - c0);
+    const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
+    for (int t = tid; t < rows * 8; t += FT) {
+      const int k = t >> 3, piece = t & 7;
+      float* dst = &sm.Rs[buf][k][piece * 4];
+      const float* src = Rf + (c0 + k) * n + a + piece * 4;
+      if (piece * 4 + 4 <= width) cp_async16(dst, src);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = (piece * 4 + j < width) ? __ldg(src + j) : 0.0f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  Pre cur, nxt;
+  fetch(c0, cur);
+  cp_async_commit();                                   // block c0 has no panel: empty group keeps the counting uniform
+  int buf = 0;
+  for (int64_t a = c0; a < c1; a += 32, buf ^= 1) {
+    const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
+    const int ka = (int)(a - c0);                      // k extent of this block's product
+    const bool has_next = a + 32 < c1;
+    if (has_next) {
+      prefetch_panel(a + 32, buf ^ 1);
+      fetch(a + 32, nxt);
+    } else {
+      cp_async_commit();
+    }
+    long long* tr = (g_sweep_trace && blockIdx.x == 0 && tid == 0) ? g_sweep_trace + ((a - c0) / 32) * 8 : nullptr;
+    if (tr) tr[0] = clock64();
+    cp_async_wait<1>();                                // this block's panel has landed
+    __syncthreads();
+    if (tr) tr[1] = clock64();
+    // ---- (1) P = D[:, c0:a] R[c0:a, J] from shared memory, split over the k groups --------------
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kb = kg * 32; kb < ka; kb += 32 * KG) {
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        const float e = sm.Dm[lrow][kb + kk];
+        const float4 u = *reinterpret_cast<const float4*>(&sm.Rs[buf][kb + kk][seg * 4]);
+        acc[0] = __fmaf_rn(e, u.x, acc[0]);
+        acc[1] = __fmaf_rn(e, u.y, acc[1]);
+        acc[2] = __fmaf_rn(e, u.z, acc[2]);
+        acc[3] = __fmaf_rn(e, u.w, acc[3]);
+      }
+    }
+    {
+      const int i = tid >> 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm.leaf.U[i][seg * 4 + j] = cur.ud[j];
+        sm.leaf.U[i][32 + seg * 4 + j] = 0.0f;
+        sm.red[kg][lrow][seg * 4 + j] = acc[j];
+      }
+      if (tid < 32) sm.leaf.Uy[tid] = cur.rdiag;
+    }
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = sm.red[0][lrow][seg * 4 + j];
+#pragma unroll
+        for (int q = 1; q < KG; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
+        sm.Qs[lrow][seg * 4 + j] = __fadd_rn(t, cur.pa[j]);
+        sm.W0[lrow][seg * 4 + j] = cur.wq[j];
+      }
+    }
+    __syncthreads();
+    // ---- (2) block = W + P Ud_J --------------------------------------------------------------------
+    if (tr) tr[2] = clock64();
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kg == 0) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float pv = sm.Qs[lrow][c];
+        const float4 u = *reinterpret_cast<const float4*>(&sm.leaf.U[c][seg * 4]);
+        s4[0] = __fmaf_rn(pv, u.x, s4[0]);
+        s4[1] = __fmaf_rn(pv, u.y, s4[1]);
+        s4[2] = __fmaf_rn(pv, u.z, s4[2]);
+        s4[3] = __fmaf_rn(pv, u.w, s4[3]);
+      }
+    }
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm.Qs[lrow][seg * 4 + j] = __fadd_rn(cur.wq[j], s4[j]);
+    }
+    __syncthreads();
+    // ---- (3) leaf: FOUR lanes per row, 8 columns each -- the owner of column i quantises it and
+    // forms the residual, a shuffle hands it to the row's other lanes, every lane updates its own
+    // columns (<= 8 FMAs instead of 31 in one thread).  D goes to shared memory (next products)
+    // and to HBM (macro-block GEMM).  obq.py:110-118 in the R form.
+    if (tr) tr[3] = clock64();
+    if (tid < R * 4) {
+      const int lr = tid >> 2, part = tid & 3, lane = tid & 31;
+      const bool rowok = row0 + lr < r;
+      float q[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) q[c] = sm.Qs[lr][part * 8 + c];
+      float* qrow = Q + (row0 + lr) * n + a;
+      float* drow = D + (row0 + lr) * n + a;
+      float w0[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w0[c] = sm.W0[lr][part * 8 + c];
+      float* dsm = &sm.Dm[lr][ka];
+      float* dhi = Dhi ? Dhi + (row0 + lr) * n + a : nullptr;
+      float* dlo = Dhi ? Dlo + (row0 + lr) * n + a : nullptr;
+      if (fastq) leaf_rows4<true>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
+      else leaf_rows4<false>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
+    }
+    if (tr) tr[4] = clock64();
+    cur = nxt;
+    if (tr) tr[5] = clock64();
+    // the barrier at the top of the next iteration orders Dm / Qs / leaf reuse
+  }
+}
+
+extern "C" int slk_debug_sweep_trace(void* buf) {
+  long long* p = (long long*)buf;
+  SLK_CUDA(cudaMemcpyToSymbol(g_sweep_trace, &p, sizeof(p)));
+  return SLK_OK;
+}
+
+template <int R>
+static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
+                        cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) {
+  auto kern = sweep_macro_kernel<R>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MacroSmem<R>)));
+    attr_done = true;
+  }
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+// R form of the sweep: r32 = Cholesky factor R (upper, H_opt = R R^T), rt32 = its transpose, ud32 =
+// [ceil(n/32), 32, 32] inverses of its diagonal blocks (slk_chol_factor_f32).  d receives W - Q.
+// Lazy batching (obq.py:121-137's idea, two levels): the columns are cut into macro blocks of
+// SWEEP_MB; inside one the fused kernel propagates locally, between them ONE tensor-core GEMM
+// (tcgen05, fp32-faithful 3xTF32) pushes the finished block to every later column:
+//     Pacc[:, e:] += D[:, s:e] R[s:e, e:]
+static constexpr int64_t SWEEP_MB = MB_COLS;
+
+static bool sweep_macro_ok(int64_t r, int64_t n, const float* d, const float* rt_hi, const float* rt_lo) {
+  static int off = -1;
+  if (off < 0) {
+    const char* ev = getenv("SLK_SWEEP_MACRO");
+    off = (ev && ev[0] == '0') ? 1 : 0;
+  }
+  return !off && rt_hi != nullptr && rt_lo != nullptr && n >= 2 * SWEEP_MB && tc_gemm_usable(rt_hi, n, rt_lo, n);
+}
+
+extern "C" size_t slk_gptq_sweep_r_ws_bytes(int64_t r, int64_t n) {
+  if (n < 2 * SWEEP_MB || n % 4 != 0) return 256;
+  return (size_t)3 * r * n * sizeof(float) + 1024;     // Pacc, D_hi, D_lo
+}
+
+extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* rt_hi,
+                                    const float* rt_lo, const float* ud32, const slk_codebook* cb, void* ws,
+                                    size_t ws_bytes, void* stream) {
   int rc = check_codebook(cb);
   if (rc) return rc;
   SLK_REQUIRE(r >= 0 && n >= 1, "bad shape");
   if (r == 0) return SLK_OK;
   SLK_REQUIRE(q && d && r32 && ud32, "NULL pointer");
   const DevGrid<float> g = make_grid<float>(cb);
-  const int64_t want = 2 * (int64_t)sm_count();
-  if (r >= 32 * want) return launch_fused<32, true>(q, d, r, n, r32, ud32, g, (cudaStream_t)stream);
-  if (r >= 16 * want) return launch_fused<16, true>(q, d, r, n, r32, ud32, g, (cudaStream_t)stream);
-  return launch_fused<8, true>(q, d, r, n, r32, ud32, g, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  // rows per CTA: the largest tile that still gives about two CTAs to every third SM -- wide tiles
+  // reuse each R element for more rows, and the chain per 32 columns does not depend on the tile
+  const int64_t want = (2 * (int64_t)sm_count()) / 3;
+  auto fused = [&](int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) -> int {
+    if (n % 4 == 0 && c1 - c0 <= MB_COLS && (((uintptr_t)r32) & 15) == 0) {
+      if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
+      if (r >= 16 * want) return launch_macro<16>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
+      return launch_macro<8>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
+    }
+    if (r >= 32 * want) return launch_fused<32, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
+    if (r >= 16 * want) return launch_fused<16, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
+    return launch_fused<8, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
+  };
+  if (!sweep_macro_ok(r, n, d, rt_hi, rt_lo) || !ws || ws_bytes < slk_gptq_sweep_r_ws_bytes(r, n))
+    return fused(0, n, nullptr, nullptr, nullptr);
+  float* pacc = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  float* dhi = pacc + (size_t)r * n;
+  float* dlo = dhi + (size_t)r * n;
+  SLK_CUDA(cudaMemsetAsync(pacc, 0, (size_t)r * n * sizeof(float), st));
+  for (int64_t s0 = 0; s0 < n; s0 += SWEEP_MB) {
+    const int64_t e0 = (s0 + SWEEP_MB) < n ? (s0 + SWEEP_MB) : n;
+    rc = fused(s0, e0, pacc, e0 < n ? dhi : nullptr, dlo);
+    if (rc) return rc;
+    if (e0 < n) {
+      TcParams p;
+      p.C = pacc + e0; p.ldc = n; p.R = nullptr; p.R2 = nullptr; p.ldr = 0;
+      p.M = r; p.N = n - e0; p.K = e0 - s0;
+      p.alpha = 1.0f; p.keep = 0.0f; p.count = 1.0f; p.error_flag = nullptr;
+      rc = tc_gemm_presplit_f32(TC_ACCUM, dhi + s0, dlo + s0, n, rt_hi + e0 * n + s0, rt_lo + e0 * n + s0, n, p, st);
+      if (rc) return rc;
+    }
+  }
+  return SLK_OK;
 }

@@ -451,6 +451,18 @@ int tc_gemm_f32(int epi, const float* A, const float* A2, int64_t lda, const flo
   return SLK_ERR_ARG;
 }
 
+// Same product from operands that are already split (hi = value with the 13 low mantissa bits
+// cleared, lo = RN_tf32(value - hi)); no workspace, one launch.
+int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi,
+                         const float* b_lo, int64_t ldb, TcParams p, cudaStream_t st) {
+  switch (epi) {
+    case TC_STORE: return tc_launch<128, TC_STORE>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case TC_ACCUM: return tc_launch<128, TC_ACCUM>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+  }
+  SLK_REQUIRE(false, "tc_gemm_presplit: unsupported epilogue %d", epi);
+  return SLK_ERR_ARG;
+}
+
 size_t tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K) {
   const int64_t Kp = (K + 3) / 4 * 4;
   return (size_t)(2 * M * Kp + 2 * N * Kp) * sizeof(float) + 1024;

@@ -24,6 +24,15 @@ size_t tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K);
 // D = (A [- A2]) * B^T; A [M, K], B [N, K] fp32 K-major
 int tc_gemm_f32(int epi, const float* A, const float* A2, int64_t lda, const float* B, int64_t ldb, TcParams p,
                 void* ws, size_t ws_bytes, cudaStream_t st);
+// same from operands already split into TF32 hi / lo parts (see split_tf32 below)
+int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi,
+                         const float* b_lo, int64_t ldb, TcParams p, cudaStream_t st);
+// the split the tensor path expects: hi = v with 13 low mantissa bits cleared, lo = RN_tf32(v - hi)
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const float l = __fsub_rn(v, hi);
+  lo = __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+}
 // same with A given transposed: At [K, M] (pitch ldat); used by K1 (X^T X with X [S, n])
 int tc_gemm_at_f32(int epi, const float* At, int64_t ldat, TcParams p, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_gemm_at_ws_bytes(int64_t M, int64_t K);

@@ -182,8 +182,8 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
     Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
     if _sweep_leaf(min_block_size) == MAX_LEAF and USE_CHOL_FORM:
         # factor only (no triangular inverse): H_opt = R R^T, sweep from R
-        r32, ud32, info = ops.chol_factor(Hd, order, dampval)             # obq.py:204 (dpotrf part)
-        ops.gptq_sweep_r(Q, r32, ud32, quantizer)                         # obq.py:208-209
+        r32, rt32, ud32, info = ops.chol_factor(Hd, order, dampval)       # obq.py:204 (dpotrf part)
+        ops.gptq_sweep_r(Q, r32, rt32, ud32, quantizer)                   # obq.py:208-209
     else:
         u64, u32, info = ops.hinv(Hd, order, dampval)                     # obq.py:204-205
         ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209

@@ -392,26 +392,28 @@ def hinv(h, order=None, dampval=None, want64=False, want32=True):
 
 
 @_timed("chol_factor")
-def chol_factor(h, order=None, dampval=None):
+def chol_factor(h, order=None, dampval=None, want_rt=True):
     """fp64 Cholesky of (h + dampval*I)[order][:, order] in the sweep's orientation: returns
-    (r32 [n,n] upper with H_opt = R R^T, ud32 [ceil(n/32),32,32] diagonal-block inverses, info)."""
+    (r32 [n,n] upper with H_opt = R R^T, rt = (hi, lo) TF32 parts of its transpose (lower part
+    only) or None, ud32 [ceil(n/32),32,32] diagonal-block inverses, info)."""
     _chk(h, torch.float32)
     n = h.shape[0]
     lib = _lib.load()
     nbytes = lib.slk_chol_factor_ws_bytes(n)
     ws = _ws(nbytes, h.device)
     r32 = torch.empty((n, n), dtype=torch.float32, device=h.device)
+    rt = torch.empty((2, n, n), dtype=torch.float32, device=h.device) if want_rt else None
     ud32 = torch.empty(((n + 31) // 32, 32, 32), dtype=torch.float32, device=h.device)
     info = torch.empty(1, dtype=torch.int32, device=h.device)
     if order is not None:
         _chk(order, torch.int64)
-    _lib.call("slk_chol_factor_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(r32), _ptr(ud32),
-              _ptr(info), _stream())
-    return r32, ud32, info
+    _lib.call("slk_chol_factor_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(r32),
+              _ptr(rt[0]) if want_rt else None, _ptr(rt[1]) if want_rt else None, _ptr(ud32), _ptr(info), _stream())
+    return r32, rt, ud32, info
 
 
 @_timed("gptq_sweep")
-def gptq_sweep_r(q, r32, ud32, cb, d=None):
+def gptq_sweep_r(q, r32, rt, ud32, cb, d=None):
     """In place on q; the sweep from the Cholesky factor (chol_factor); returns (q, d = W - Q)."""
     cb = device_codebook(cb)
     _chk(q, torch.float32)
@@ -419,7 +421,11 @@ def gptq_sweep_r(q, r32, ud32, cb, d=None):
     _chk(ud32, torch.float32)
     if d is None:
         d = torch.empty_like(q)
-    _lib.call("slk_gptq_sweep_r_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32), _ptr(ud32), cb.ref, _stream())
+    nbytes = _lib.load().slk_gptq_sweep_r_ws_bytes(q.shape[0], q.shape[1]) if rt is not None else 0
+    ws = _ws(nbytes, q.device) if nbytes else None
+    _lib.call("slk_gptq_sweep_r_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32),
+              _ptr(rt[0]) if rt is not None else None, _ptr(rt[1]) if rt is not None else None, _ptr(ud32),
+              cb.ref, _ptr(ws), nbytes, _stream())
     return q, d
 
 

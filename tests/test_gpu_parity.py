@@ -273,11 +273,12 @@ def test_cholesky_form_vs_oracle(slk, n, perm, damp):
     L = np.linalg.cholesky(Hd[::-1, ::-1])
     R = np.ascontiguousarray(L[::-1, ::-1])           # upper, Hd = R R^T, U = inv(R)
     Hdev = torch.from_numpy(H).cuda()
-    r32, ud32, info = ops.chol_factor(Hdev, torch.from_numpy(order).cuda() if perm else None,
-                                      torch.tensor([dampval], dtype=torch.float32, device="cuda"))
+    r32, rt32, ud32, info = ops.chol_factor(Hdev, torch.from_numpy(order).cuda() if perm else None,
+                                            torch.tensor([dampval], dtype=torch.float32, device="cuda"))
     assert int(info.item()) == 0
-    r32, ud32 = r32.cpu().numpy(), ud32.cpu().numpy()
+    r32, rt32, ud32 = r32.cpu().numpy(), rt32.cpu().numpy(), ud32.cpu().numpy()
     np.testing.assert_array_equal(np.tril(r32, -1), 0)
+    np.testing.assert_allclose(np.tril(rt32[0] + rt32[1]), r32.T, rtol=3e-7, atol=0)   # TF32 hi + lo parts
     assert np.abs(r32 - R).max() <= 2e-7 * np.abs(R).max()
     for b in range((n + 31) // 32):
         w = min(32, n - 32 * b)

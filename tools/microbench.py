@@ -85,8 +85,8 @@ def main():
             t_s = timeit(lambda: ops.gptq_sweep(Ws.clone(), u64, u32, cb), reps=5)
             t_a = timeit(lambda: ops.argsort(ops.order_keys(Hd, damp, None)), reps=5)
             t_c = timeit(lambda: ops.chol_factor(Hd, order, damp), reps=5)
-            r32, ud32, info2 = ops.chol_factor(Hd, order, damp)
-            t_r = timeit(lambda: ops.gptq_sweep_r(Ws.clone(), r32, ud32, cb), reps=5)
+            r32, rt32, ud32, info2 = ops.chol_factor(Hd, order, damp)
+            t_r = timeit(lambda: ops.gptq_sweep_r(Ws.clone(), r32, rt32, ud32, cb), reps=5)
             print(f"[{r}x{n}] hinv {t_h:9.1f} us   sweep {t_s:9.1f} us   argsort {t_a:7.1f} us  info={int(info.item())}"
                   f"   chol {t_c:9.1f} us  sweep_r {t_r:9.1f} us  info={int(info2.item())}")
     if what in ("search", "all"):
