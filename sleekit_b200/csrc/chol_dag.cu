@@ -97,34 +97,43 @@ __global__ void __launch_bounds__(256) chol_gather_kernel(const TS* __restrict__
 // M holds the lower triangle column-major (M[c*CP + r] = S[r][c], r >= c) so that a lane that owns
 // a row reads consecutive addresses.
 
-// Panel of 8 columns, one warp, rows lane and lane+32 in registers; right-looking inside the panel.
-// The dependent chain per column is shuffle -> rsqrt -> multiply -> shuffle -> fma.
+// Panel of 8 columns, one warp.  Every lane keeps the 8x8 diagonal block in registers and factors
+// it redundantly, so the dependent chain per column is rsqrt -> multiply -> fma with no shuffle
+// on it; the lane's own two rows (lane, lane+32) are carried along right-looking with the block's
+// multipliers taken from those registers.
 __device__ __forceinline__ void chol_panel8(double* M, double* rd, int b, int lane, int32_t* info, int64_t gcol0) {
   const int c0 = 8 * b;
-  const bool hi = c0 >= 32;
+  double dg[8][8];          // dg[c][r] = block(r, c), r >= c
   double v0[8], v1[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int r = c; r < 8; ++r) dg[c][r] = M[(c0 + c) * CP + c0 + r];
     v0[c] = M[(c0 + c) * CP + lane];
     v1[c] = M[(c0 + c) * CP + lane + 32];
   }
+  bool bad = false;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int prow = c0 + j;
-    const double piv = __shfl_sync(0xffffffffu, hi ? v1[j] : v0[j], prow & 31);
-    if (lane == 0 && !(piv > 0.0)) atomicCAS(info, 0, (int32_t)(gcol0 + prow + 1));
+    const double piv = dg[j][j];
+    bad = bad || !(piv > 0.0);
     const double y = rsqrt(piv);
-    v0[j] = __dmul_rn(v0[j], y);               // the pivot row's own entry becomes piv*y = sqrt(piv)
+#pragma unroll
+    for (int r = j + 1; r < 8; ++r) dg[j][r] = __dmul_rn(dg[j][r], y);        // L(r, j)
+#pragma unroll
+    for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+      for (int r = c; r < 8; ++r) dg[c][r] = __fma_rn(-dg[j][r], dg[j][c], dg[c][r]);
+    v0[j] = __dmul_rn(v0[j], y);                 // the pivot row's own entry becomes piv*y = sqrt(piv)
     v1[j] = __dmul_rn(v1[j], y);
-    if (lane == (prow & 31)) rd[prow] = y;
-    const double mine = hi ? v1[j] : v0[j];
 #pragma unroll
     for (int c = j + 1; c < 8; ++c) {
-      const double l = __shfl_sync(0xffffffffu, mine, (c0 + c) & 31);   // L[c0+c][c0+j]
-      v0[c] = __fma_rn(-v0[j], l, v0[c]);
-      v1[c] = __fma_rn(-v1[j], l, v1[c]);
+      v0[c] = __fma_rn(-v0[j], dg[j][c], v0[c]);
+      v1[c] = __fma_rn(-v1[j], dg[j][c], v1[c]);
     }
+    if (lane == j) rd[c0 + j] = y;
   }
+  if (lane == 0 && bad) atomicCAS(info, 0, (int32_t)(gcol0 + c0 + 1));
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     M[(c0 + c) * CP + lane] = v0[c];
@@ -132,23 +141,39 @@ __device__ __forceinline__ void chol_panel8(double* M, double* rd, int b, int la
   }
 }
 
-// Rank-8 update of the 8x8 tiles (ti, tk), b < tk <= ti, by the panel b just factored.
+// Rank-8 update of the 8x8 tiles (ti, tk), b < tk <= ti, by the panel b just factored.  A warp owns
+// up to four tiles (linear index warp + 8m in the row-major enumeration of the triangle); their
+// operands are all loaded before the first DMMA so that the shared-memory latencies overlap.
 __device__ __forceinline__ void chol_trailing8(double* M, int b, int warp, int lane) {
   const int fr = lane >> 2, fk = lane & 3;
-  int cnt = 0;
-  for (int ti = b + 1; ti < 8; ++ti) {
-    for (int tk = b + 1; tk <= ti; ++tk, ++cnt) {
-      if ((cnt & 7) != warp) continue;
-      double* c0p = &M[(8 * tk + 2 * fk) * CP + 8 * ti + fr];
-      double c[2] = {c0p[0], c0p[CP]};
+  const int m = 7 - b, ntile = m * (m + 1) / 2;
+  const int abase = (8 * b + fk) * CP + fr;
+  int co[4], ao[4], bo[4];
 #pragma unroll
-      for (int ks = 0; ks < 8; ks += 4) {
-        const double a = M[(8 * b + ks + fk) * CP + 8 * ti + fr];
-        const double bb = M[(8 * b + ks + fk) * CP + 8 * tk + fr];
-        cd_dmma(c, -a, bb);
-      }
-      c0p[0] = c[0];
-      c0p[CP] = c[1];
+  for (int q = 0; q < 4; ++q) {
+    const int t = warp + 8 * q;
+    int ti = 0, rem = t < ntile ? t : 0;                 // inactive slots alias tile 0 (loads only)
+    while (rem > ti) { rem -= ti + 1; ++ti; }           // row ti holds ti + 1 tiles
+    const int gi = 8 * (b + 1 + ti), gk = 8 * (b + 1 + rem);
+    co[q] = (gk + 2 * fk) * CP + gi + fr;
+    ao[q] = abase + gi;
+    bo[q] = abase + gk;
+  }
+  double c[4][2], a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    c[q][0] = M[co[q]]; c[q][1] = M[co[q] + CP];
+    a0[q] = M[ao[q]]; a1[q] = M[ao[q] + 4 * CP];
+    b0[q] = M[bo[q]]; b1[q] = M[bo[q] + 4 * CP];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cd_dmma(c[q], -a0[q], b0[q]);
+    cd_dmma(c[q], -a1[q], b1[q]);
+    if (warp + 8 * q < ntile) {
+      M[co[q]] = c[q][0];
+      M[co[q] + CP] = c[q][1];
     }
   }
 }
@@ -163,14 +188,11 @@ __device__ __forceinline__ void smem_mm_batched(double* C, int sci, int scn, int
   for (int t = warp; t < tiles * nprob; t += CTH / 32) {
     const int p = t / tiles, tt = t - p * tiles;
     const int i0 = (tt / tn) * 8, n0 = (tt % tn) * 8;
-    const double* Ap = A + p * spa;
-    const double* Bp = B + p * spb;
+    const double* Ap = A + p * spa + (i0 + fr) * sai + fk * sak;
+    const double* Bp = B + p * spb + fk * sbk + (n0 + fr) * sbn;
     double c[2] = {0.0, 0.0};
-    for (int k0 = 0; k0 < s; k0 += 4) {
-      const double a = Ap[(i0 + fr) * sai + (k0 + fk) * sak];
-      const double bb = Bp[(k0 + fk) * sbk + (n0 + fr) * sbn];
-      cd_dmma(c, a, bb);
-    }
+#pragma unroll 8
+    for (int k0 = 0; k0 < s; k0 += 4) cd_dmma(c, Ap[k0 * sak], Bp[k0 * sbk]);
     double* cp = C + p * spc + (i0 + fr) * sci + (n0 + 2 * fk) * scn;
     cp[0] = __dmul_rn(alpha, c[0]);
     cp[scn] = __dmul_rn(alpha, c[1]);
@@ -179,19 +201,24 @@ __device__ __forceinline__ void smem_mm_batched(double* C, int sci, int scn, int
 
 // In: sm.f.M lower triangle (column-major).  Out: L in sm.f.M (same layout, entries with r < c are
 // garbage), X = L^-1 row-major in sm.f.X (upper part zero).  All 256 threads.
-__device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t* info, int64_t gcol0) {
+__device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t* info, int64_t gcol0,
+                                                 long long* tr = nullptr) {
   const int warp = tid >> 5, lane = tid & 31;
   double* M = sm.f.M;
   double* X = sm.f.X;
   for (int t = tid; t < CT * CP; t += CTH) X[t] = 0.0;
+  long long tp = 0, tt = 0, c0 = tr ? clock64() : 0;
   for (int b = 0; b < 8; ++b) {
     if (warp == 0) chol_panel8(M, sm.rd, b, lane, info, gcol0);
     __syncthreads();
+    if (tr) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
     if (b < 7) {
       chol_trailing8(M, b, warp, lane);
       __syncthreads();
+      if (tr) { const long long c1 = clock64(); tt += c1 - c0; c0 = c1; }
     }
   }
+  if (tr) { tr[8] = tp; tr[9] = tt; tr[10] = clock64(); }
   // inverses of the 8x8 diagonal blocks: thread c solves L_bb x = e_cc by forward substitution
   if (tid < CT) {
     const int b8 = tid & ~7, cc = tid & 7;
@@ -206,6 +233,7 @@ __device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t*
     }
   }
   __syncthreads();
+  if (tr) tr[11] = clock64();
   // doubling: inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]]
   for (int s = 8; s < CT; s *= 2) {
     const int pairs = CT / (2 * s);
@@ -218,9 +246,10 @@ __device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t*
                     s, pairs, -1.0, warp, lane);
     __syncthreads();
   }
+  if (tr) tr[12] = clock64();
 }
 
-// Optional per-task trace (development aid, tools/chol_trace.py): 8 int64 per task --
+// Optional per-task trace (development aid, tools/chol_trace.py): 16 int64 per task --
 // i, j, globaltimer at start / end, clock64 after the ticket / k loop / tile math / publish.
 __device__ long long* g_chol_trace = nullptr;
 __device__ __forceinline__ long long gtimer() {
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
     while (rem >= T - j) { rem -= T - j; ++j; }
     const int i = j + rem;
     const bool diag = (i == j);
-    long long* tr = (g_chol_trace && tid == 0) ? g_chol_trace + (int64_t)t * 8 : nullptr;
+    long long* tr = (g_chol_trace && tid == 0) ? g_chol_trace + (int64_t)t * 16 : nullptr;
     if (tr) { tr[0] = i; tr[1] = j; tr[2] = gtimer(); tr[4] = clock64(); }
     const double* Ai = A + (int64_t)i * CT * ld;
     const double* Aj = A + (int64_t)j * CT * ld;
@@ -336,13 +365,20 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
           sm.f.M[(col + 1) * CP + row] = __dsub_rn(cij[ii][jj].y, acc[ii][jj][1]);
         }
       __syncthreads();
-      chol_factor_tile(sm, tid, info, (int64_t)j * CT);
+      chol_factor_tile(sm, tid, info, (int64_t)j * CT, tr);
+      // X_j is what the panel solves below wait for: publish it first; L(j,j) itself is only read
+      // by the export kernel after this launch
       double* Xg = Dinv + (int64_t)j * CT * CT;
+      for (int e = tid; e < CT * CT; e += CTH) Xg[e] = sm.f.X[(e >> 6) * CP + (e & 63)];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
       for (int e = tid; e < CT * CT; e += CTH) {
         const int r = e >> 6, c = e & 63;
         Cij[(int64_t)r * ld + c] = (r >= c) ? sm.f.M[c * CP + r] : 0.0;
-        Xg[e] = sm.f.X[r * CP + c];
       }
+      if (tr) { tr[6] = clock64(); tr[7] = tr[6]; tr[3] = gtimer(); }
+      continue;
     } else {
       // S row-major into M, X_j into X, L(i,j) = S X_j^T
 #pragma unroll

@@ -20,12 +20,13 @@ T = (n + 63) // 64
 nt = T * (T + 1) // 2
 for _ in range(3):
     ops.chol_factor(Hd, order, damp)
-buf = torch.zeros(nt * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(nt * 16, dtype=torch.int64, device="cuda")
 _lib.call("slk_debug_chol_trace", ctypes.c_void_p(buf.data_ptr()))
 ops.chol_factor(Hd, order, damp)
 torch.cuda.synchronize()
 _lib.call("slk_debug_chol_trace", None)
-tr = buf.cpu().numpy().reshape(nt, 8)
+trf = buf.cpu().numpy().reshape(nt, 16)
+tr = trf[:, :8]
 t0 = tr[:, 2].min()
 clk = 1.0  # clock64 ticks -> reported raw (SM clock)
 print(f"n={n} T={T} tasks={nt} kernel span {(tr[:, 3].max() - t0) / 1e3:.1f} us")
@@ -39,3 +40,5 @@ o = tr[tr[:, 0] != tr[:, 1]]
 print("diag  mean clk: kloop %.0f math %.0f publish %.0f" % tuple((d[:, k + 1] - d[:, k]).mean() for k in (4, 5, 6)))
 if len(o):
     print("offd  mean clk: kloop %.0f math %.0f publish %.0f" % tuple((o[:, k + 1] - o[:, k]).mean() for k in (4, 5, 6)))
+dd = trf[trf[:, 0] == trf[:, 1]]
+print("diag factor clk: panels %.0f trailing %.0f diag-inv %.0f doubling %.0f" % (dd[:, 8].mean(), dd[:, 9].mean(), (dd[:, 11] - dd[:, 10]).mean(), (dd[:, 12] - dd[:, 11]).mean()))
