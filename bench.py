@@ -363,6 +363,7 @@ def run_ours(args):
         launches_per_step = ops.launch_count() - launches0
         launches = launches_per_step * args.steps
     top_ms, top_calls = ops.profile_totals_ms(ops.PROFILE).get(top, (0.0, 0))
+    top_events = list(ops.PROFILE.get(top, []))
     ops.PROFILE, ops.PROFILE_ONLY = None, None
     clocks = sampler.stop()
     ms_per_step = ms / args.steps
@@ -413,45 +414,67 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     roofline = None
     if top_calls:
-        per_launch_ms = top_ms / top_calls
+        # The dominant operation is timed per launch (events on the launching stream, serial pass);
+        # launches are grouped by layer shape and the group with the largest total is reported.
+        per_launch = [s_.elapsed_time(e_) for s_, e_ in top_events]
+        groups = {}
+        for (r_, n_), ms_ in zip(shapes, per_launch):
+            groups.setdefault((r_, n_) if top not in ("chol_factor", "hinv") else (0, n_), []).append(ms_)
+        gkey = max(groups, key=lambda k: sum(groups[k]))
+        g_ms = sum(groups[gkey]) / len(groups[gkey])
+        gr, gn = gkey
         share = phases[top][0] / serial_total_ms if serial_total_ms else None
-        common = {"kernel": top, "avg_launch_ms": per_launch_ms, "launches_timed": top_calls, "traffic": None,
-                  "share_of_serial_device_time": share}
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            traffic = tj.get(f"{top}:n={gn}" if gr == 0 else f"{top}:{gr}x{gn}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        common = {"kernel": top, "group": (f"n={gn}" if gr == 0 else f"[{gr},{gn}]"), "avg_launch_ms": g_ms,
+                  "launches_timed": len(groups[gkey]), "traffic": traffic, "share_of_serial_device_time": share,
+                  "all_groups_ms": {(f"n={k[1]}" if k[0] == 0 else f"{k[0]}x{k[1]}"): round(sum(v) / len(v), 4)
+                                    for k, v in groups.items()}}
+
+        def fp64_peak():
+            a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+            torch.matmul(a, a)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                torch.matmul(a, a)
+            e1.record()
+            torch.cuda.synchronize()
+            return 3 * 2.0 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
         if top == "scale_search":
             # reference traffic model = one pass over W per grid point = 4*G bytes/weight
-            achieved = 4.0 * GRID * weights / L / (per_launch_ms * 1e-3) / 1e9
+            achieved = 4.0 * GRID * gr * gn / (g_ms * 1e-3) / 1e9
             roofline = dict(common, bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
                             peak_source=peak_src,
                             note=("effective GB/s: algorithmic bytes = 4*G bytes per weight (the reference's G passes "
-                                  "over W, scaling.py:127-133); the fused kernel reads W once (4 B/weight of real DRAM "
-                                  "traffic) and is bound by the fp32 pipe"))
-        elif top in ("hinv", "gptq_sweep", "hweighted_error"):
-            if top == "hinv":
-                flop = sum(2.0 * n ** 3 / 3.0 for _, n in shapes) / L     # n^3/3 factor + n^3/3 inverse, fp64
-                a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-                torch.matmul(a, a)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(3):
-                    torch.matmul(a, a)
-                e1.record()
-                torch.cuda.synchronize()
-                peak = 3 * 2.0 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-                psrc = "cuBLAS fp64 GEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)"
-                note = ("fp64 damp+permute+factor+inverse (K2): algorithmic 2n^3/3 fp64 flop per layer; small layers "
-                        "are bound by the latency of n/64 dependent panels, not by the FP64 pipe")
-            else:
-                flop = (sum(float(r) * n * n for r, n in shapes) if top == "gptq_sweep"
-                        else sum(2.0 * r * n * n for r, n in shapes)) / L
-                peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
-                psrc = "half of the measured bf16 peak (dense TF32 = bf16/2)"
-                note = "algorithmic fp32 flop of the GEMM phase per launch"
-            achieved = flop / (per_launch_ms * 1e-3) / 1e12
+                                  "over W, scaling.py:127-133); the fused kernel reads W twice (8 B/weight of real "
+                                  "traffic) and is bound by instruction issue (exact threshold tables, ~16 "
+                                  "instructions per weight and grid point)"))
+        elif top in ("hinv", "chol_factor"):
+            flop = (2.0 if top == "hinv" else 1.0) * gn ** 3 / 3.0
+            peak = fp64_peak()
+            achieved = flop / (g_ms * 1e-3) / 1e12
             roofline = dict(common, bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                            peak_source=psrc, note=note)
+                            peak_source="cuBLAS fp64 GEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                            note=("K2: fp64 damp + permute + Cholesky factor (n^3/3 flop; the sweep's R form needs no "
+                                  "inverse), one tile-task kernel on the FP64 tensor path (DMMA); bounded by the chain "
+                                  "of n/64 dependent 64x64 tile factorisations (64 dependent rsqrt each), not by the "
+                                  "FP64 pipe, at these sizes; all_groups_ms lists the other shapes"))
+        elif top in ("gptq_sweep", "hweighted_error"):
+            flop = float(gr) * gn * gn * (1.0 if top == "gptq_sweep" else 2.0)
+            peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+            achieved = flop / (g_ms * 1e-3) / 1e12
+            roofline = dict(common, bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                            peak_source="half of the measured bf16 peak (dense TF32 = bf16/2)",
+                            note="algorithmic fp32 flop of the GEMM phase per launch (r*n^2 sweep, 2*r*n^2 error)")
         else:
-            achieved = 8.0 * weights / L / (per_launch_ms * 1e-3) / 1e9
+            achieved = 8.0 * gr * gn / (g_ms * 1e-3) / 1e9
             roofline = dict(common, bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
                             peak_source=peak_src, note="algorithmic bytes = one read + one write of W per launch")
 

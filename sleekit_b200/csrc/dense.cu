@@ -48,14 +48,24 @@ static int gain_impl(const T* w, const T* q, const T* h, const T* cand, int64_t 
   return gemm_launch<T, false, false, EPI_GAIN>(p, 1, st);
 }
 
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t S, int64_t n, int64_t ldx,
-                                                     float* __restrict__ mean, float keep, float count) {
-  // one thread per column, coalesced across the warp; fp64 running sum, rounded once
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ x, int64_t S, int64_t n, int64_t ldx,
+                                                      float* __restrict__ mean, float keep, float count) {
+  // 32 columns x 32 row groups per CTA: coalesced 128-byte row segments, fp64 partial sums per row
+  // group, combined in a fixed order (deterministic), rounded once (statistics.py:84-85)
+  __shared__ double part[32][33];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + cx;
   double acc = 0.0;
-  for (int64_t i = 0; i < S; ++i) acc += (double)__ldg(x + i * ldx + j);
-  mean[j] = __fadd_rn(__fmul_rn(mean[j], keep), __fdiv_rn((float)acc, count));
+  if (j < n)
+    for (int64_t i = rg; i < S; i += 32) acc += (double)__ldg(x + i * ldx + j);
+  part[rg][cx] = acc;
+  __syncthreads();
+  if (rg == 0 && j < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += part[k][cx];
+    mean[j] = __fadd_rn(__fmul_rn(mean[j], keep), __fdiv_rn((float)t, count));
+  }
 }
 
 // ---- full-H scale search pieces --------------------------------------------
@@ -174,7 +184,7 @@ int slk_hessian_accum_f32(const float* x, int64_t S, int64_t n, int64_t ldx, flo
                           double new_count, void* ws, size_t ws_bytes, void* stream) {
   SLK_REQUIRE(x && hess && mean && S >= 1 && n >= 1 && ldx >= n, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  colsum_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(x, S, n, ldx, mean, (float)keep, (float)new_count);
+  colsum_kernel<<<(int)ceil_div(n, 32), 1024, 0, st>>>(x, S, n, ldx, mean, (float)keep, (float)new_count);
   SLK_LAUNCH_CHECK();
   if (n >= 64 && S >= 32 && ws && ws_bytes >= slk_hessian_accum_ws_bytes(S, n) && tc_gemm_usable(hess, 4, hess, 4)) {
     // tensor-core path: X is split and transposed once into K-major hi/lo [n, S]; both operands of

@@ -162,10 +162,12 @@ def _quantize_opt_core(Q, E, Hinv, quantizer):
 
 
 def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
-                check=False):
+                check=False, colsum_reduce=None):
     """quantize_opt on device tensors (fp32 W [r,n], fp32 H [n,n]); returns quantized values [r,n].
     The whole chain -- damp, keys, argsort, gather, fp64 factor, sweep, scatter, local search --
-    is enqueued on the current stream without a host round trip."""
+    is enqueued on the current stream without a host round trip.  colsum_reduce: optional callable
+    applied to the column residual sums of the err / sqerr orderings (row-sharded runs all-reduce
+    them there, dist.allreduce_column_sums)."""
     dampval = ops.damp_value(Hd, damp)                                   # obq.py:198
     if act_order == "none":
         order = None
@@ -173,6 +175,8 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
         col = None
         if act_order != "diag":
             col = ops.col_resid_sums(Wd, quantizer, squared=(act_order == "sqerr"))
+            if colsum_reduce is not None:
+                col = colsum_reduce(col)
         order = ops.argsort(ops.order_keys(Hd, dampval, col))            # obq.py:199
     else:
         hopt_diag = Hd.diagonal().to(torch.float64) + dampval.to(torch.float64)

@@ -145,3 +145,42 @@ class HostPlan:
         if sync:
             torch.cuda.current_stream().synchronize()
         return self.Q, self.err
+
+
+def quantize_layer_sharded(W_rows, X_rows, codebook, scaling_mode="diag", act_order="diag", damp=0.01, nb_ls_moves=0,
+                           bias_correction=False, grid_size=100, min_factor=0.05, max_factor=1.0, group=None):
+    """One big layer over the ranks of a process group (BASELINE config 5).
+
+    W_rows [r_local, n]: this rank's contiguous slice of the output rows of W (dist.row_partition).
+    X_rows [S_local, n]: this rank's slice of the calibration samples.
+    1. every rank folds its samples into running statistics (K1) and ONE all-reduce of
+       [n*n + n + 1] floats makes H and the mean identical everywhere (statistics.py:76-87);
+    2. scale search, ordering, fp64 factor, sweep, local search and the row errors run on the local
+       rows with no communication (rows never interact); the factor is recomputed on every rank
+       (deterministic, hence identical) -- it is the term that does not shard;
+    3. the only other exchanges: the column residual sums of the err / sqerr orderings (n floats)
+       and the scalar layer error.
+    Returns (quantized rows [r_local, n], scales [r_local], layer error (0-dim tensor), H, mean)."""
+    import torch.distributed as tdist
+
+    from . import dist as sdist
+
+    ops.require_cuda()
+    dev = W_rows.device
+    n = W_rows.shape[1]
+    H = torch.zeros((n, n), dtype=torch.float32, device=dev)
+    mean = torch.zeros(n, dtype=torch.float32, device=dev)
+    count = int(X_rows.shape[0])
+    if count:
+        ops.hessian_accum(X_rows.contiguous(), H, mean, 0.0, count)
+    H, mean, count = sdist.allreduce_statistics(H, mean, count, group)
+    Hq = ops.remove_input_bias(H, mean) if bias_correction else H
+    sc = _device_scaling(W_rows, codebook, Hq, scaling_mode, grid_size, min_factor, max_factor)
+    reduce_cols = (lambda c: sdist.allreduce_column_sums(c, group)) if act_order in ("err", "sqerr") else None
+    q = quantize_scaled_device(W_rows, sc, codebook, Hq, act_order, damp, nb_ls_moves, colsum_reduce=reduce_cols)
+    rows_err = ops.hweighted_error(W_rows, q, Hq)
+    total_rows = torch.tensor([W_rows.shape[0]], dtype=torch.int64, device=dev)
+    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
+        tdist.all_reduce(total_rows, group=group)
+    err = sdist.allreduce_row_error_mean(rows_err, int(total_rows.item()), group)
+    return q, sc, err, Hq, mean

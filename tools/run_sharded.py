@@ -1,0 +1,78 @@
+"""Row- and sample-sharded quantization of one big layer (BASELINE config 5) under torchrun.
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/run_sharded.py [r n S]
+
+Every rank generates the same synthetic layer (seeded), keeps its row slice of W and its sample
+slice of X, runs sleekit_b200.pipeline.quantize_layer_sharded and reports device time (max over
+ranks).  With --check, rank 0 also quantizes the first rows on its own from the all-reduced H and
+compares (rows never interact, so the sharded rows must match the single-GPU rows)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sleekit_b200 import codebook, ops  # noqa: E402
+from sleekit_b200 import dist as sdist  # noqa: E402
+from sleekit_b200 import workloads as wl  # noqa: E402
+from sleekit_b200.pipeline import quantize_layer_sharded  # noqa: E402
+from sleekit_b200.scaling import quantize_scaled_device, search_scale_device  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("shape", nargs="*", type=int, default=[8192, 28672, 2048])
+    ap.add_argument("--codebook", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    r, n, S = (args.shape + [2048])[:3]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cb = codebook.UniformCodebook(args.codebook, -1, 1)
+    a, b = sdist.row_partition(r, world)[rank]
+    sa, sb = sdist.row_partition(S, world)[rank]
+    g = np.random.default_rng(1000)
+    W = torch.from_numpy((0.02 * g.standard_normal((r, n), dtype=np.float32))[a:b].copy()).to(dev)
+    X = torch.from_numpy(wl.synthetic_calibration(n, 0, S)[sa:sb].copy()).to(dev)
+    times = []
+    for _ in range(args.reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        q, sc, err, H, mean = quantize_layer_sharded(W, X, cb)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t))
+    ok = None
+    if args.check and rank == 0:
+        rows = min(64, b - a)
+        sc1 = search_scale_device(W[:rows].contiguous(), cb, H.diagonal().contiguous())
+        q1 = quantize_scaled_device(W[:rows].contiguous(), sc1, cb, H)
+        ok = bool(torch.equal(sc1, sc[:rows]) and torch.equal(q1, q[:rows]))
+    if rank == 0:
+        print(json.dumps({"config": f"[{r},{n}] rows sharded over {world} GPU(s), S={S} samples sharded, "
+                                    f"{args.codebook}-entry codebook, diag-H scaling + GPTQ + layer error",
+                          "n_gpus": world, "ms": times, "weights_per_s": r * n / (min(times) * 1e-3),
+                          "layer_error": float(err), "rows_match_single_gpu": ok,
+                          "mem_gb": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
