@@ -181,7 +181,13 @@ def obq_scale_device(Wd, codebook, Hd, damp=0.01, act_order="diag", min_factor=0
         order = _device_order(ws, hopt, codebook, act_order)
     Wp = ops.permute_cols(Wd, order)                                                  # scaling.py:171
     Hp = Hd[order][:, order].contiguous()                                             # scaling.py:172 (plumbing gather)
-    u64, u32, info = ops.hinv(Hd, order, dampval)                                     # scaling.py:173-174
+    from . import obq as _obq
+
+    chol_form = _obq.USE_CHOL_FORM
+    if chol_form:
+        r32, rt, ud32, info = ops.chol_factor(Hd, order, dampval)                     # scaling.py:173-174 (factor only)
+    else:
+        u64, u32, info = ops.hinv(Hd, order, dampval)                                 # scaling.py:173-174
     f = _factors(min_factor, max_factor, grid_size, Wd.device)
     best_err = torch.full((r,), float("inf"), dtype=torch.float32, device=Wd.device)
     best_f = torch.full((r,), float("inf"), dtype=torch.float32, device=Wd.device)
@@ -192,7 +198,10 @@ def obq_scale_device(Wd, codebook, Hd, damp=0.01, act_order="diag", min_factor=0
         scale = (fs.unsqueeze(1) * base.unsqueeze(0)).reshape(-1).contiguous()        # scaling.py:181
         Wrep = Wp.unsqueeze(0).expand(gc, r, n).reshape(gc * r, n).contiguous()
         Q = ops.scale_rows(Wrep, scale, 0)                                            # scaling.py:182
-        ops.gptq_sweep(Q, u64, u32, codebook, 32, 8)                                  # scaling.py:183-184
+        if chol_form:
+            ops.gptq_sweep_r(Q, r32, rt, ud32, codebook)                              # scaling.py:183-184
+        else:
+            ops.gptq_sweep(Q, u64, u32, codebook, 32, 8)
         Q = ops.scale_rows(Q, scale, 1)                                               # scaling.py:185
         err = ops.hweighted_error(Q, Wrep, Hp).reshape(gc, r)                         # scaling.py:186
         for k in range(gc):                                                           # scaling.py:187-189

@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_configs.py -m gpu -x -q -s > gpurun_out/pytest_cfg.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_cfg.log
+timeout 600 python tools/run_sharded.py 8192 28672 2048 --check --reps 2 2>&1 | tail -2
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/run_sharded.py 8192 28672 2048 --check --reps 2 2>&1 | tail -3
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-1500
