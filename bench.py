@@ -326,9 +326,11 @@ def run_ours(args):
     serial(Wd, Hd, errs_out=errs, keep_outputs=False)
     torch.cuda.synchronize()
     phases = ops.profile_totals_ms(ops.PROFILE)
+    serial_profile = ops.PROFILE
     ops.PROFILE = None
     top = max(phases, key=lambda k: phases[k][0])
     serial_total_ms = sum(v[0] for v in phases.values())
+    top_events = list(serial_profile.get(top, []))     # per-launch events of the dominant operation
 
     graph = None
     if not args.no_graph:
@@ -347,24 +349,16 @@ def run_ours(args):
     # ---- timed region (device resident) ------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    launches_per_step = None
-    if graph is None:
-        ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
     launches0 = ops.launch_count()
     ms, wall = timed(step_device, args.steps)
     launches = ops.launch_count() - launches0
     if graph is not None:
-        # a replay launches the kernels recorded at capture time; count them with one eager pass,
-        # which also times the dominant kernel with events on the stream it runs on
-        ops.PROFILE, ops.PROFILE_ONLY = {}, {top}
+        # a replay launches the kernels recorded at capture time; count them with one eager pass
         launches0 = ops.launch_count()
         serial(Wd, Hd, errs_out=errs, keep_outputs=False)
         torch.cuda.synchronize()
-        launches_per_step = ops.launch_count() - launches0
-        launches = launches_per_step * args.steps
-    top_ms, top_calls = ops.profile_totals_ms(ops.PROFILE).get(top, (0.0, 0))
-    top_events = list(ops.PROFILE.get(top, []))
-    ops.PROFILE, ops.PROFILE_ONLY = None, None
+        launches = (ops.launch_count() - launches0) * args.steps
+    top_calls = len(top_events)
     clocks = sampler.stop()
     ms_per_step = ms / args.steps
     value = world * weights / (ms_per_step * 1e-3)

@@ -1,4 +1,11 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python tools/run_sharded.py 8192 28672 2048 --check --reps 2 2>&1 | tail -2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/run_sharded.py 8192 28672 2048 --check --reps 2 2>&1 | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-1500
+timeout 900 python -m pytest tests -m gpu -x -q -k "scale or scaling or edge or presets or statistics" > gpurun_out/pytest_s3c.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_s3c.log
+timeout 300 python tools/microbench.py search 2>&1 | tail -4
+timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_s3c.log 2>&1; echo "bench rc=$?"
+python - <<'PY'
+import json
+for ln in open("gpurun_out/bench_s3c.log"):
+    if ln.startswith("{"):
+        d=json.loads(ln); print(d["ms_per_step"], d["serial_phases_ms_per_step"], d["layer_error_mean"], d["gpu_launches"]); print(d["roofline"])
+PY
+tail -3 gpurun_out/bench_s3c.log | cut -c1-400
