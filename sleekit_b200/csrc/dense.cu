@@ -74,7 +74,8 @@ template <typename TE>
 __global__ void __launch_bounds__(256) grid_resid_kernel(const float* __restrict__ w, int64_t r, int64_t n,
                                                          DevGrid<float> g, const float* __restrict__ factors,
                                                          int g0, int gcount, const float* __restrict__ init,
-                                                         TE* __restrict__ resid) {
+                                                         TE* __restrict__ resid, float* __restrict__ rhi = nullptr,
+                                                         float* __restrict__ rlo = nullptr) {
   const int64_t total = (int64_t)gcount * r * n;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -86,7 +87,14 @@ __global__ void __launch_bounds__(256) grid_resid_kernel(const float* __restrict
     float x = __ldg(w + row * n + j);
     float v = grid_value(g, __fdiv_rn(x, scale));
     float dq = __fdiv_rn(v, rs);
-    resid[i] = (TE)__fsub_rn(dq, x);
+    const float e = __fsub_rn(dq, x);
+    resid[i] = (TE)e;
+    if (rhi) {                                   // TF32 parts for the tensor-core product
+      float hh, ll;
+      split_tf32(e, hh, ll);
+      rhi[i] = hh;
+      rlo[i] = ll;
+    }
   }
 }
 
@@ -210,6 +218,8 @@ size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t 
   bytes += align256((size_t)chunk * r * tiles * elem);   // row-dot partials
   bytes += align256((size_t)chunk * r * elem);           // errors
   bytes += 3 * align256((size_t)r * sizeof(float));      // init, best_err, best_f
+  if (h_dtype == 1 && n % 4 == 0)                        // tensor-core path: TF32 parts of the residuals and of H
+    bytes += 2 * align256((size_t)chunk * r * n * 4) + 2 * align256((size_t)n * n * 4);
   return bytes;
 }
 
@@ -231,7 +241,18 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
   void* errs = base; base += align256((size_t)chunk * r * elem);
   float* init = (float*)base; base += align256((size_t)r * sizeof(float));
   float* best_err = (float*)base; base += align256((size_t)r * sizeof(float));
-  float* best_f = (float*)base;
+  float* best_f = (float*)base; base += align256((size_t)r * sizeof(float));
+  // tensor-core path (fp32 H): residuals are written with their TF32 parts, H is split once
+  const bool tc = h_dtype == 1 && n % 4 == 0 && n >= 32 && tc_gemm_usable(resid, n, h, n);
+  float *rhi = nullptr, *rlo = nullptr, *hhi = nullptr, *hlo = nullptr;
+  if (tc) {
+    rhi = (float*)base; base += align256((size_t)chunk * r * n * 4);
+    rlo = (float*)base; base += align256((size_t)chunk * r * n * 4);
+    hhi = (float*)base; base += align256((size_t)n * n * 4);
+    hlo = (float*)base;
+    rc = tc_split_f32((const float*)h, n, n, n, n, hhi, hlo, st);
+    if (rc) return rc;
+  }
 
   rc = slk_row_noclip_scale_f32(w, r, n, cb->lo, cb->hi, init, stream);
   if (rc) return rc;
@@ -243,12 +264,21 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
     const int64_t rows = (int64_t)gc * r;
     int blocks = (int)(ceil_div(rows * n, 256) < (int64_t)sm_count() * 16 ? ceil_div(rows * n, 256) : (int64_t)sm_count() * 16);
     if (h_dtype == 1) {
-      grid_resid_kernel<float><<<blocks, 256, 0, st>>>(w, r, n, g, factors, g0, gc, init, (float*)resid);
+      grid_resid_kernel<float><<<blocks, 256, 0, st>>>(w, r, n, g, factors, g0, gc, init, (float*)resid, rhi, rlo);
       SLK_LAUNCH_CHECK();
-      GemmParams<float> p = gemm_params<float>((const float*)resid, n, (const float*)h, n, (float*)part, 0, rows, n, n);
-      rc = gemm_launch<float, false, false, EPI_ROWDOT>(p, 1, st);
+      if (tc) {
+        // (E H) . E per row on tcgen05: H symmetric, hence its own K-major B operand; row dot in the epilogue
+        TcParams tp;
+        tp.C = (float*)part; tp.ldc = ceil_div(n, TC_TILE_N); tp.R = (const float*)resid; tp.R2 = nullptr; tp.ldr = n;
+        tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+        rc = tc_gemm_presplit_f32(TC_ROWDOT, rhi, rlo, n, hhi, hlo, n, tp, st);
+      } else {
+        GemmParams<float> p = gemm_params<float>((const float*)resid, n, (const float*)h, n, (float*)part, 0, rows, n, n);
+        rc = gemm_launch<float, false, false, EPI_ROWDOT>(p, 1, st);
+      }
       if (rc) return rc;
-      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const float*)part, rows, tiles, (float*)errs);
+      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const float*)part, rows,
+                                                                           tc ? ceil_div(n, TC_TILE_N) : tiles, (float*)errs);
       SLK_LAUNCH_CHECK();
       grid_argmin_kernel<float><<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, r, g0, gc, factors, best_err, best_f);
     } else {

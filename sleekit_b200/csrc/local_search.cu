@@ -11,6 +11,7 @@
 // the one row of H the flip touches: p += delta * H[b, :].  Per move and row the traffic is one
 // row of H (4n bytes, L2-resident across rows) instead of ~20n bytes of gain patches.
 #include "gemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace slk {
 
@@ -112,7 +113,9 @@ using namespace slk;
 extern "C" {
 
 size_t slk_local_search_ws_bytes(int64_t r, int64_t n) {
-  return align256((size_t)r * n * sizeof(float)) + align256((size_t)n * sizeof(float));
+  size_t bytes = align256((size_t)r * n * sizeof(float)) + align256((size_t)n * sizeof(float));
+  if (n % 4 == 0 && n >= 32) bytes += tc_gemm_ws_bytes(r, n, n);   // TF32 parts for the tensor-core init product
+  return bytes;
 }
 
 int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
@@ -132,9 +135,18 @@ int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, in
   ls_diag_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(h, n, hdiag);
   SLK_LAUNCH_CHECK();
   // P = (Q - W) @ H                                           obq.py:229-231
-  GemmParams<float> p = gemm_params<float>(q, n, h, n, P, n, r, n, n);
-  p.A2 = w;
-  rc = gemm_launch<float, false, false, EPI_STORE>(p, 1, st);
+  void* gws = (char*)ws + align256((size_t)r * n * sizeof(float)) + align256((size_t)n * sizeof(float));
+  if (n % 4 == 0 && n >= 32 && tc_gemm_usable(q, n, h, n) && (uintptr_t)w % 16 == 0) {
+    // tcgen05, fp32-faithful 3xTF32; H is symmetric, hence its own K-major B operand
+    TcParams tp;
+    tp.C = P; tp.ldc = n; tp.R = nullptr; tp.R2 = nullptr; tp.ldr = 0; tp.M = r; tp.N = n; tp.K = n;
+    tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+    rc = tc_gemm_f32(TC_STORE, q, w, n, h, n, tp, gws, tc_gemm_ws_bytes(r, n, n), st);
+  } else {
+    GemmParams<float> p = gemm_params<float>(q, n, h, n, P, n, r, n, n);
+    p.A2 = w;
+    rc = gemm_launch<float, false, false, EPI_STORE>(p, 1, st);
+  }
   if (rc) return rc;
   if (smem > 48 * 1024)
     SLK_CUDA(cudaFuncSetAttribute(local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

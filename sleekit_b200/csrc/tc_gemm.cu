@@ -458,9 +458,18 @@ int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t 
   switch (epi) {
     case TC_STORE: return tc_launch<128, TC_STORE>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
     case TC_ACCUM: return tc_launch<128, TC_ACCUM>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case TC_ROWDOT: return tc_launch<128, TC_ROWDOT>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
   }
   SLK_REQUIRE(false, "tc_gemm_presplit: unsupported epilogue %d", epi);
   return SLK_ERR_ARG;
+}
+
+// hi / lo TF32 parts of a [rows, cols] matrix (row pitch ld) into two matrices of pitch ldo
+int tc_split_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, int64_t ldo, float* hi, float* lo,
+                 cudaStream_t st) {
+  split_tf32_kernel<<<split_grid(rows * cols), 256, 0, st>>>(x, nullptr, rows, cols, ld, ldo, hi, lo);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
 }
 
 size_t tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K) {

@@ -27,6 +27,8 @@ int tc_gemm_f32(int epi, const float* A, const float* A2, int64_t lda, const flo
 // same from operands already split into TF32 hi / lo parts (see split_tf32 below)
 int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi,
                          const float* b_lo, int64_t ldb, TcParams p, cudaStream_t st);
+int tc_split_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, int64_t ldo, float* hi, float* lo,
+                 cudaStream_t st);
 // the split the tensor path expects: hi = v with 13 low mantissa bits cleared, lo = RN_tf32(v - hi)
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
