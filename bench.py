@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--only", default="", choices=["", "big", "small"], help="debug: only layers with n >= 2048 / n < 2048")
     ap.add_argument("--streams", type=int, default=72, help="CUDA streams the independent layers are spread over")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--model-order", action="store_true", help="issue layers in model order instead of longest chains first")
     return ap.parse_args()
 
 
@@ -272,7 +273,7 @@ def run_ours(args):
     from sleekit_b200.pipeline import LayerSetQuantizer
 
     lsq = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=DAMP, nb_ls_moves=0, grid_size=GRID,
-                            streams=args.streams)
+                            streams=args.streams, big_first=not args.model_order)
 
     def step_eager():
         lsq(Wd, Hd, errs_out=errs, keep_outputs=False)
@@ -319,7 +320,7 @@ def run_ours(args):
     # per-operation device time from a SERIAL eager pass (one stream: event pairs then bracket
     # exactly one operation's kernels; on overlapping streams they would include each other)
     serial = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=DAMP, nb_ls_moves=0, grid_size=GRID,
-                               streams=1)
+                               streams=1, big_first=False)
     serial(Wd, Hd, errs_out=errs, keep_outputs=False)
     torch.cuda.synchronize()
     ops.PROFILE = {}

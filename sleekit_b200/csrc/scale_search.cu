@@ -69,7 +69,7 @@ __device__ __forceinline__ HT row_error(const float* __restrict__ rowp, int64_t 
 constexpr int TAB_MAXC = 16;
 constexpr int TAB_PITCH = 18;     // T[0..C] then padding; all lanes read one grid point's table -> distinct banks
 constexpr int TAB_THREADS = 128;
-constexpr int TAB_MAXG = 256;
+constexpr int TAB_MAXG = 128;    // grid points per row held in shared memory (23 KB per CTA: 9 CTAs per SM)
 
 __device__ __forceinline__ int f32_ord(float x) {
   const int i = __float_as_int(x);

@@ -20,13 +20,14 @@ class LayerSetQuantizer:
     """Holds the side streams; call it with lists of device tensors."""
 
     def __init__(self, codebook, scaling_mode="diag", act_order="diag", damp=0.01, nb_ls_moves=0, grid_size=100,
-                 min_factor=0.05, max_factor=1.0, streams=8):
+                 min_factor=0.05, max_factor=1.0, streams=8, big_first=True):
         ops.require_cuda()
         self.cb = codebook
         self.scaling_mode, self.act_order = scaling_mode, act_order
         self.damp, self.nb_ls_moves = damp, nb_ls_moves
         self.grid_size, self.min_factor, self.max_factor = grid_size, min_factor, max_factor
         self.streams = [torch.cuda.Stream() for _ in range(max(1, int(streams)))]
+        self.big_first = bool(big_first)
 
     def _one(self, W, H):
         sc = _device_scaling(W, self.cb, H, self.scaling_mode, self.grid_size, self.min_factor, self.max_factor)
@@ -47,9 +48,12 @@ class LayerSetQuantizer:
         start.record(main)
         outs, scales = [None] * L, [None] * L
         S = len(self.streams)
-        for i in range(L):
-            st = self.streams[i % S]
-            if i < S:
+        # longest serial chains first (the fp64 factor chain grows with n, the sweep chain with n):
+        # their launches then enter the queues ahead of the short layers that fill the gaps
+        issue = sorted(range(L), key=lambda k: (-Ws[k].shape[1], -Ws[k].shape[0], k)) if self.big_first else range(L)
+        for slot, i in enumerate(issue):
+            st = self.streams[slot % S]
+            if slot < S:
                 st.wait_event(start)
             with torch.cuda.stream(st):
                 if _pre is not None:
