@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
       // by the export kernel after this launch
       double* Xg = Dinv + (int64_t)j * CT * CT;
       for (int e = tid; e < CT * CT; e += CTH) Xg[e] = sm.f.X[(e >> 6) * CP + (e & 63)];
-      __threadfence();
+      // publish: the CTA barrier orders every thread's stores before thread 0's release store, and a
+      // gpu-scope release is cumulative -- no per-thread fence (the pattern of a split-K semaphore)
       __syncthreads();
       if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
       for (int e = tid; e < CT * CT; e += CTH) {
@@ -428,7 +429,6 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
         }
     }
     if (tr) tr[6] = clock64();
-    __threadfence();
     __syncthreads();
     if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
     if (tr) { tr[7] = clock64(); tr[3] = gtimer(); }
