@@ -148,8 +148,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  if (EPI == TC_HESS_SYM && n0 + BN <= m0) return;   // strictly-lower tile of a symmetric product
-  const int num_kb = (int)((p.K + TC_BK - 1) / TC_BK);
+  if ((EPI == TC_HESS_SYM || EPI == TC_SYM_PART) && n0 + BN <= m0) return;   // strictly-lower tile of a symmetric product
+  const int num_kb_all = (int)((p.K + TC_BK - 1) / TC_BK);
+  // split-K (TC_SYM_PART): this CTA covers k-blocks [kb0, kb0 + num_kb) and writes plane blockIdx.z
+  const int kb0 = EPI == TC_SYM_PART ? (int)blockIdx.z * p.kb_per_split : 0;
+  const int num_kb = EPI == TC_SYM_PART ? max(0, min(p.kb_per_split, num_kb_all - kb0)) : num_kb_all;
   const int num_chunks = (num_kb + TC_KC - 1) / TC_KC;
 
   if (warp == 0 && lane == 0) {
@@ -176,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_wait(empty_bar + s, ph ^ 1u, p.error_flag);
         uint8_t* st = tiles + s * SM::STAGE_BYTES;
         mbar_expect_tx(full_bar + s, SM::STAGE_BYTES);
-        const int k0 = kb * TC_BK;
+        const int k0 = (kb0 + kb) * TC_BK;
         tma_load_2d(st, &map_a_hi, full_bar + s, k0, m0);
         tma_load_2d(st + SM::A_BYTES, &map_a_lo, full_bar + s, k0, m0);
         tma_load_2d(st + 2 * SM::A_BYTES, &map_b_hi, full_bar + s, k0, n0);
@@ -242,6 +245,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tc_ld16(tmem_lo + lane_sel + (uint32_t)c0, v);
+      if (num_kb == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;       // empty k range: TMEM was never written
+      }
       const int64_t col = (int64_t)n0 + c0;
       if (!row_ok || col >= p.N) continue;
 #pragma unroll
@@ -260,6 +267,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             p.C[n * p.ldc + row] = o;
           }
         }
+      } else if (EPI == TC_SYM_PART) {
+        float* cc = p.C + (int64_t)blockIdx.z * p.M * p.ldc + row * p.ldc + col;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col + j < p.N) cc[j] = v[j];
       } else if (EPI == TC_ROWDOT) {
         const float* rr = p.R + row * p.ldr + col;
         const float* r2 = p.R2 ? p.R2 + row * p.ldr + col : nullptr;
@@ -401,7 +413,7 @@ bool tc_gemm_usable(const void* a, int64_t lda, const void* b, int64_t ldb) {
 
 template <int BN, int EPI>
 static int tc_launch(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
-                     int64_t ldb, const TcParams& p, cudaStream_t st) {
+                     int64_t ldb, const TcParams& p, cudaStream_t st, int splits = 1) {
   constexpr int STAGES = BN == 128 ? 3 : 4;
   typedef TcSmem<BN, STAGES> SM;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -416,7 +428,7 @@ static int tc_launch(const float* a_hi, const float* a_lo, int64_t lda, const fl
     SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_done = true;
   }
-  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, TC_BM));
+  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, TC_BM), (unsigned)splits);
   kern<<<grid, TC_THREADS, SM::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
@@ -477,6 +489,33 @@ size_t tc_gemm_ws_bytes(int64_t M, int64_t N, int64_t K) {
   return (size_t)(2 * M * Kp + 2 * N * Kp) * sizeof(float) + 1024;
 }
 
+// Split-K reduction of the symmetric Hessian product: planes are added in order (deterministic),
+// then H = H*keep + D/count is applied to (m, n) and mirrored to (n, m) (statistics.py:82-87).
+__global__ void __launch_bounds__(256) sym_part_reduce_kernel(const float* __restrict__ part, int splits, int64_t n,
+                                                              float* __restrict__ H, float keep, float count) {
+  const int64_t total = n * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t m = t / n, c = t - m * n;
+    if (c < m) continue;
+    float d = part[t];
+    for (int z = 1; z < splits; ++z) d = __fadd_rn(d, part[(int64_t)z * total + t]);
+    const float o = __fadd_rn(__fmul_rn(H[t], keep), __fdiv_rn(d, count));
+    H[t] = o;
+    H[c * n + m] = o;
+  }
+}
+
+static inline int sym_splits(int64_t M, int64_t K) {
+  const int64_t tm = ceil_div(M, TC_BM);
+  const int64_t tiles = tm * (tm + 1) / 2;
+  const int64_t kb = ceil_div(K, TC_BK);
+  int s = (int)((int64_t)sm_count() / (tiles > 0 ? tiles : 1));
+  if (s > 8) s = 8;
+  if ((int64_t)s > kb / 8) s = (int)(kb / 8);      // at least 8 k-blocks (two drained chunks) per split
+  return s < 2 ? 1 : s;
+}
+
 // D = At^T * At (M = N = columns of At): one transposing split feeds both operands.
 int tc_gemm_at_f32(int epi, const float* At, int64_t ldat, TcParams p, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t Kp = (p.K + 3) / 4 * 4;
@@ -488,6 +527,21 @@ int tc_gemm_at_f32(int epi, const float* At, int64_t ldat, TcParams p, void* ws,
   dim3 grid((unsigned)ceil_div(p.M, 32), (unsigned)ceil_div(p.K, 32));
   split_tf32_transpose_kernel<<<grid, 256, 0, st>>>(At, p.K, p.M, ldat, Kp, hi, lo);
   SLK_LAUNCH_CHECK();
+  if (epi == TC_HESS_SYM) {
+    // few output tiles (small n): split K over blockIdx.z so that the grid covers the SMs
+    const int splits = sym_splits(p.M, p.K);
+    if (splits > 1 && ws_bytes >= tc_gemm_at_ws_bytes(p.M, p.K)) {
+      float* part = lo + elems;
+      TcParams q = p;
+      q.C = part; q.ldc = p.N;
+      q.kb_per_split = (int)ceil_div(ceil_div(p.K, TC_BK), splits);
+      int rc = tc_launch<128, TC_SYM_PART>(hi, lo, Kp, hi, lo, Kp, q, st, splits);
+      if (rc) return rc;
+      sym_part_reduce_kernel<<<split_grid(p.M * p.N), 256, 0, st>>>(part, splits, p.M, p.C, p.keep, p.count);
+      SLK_LAUNCH_CHECK();
+      return SLK_OK;
+    }
+  }
   switch (epi) {
     case TC_STORE: return tc_launch<128, TC_STORE>(hi, lo, Kp, hi, lo, Kp, p, st);
     case TC_HESS: return tc_launch<128, TC_HESS>(hi, lo, Kp, hi, lo, Kp, p, st);
@@ -499,7 +553,8 @@ int tc_gemm_at_f32(int epi, const float* At, int64_t ldat, TcParams p, void* ws,
 
 size_t tc_gemm_at_ws_bytes(int64_t M, int64_t K) {
   const int64_t Kp = (K + 3) / 4 * 4;
-  return (size_t)(2 * M * Kp) * sizeof(float) + 1024;
+  const int splits = sym_splits(M, K);
+  return (size_t)(2 * M * Kp + (splits > 1 ? (int64_t)splits * M * M : 0)) * sizeof(float) + 1024;
 }
 
 }  // namespace slk

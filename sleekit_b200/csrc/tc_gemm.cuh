@@ -5,7 +5,7 @@
 
 namespace slk {
 
-enum TcEpilogue { TC_STORE = 0, TC_ACCUM = 1, TC_HESS = 2, TC_ROWDOT = 3, TC_HESS_SYM = 4 };
+enum TcEpilogue { TC_STORE = 0, TC_ACCUM = 1, TC_HESS = 2, TC_ROWDOT = 3, TC_HESS_SYM = 4, TC_SYM_PART = 5 };
 
 struct TcParams {
   float* C; int64_t ldc;         // TC_STORE / TC_ACCUM / TC_HESS: [M, N]; TC_ROWDOT: partials [M, tiles_n]
@@ -13,6 +13,7 @@ struct TcParams {
   int64_t M, N, K;
   float alpha, keep, count;
   int* error_flag;               // set (and the kernel traps) if a barrier wait exceeds its budget
+  int kb_per_split = 0;          // TC_SYM_PART: k-blocks (of 32) per blockIdx.z; plane z of C is C + z*M*ldc
 };
 
 constexpr int TC_TILE_N = 128;
