@@ -756,6 +756,7 @@ static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r
 // (tcgen05, fp32-faithful 3xTF32) pushes the finished block to every later column:
 //     Pacc[:, e:] += D[:, s:e] R[s:e, e:]
 static constexpr int64_t SWEEP_MB = MB_COLS;
+static constexpr int64_t SWEEP_SUPER = 2048;
 
 static bool sweep_macro_ok(int64_t r, int64_t n, const float* d, const float* rt_hi, const float* rt_lo) {
   static int off = -1;
@@ -800,18 +801,26 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
   float* dhi = pacc + (size_t)r * n;
   float* dlo = dhi + (size_t)r * n;
   SLK_CUDA(cudaMemsetAsync(pacc, 0, (size_t)r * n * sizeof(float), st));
-  for (int64_t s0 = 0; s0 < n; s0 += SWEEP_MB) {
-    const int64_t e0 = (s0 + SWEEP_MB) < n ? (s0 + SWEEP_MB) : n;
-    rc = fused(s0, e0, pacc, e0 < n ? dhi : nullptr, dlo);
-    if (rc) return rc;
-    if (e0 < n) {
-      TcParams p;
-      p.C = pacc + e0; p.ldc = n; p.R = nullptr; p.R2 = nullptr; p.ldr = 0;
-      p.M = r; p.N = n - e0; p.K = e0 - s0;
-      p.alpha = 1.0f; p.keep = 0.0f; p.count = 1.0f; p.error_flag = nullptr;
-      rc = tc_gemm_presplit_f32(TC_ACCUM, dhi + s0, dlo + s0, n, rt_hi + e0 * n + s0, rt_lo + e0 * n + s0, n, p, st);
+  auto push = [&](int64_t k0, int64_t k1, int64_t c0, int64_t c1) -> int {   // Pacc[:, c0:c1] += D[:, k0:k1] R[k0:k1, c0:c1]
+    TcParams p;
+    p.C = pacc + c0; p.ldc = n; p.R = nullptr; p.R2 = nullptr; p.ldr = 0;
+    p.M = r; p.N = c1 - c0; p.K = k1 - k0;
+    p.alpha = 1.0f; p.keep = 0.0f; p.count = 1.0f; p.error_flag = nullptr;
+    return tc_gemm_presplit_f32(TC_ACCUM, dhi + k0, dlo + k0, n, rt_hi + c0 * n + k0, rt_lo + c0 * n + k0, n, p, st);
+  };
+  // Two levels of lazy batching for wide layers (the read-modify-write of Pacc is HBM traffic:
+  // r (n - e) 8 bytes per GEMM): inside a super block of SWEEP_SUPER columns the macro-block GEMMs
+  // only reach to its end; one K = SWEEP_SUPER GEMM then pushes the whole super block to the rest.
+  const int64_t super = n > 2 * SWEEP_SUPER ? SWEEP_SUPER : n;
+  for (int64_t S0 = 0; S0 < n; S0 += super) {
+    const int64_t S1 = (S0 + super) < n ? (S0 + super) : n;
+    for (int64_t s0 = S0; s0 < S1; s0 += SWEEP_MB) {
+      const int64_t e0 = (s0 + SWEEP_MB) < S1 ? (s0 + SWEEP_MB) : S1;
+      rc = fused(s0, e0, pacc, e0 < n ? dhi : nullptr, dlo);
       if (rc) return rc;
+      if (e0 < S1 && (rc = push(s0, e0, e0, S1))) return rc;
     }
+    if (S1 < n && (rc = push(S0, S1, S1, n))) return rc;
   }
   return SLK_OK;
 }
