@@ -60,5 +60,30 @@ def main():
         torch.cuda.empty_cache()
 
 
+def obq_case():
+    """compute_obq_scaling: 100 full sweeps per layer sharing one factor."""
+    dev = "cuda"
+    for r, n in ((768, 768), (3072, 768), (768, 3072)):
+        cb = codebook.UniformCodebook(8, -1, 1)
+        g = np.random.default_rng(1)
+        Wd = torch.from_numpy(0.02 * g.standard_normal((r, n), dtype=np.float32)).to(dev)
+        X = torch.from_numpy(wl.synthetic_calibration(n, 7, 2048)).to(dev)
+        H = torch.zeros((n, n), dtype=torch.float32, device=dev)
+        m = torch.zeros(n, dtype=torch.float32, device=dev)
+        ops.hessian_accum(X, H, m, 0.0, 2048)
+        scaling.obq_scale_device(Wd, cb, H)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sc, info = scaling.obq_scale_device(Wd, cb, H)
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"case": f"compute_obq_scaling [{r},{n}] 100 grid points", "ms": round(e0.elapsed_time(e1), 2),
+                          "sweeps_per_s": round(100 / (e0.elapsed_time(e1) * 1e-3), 1)}), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "obq":
+        obq_case()
+    else:
+        main()
