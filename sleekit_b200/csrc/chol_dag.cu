@@ -20,6 +20,8 @@
 // however few CTAs are resident (the decoupled look-back argument).  No dependent launches: the
 // n/64-panel launch chain of the right-looking version (hinv.cu) becomes in-kernel flag latency.
 #include "common.cuh"
+
+#include <stdlib.h>
 #include "tc_gemm.cuh"
 
 namespace slk {
@@ -508,7 +510,17 @@ static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const 
     attr_done = true;
   }
   const int64_t ntasks = (int64_t)T * (T + 1) / 2;
-  int64_t grid = 2 * (int64_t)T + 2;
+  // CTAs: a small factorisation is bound by the chain of diagonal tiles, not by the number of CTAs
+  // (n = 768: the same 0.28 ms with 11 to 26 CTAs), and every CTA beyond the useful ones only holds
+  // an SM slot while it spins; larger ones get 1.5 CTAs per tile row (n = 3072: 1.14 ms with 2 per
+  // row, 1.29 ms with 1.5, 1.65 ms with 1).  SLK_CHOL_GRID overrides the percentage (experiments).
+  static int grid_pct = -1;
+  if (grid_pct < 0) {
+    const char* ev = getenv("SLK_CHOL_GRID");
+    grid_pct = ev ? atoi(ev) : 0;
+  }
+  const int pct = grid_pct >= 50 ? grid_pct : (T <= 16 ? 100 : 150);
+  int64_t grid = (int64_t)T * pct / 100 + 2;
   if (grid > ntasks) grid = ntasks;
   if (grid > 2 * (int64_t)sm_count()) grid = 2 * (int64_t)sm_count();
   chol_dag_kernel<<<(unsigned)grid, CTH, sizeof(CholSmem), st>>>(A, npad, T, Dinv, sync, info);

@@ -790,7 +790,7 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
     const char* ev = getenv("SLK_SWEEP_CTAS");
     want_env = ev ? atoll(ev) : 0;
   }
-  const int64_t want = want_env > 0 ? want_env : (int64_t)sm_count() / 3;
+  const int64_t want = want_env > 0 ? want_env : ((int64_t)sm_count() / 48) * 16;   // 48 on a B200: 768 rows -> 16 per CTA
   auto fused = [&](int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) -> int {
     if (n % 4 == 0 && c1 - c0 <= MB_COLS && (((uintptr_t)r32) & 15) == 0) {
       if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
