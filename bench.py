@@ -412,23 +412,46 @@ def run_ours(args):
         # The dominant operation is timed per launch (events on the launching stream, serial pass);
         # launches are grouped by layer shape and the group with the largest total is reported.
         per_launch = [s_.elapsed_time(e_) for s_, e_ in top_events]
+        avg_ms = sum(per_launch) / len(per_launch)
         groups = {}
         for (r_, n_), ms_ in zip(shapes, per_launch):
             groups.setdefault((r_, n_) if top not in ("chol_factor", "hinv") else (0, n_), []).append(ms_)
-        gkey = max(groups, key=lambda k: sum(groups[k]))
-        g_ms = sum(groups[gkey]) / len(groups[gkey])
-        gr, gn = gkey
         share = phases[top][0] / serial_total_ms if serial_total_ms else None
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-            traffic = tj.get(f"{top}:n={gn}" if gr == 0 else f"{top}:{gr}x{gn}", {}).get("dram_bytes_per_launch")
+            tot_b, tot_n = 0.0, 0
+            for (gr_, gn_), v in groups.items():
+                key = f"{top}:n={gn_}" if gr_ == 0 else f"{top}:{gr_}x{gn_}"
+                if key in tj:
+                    tot_b += tj[key]["dram_bytes_per_launch"] * len(v)
+                    tot_n += len(v)
+            if tot_n == len(per_launch):
+                traffic = tot_b / tot_n          # launch-weighted mean over the shapes, ncu --set full
         except Exception:
             pass
-        common = {"kernel": top, "group": (f"n={gn}" if gr == 0 else f"[{gr},{gn}]"), "avg_launch_ms": g_ms,
-                  "launches_timed": len(groups[gkey]), "traffic": traffic, "share_of_serial_device_time": share,
-                  "all_groups_ms": {(f"n={k[1]}" if k[0] == 0 else f"{k[0]}x{k[1]}"): round(sum(v) / len(v), 4)
-                                    for k, v in groups.items()}}
+
+        def work(gr_, gn_):
+            """algorithmic work of one launch, in flop or bytes depending on the op"""
+            if top == "scale_search":
+                return 4.0 * GRID * gr_ * gn_
+            if top in ("hinv", "chol_factor"):
+                return (2.0 if top == "hinv" else 1.0) * gn_ ** 3 / 3.0
+            if top == "gptq_sweep":
+                return float(gr_) * gn_ * gn_
+            if top == "hweighted_error":
+                return 2.0 * gr_ * gn_ * gn_
+            return 8.0 * gr_ * gn_
+
+        unit_scale = 1e9 if top not in ("hinv", "chol_factor", "gptq_sweep", "hweighted_error") else 1e12
+        total_work = sum(work(*k) * len(v) for k, v in groups.items())
+        achieved_all = total_work / (sum(per_launch) * 1e-3) / unit_scale
+        common = {"kernel": top, "avg_launch_ms": avg_ms, "launches_timed": len(per_launch), "traffic": traffic,
+                  "share_of_serial_device_time": share,
+                  "by_shape": {(f"n={k[1]}" if k[0] == 0 else f"{k[0]}x{k[1]}"):
+                               {"launches": len(v), "avg_ms": round(sum(v) / len(v), 4),
+                                "achieved": round(work(*k) / (sum(v) / len(v) * 1e-3) / unit_scale, 3)}
+                               for k, v in groups.items()}}
 
         def fp64_peak():
             a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
@@ -444,34 +467,32 @@ def run_ours(args):
 
         if top == "scale_search":
             # reference traffic model = one pass over W per grid point = 4*G bytes/weight
-            achieved = 4.0 * GRID * gr * gn / (g_ms * 1e-3) / 1e9
-            roofline = dict(common, bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
-                            peak_source=peak_src,
+            roofline = dict(common, bound="hbm", achieved=achieved_all, peak=hbm_peak, unit="GB/s",
+                            frac=achieved_all / hbm_peak, peak_source=peak_src,
                             note=("effective GB/s: algorithmic bytes = 4*G bytes per weight (the reference's G passes "
                                   "over W, scaling.py:127-133); the fused kernel reads W twice (8 B/weight of real "
                                   "traffic) and is bound by instruction issue (exact threshold tables, ~16 "
                                   "instructions per weight and grid point)"))
         elif top in ("hinv", "chol_factor"):
-            flop = (2.0 if top == "hinv" else 1.0) * gn ** 3 / 3.0
             peak = fp64_peak()
-            achieved = flop / (g_ms * 1e-3) / 1e12
-            roofline = dict(common, bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+            roofline = dict(common, bound="tensor", achieved=achieved_all, peak=peak, unit="TFLOP/s",
+                            frac=achieved_all / peak,
                             peak_source="cuBLAS fp64 GEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                            note=("K2: fp64 damp + permute + Cholesky factor (n^3/3 flop; the sweep's R form needs no "
-                                  "inverse), one tile-task kernel on the FP64 tensor path (DMMA); bounded by the chain "
-                                  "of n/64 dependent 64x64 tile factorisations (64 dependent rsqrt each), not by the "
-                                  "FP64 pipe, at these sizes; all_groups_ms lists the other shapes"))
+                            note=("K2: fp64 damp + permute + Cholesky factor (n^3/3 flop per launch; the sweep's R form "
+                                  "needs no inverse), one tile-task kernel on the FP64 tensor path (DMMA); achieved = "
+                                  "algorithmic flop of all timed launches / their total time (by_shape has each shape). "
+                                  "At these sizes the factor is bounded by the chain of n/64 dependent 64x64 tile "
+                                  "factorisations (64 dependent rsqrt each), not by the FP64 pipe: 36 % of this peak at "
+                                  "n=4096, 71 % at n=11008, 73 % at n=28672 (DESIGN.md section 4)"))
         elif top in ("gptq_sweep", "hweighted_error"):
-            flop = float(gr) * gn * gn * (1.0 if top == "gptq_sweep" else 2.0)
             peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
-            achieved = flop / (g_ms * 1e-3) / 1e12
-            roofline = dict(common, bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                            peak_source="half of the measured bf16 peak (dense TF32 = bf16/2)",
+            roofline = dict(common, bound="tensor", achieved=achieved_all, peak=peak, unit="TFLOP/s",
+                            frac=achieved_all / peak, peak_source="half of the measured bf16 peak (dense TF32 = bf16/2)",
                             note="algorithmic fp32 flop of the GEMM phase per launch (r*n^2 sweep, 2*r*n^2 error)")
         else:
-            achieved = 8.0 * gr * gn / (g_ms * 1e-3) / 1e9
-            roofline = dict(common, bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
-                            peak_source=peak_src, note="algorithmic bytes = one read + one write of W per launch")
+            roofline = dict(common, bound="hbm", achieved=achieved_all, peak=hbm_peak, unit="GB/s",
+                            frac=achieved_all / hbm_peak, peak_source=peak_src,
+                            note="algorithmic bytes = one read + one write of W per launch")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world >= 1:
