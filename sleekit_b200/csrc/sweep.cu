@@ -568,9 +568,15 @@ __device__ long long* g_sweep_trace = nullptr;   // development aid: per-block p
 template <int R>
 struct MacroSmem {
   static constexpr int KG = 32 / R;
+  static constexpr int NLEAF = 4 * R;                       // threads of the leaf
+  static constexpr int NSLOT = 8 * R;                       // (row, 4-column) output slots of a block
+  static constexpr int HELP = FT - NLEAF;                   // threads free while the leaf runs
+  static constexpr int KGH = HELP >= NSLOT ? HELP / NSLOT : 1;   // their k groups
+  static constexpr int SPT = HELP >= NSLOT ? 1 : NSLOT / HELP;   // slots per helper thread
   float Dm[R][MB_PITCH];                    // D = W - Q of this macro block
   float Rs[2][MB_COLS - 32][32];            // R[c0 + k][a + col], k < a - c0
   float red[KG][R][33];
+  float red2[KGH][R][33];                   // look-ahead part of the next block's product
   float Qs[R][33];
   float W0[R][33];
   LeafShared32 leaf;
@@ -626,30 +632,34 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
     cp_async_commit();
   };
 
+  // Schedule per 32-column block J (panel = R[c0:a, J], landed one block earlier):
+  //   (1) tail of the product: the 32 columns of D the previous leaf produced, all threads
+  //   (2) + the look-ahead part computed during the previous leaf (red2) + Pacc, times Ud_J
+  //   (3) leaf on 4R threads  ||  the other threads form the next block's product over all
+  //       columns of D that already exist (look-ahead), so only 32 k-steps remain on the chain
+  for (int t = tid; t < SM::KGH * R * 33; t += FT) (&sm.red2[0][0][0])[t] = 0.0f;
   Pre cur, nxt;
   fetch(c0, cur);
-  cp_async_commit();                                   // block c0 has no panel: empty group keeps the counting uniform
   int buf = 0;
   for (int64_t a = c0; a < c1; a += 32, buf ^= 1) {
     const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
-    const int ka = (int)(a - c0);                      // k extent of this block's product
+    const int ka = (int)(a - c0);                      // columns of D that exist when this block starts
     const bool has_next = a + 32 < c1;
     if (has_next) {
-      prefetch_panel(a + 32, buf ^ 1);
+      prefetch_panel(a + 32, buf ^ 1);                 // read by the look-ahead below and by the next tail
       fetch(a + 32, nxt);
-    } else {
-      cp_async_commit();
     }
     long long* tr = (g_sweep_trace && blockIdx.x == 0 && tid == 0) ? g_sweep_trace + ((a - c0) / 32) * 8 : nullptr;
     if (tr) tr[0] = clock64();
-    cp_async_wait<1>();                                // this block's panel has landed
-    __syncthreads();
+    __syncthreads();                                   // previous leaf's D and the look-ahead sums are visible
     if (tr) tr[1] = clock64();
-    // ---- (1) P = D[:, c0:a] R[c0:a, J] from shared memory, split over the k groups --------------
+    // ---- (1) tail: D[:, a-32:a] R[a-32:a, J], the 32 k split over the k groups --------------------
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kb = kg * 32; kb < ka; kb += 32 * KG) {
-#pragma unroll 8
-      for (int kk = 0; kk < 32; ++kk) {
+    if (ka > 0) {
+      constexpr int KPG = 32 / KG;
+      const int kb = ka - 32 + kg * KPG;
+#pragma unroll
+      for (int kk = 0; kk < KPG; ++kk) {
         const float e = sm.Dm[lrow][kb + kk];
         const float4 u = *reinterpret_cast<const float4*>(&sm.Rs[buf][kb + kk][seg * 4]);
         acc[0] = __fmaf_rn(e, u.x, acc[0]);
@@ -675,6 +685,8 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
         float t = sm.red[0][lrow][seg * 4 + j];
 #pragma unroll
         for (int q = 1; q < KG; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
+#pragma unroll
+        for (int q = 0; q < SM::KGH; ++q) t = __fadd_rn(t, sm.red2[q][lrow][seg * 4 + j]);
         sm.Qs[lrow][seg * 4 + j] = __fadd_rn(t, cur.pa[j]);
         sm.W0[lrow][seg * 4 + j] = cur.wq[j];
       }
@@ -699,13 +711,11 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) sm.Qs[lrow][seg * 4 + j] = __fadd_rn(cur.wq[j], s4[j]);
     }
+    cp_async_wait<0>();                                // the next block's panel (own pieces) has landed
     __syncthreads();
-    // ---- (3) leaf: FOUR lanes per row, 8 columns each -- the owner of column i quantises it and
-    // forms the residual, a shuffle hands it to the row's other lanes, every lane updates its own
-    // columns (<= 8 FMAs instead of 31 in one thread).  D goes to shared memory (next products)
-    // and to HBM (macro-block GEMM).  obq.py:110-118 in the R form.
     if (tr) tr[3] = clock64();
-    if (tid < R * 4) {
+    if (tid < SM::NLEAF) {
+      // ---- (3a) leaf: four lanes per row (leaf_rows4) -----------------------------------------------
       const int lr = tid >> 2, part = tid & 3, lane = tid & 31;
       const bool rowok = row0 + lr < r;
       float q[8];
@@ -721,11 +731,36 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
       float* dlo = Dhi ? Dlo + (row0 + lr) * n + a : nullptr;
       if (fastq) leaf_rows4<true>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
       else leaf_rows4<false>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
+    } else if (has_next) {
+      // ---- (3b) look-ahead: D[:, c0:a] R[c0:a, J+1] on the threads the leaf does not use -----------
+      const int h = tid - SM::NLEAF;
+      const int gh = SM::SPT == 1 ? h / SM::NSLOT : 0;
+      if (gh < SM::KGH) {
+#pragma unroll
+        for (int sp = 0; sp < SM::SPT; ++sp) {
+          const int slot = (SM::SPT == 1 ? h % SM::NSLOT : h + sp * SM::HELP);
+          const int hr = slot >> 3, hs = slot & 7;
+          float la[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int kb = gh * 32; kb < ka; kb += 32 * SM::KGH) {
+#pragma unroll 8
+            for (int kk = 0; kk < 32; ++kk) {
+              const float e = sm.Dm[hr][kb + kk];
+              const float4 u = *reinterpret_cast<const float4*>(&sm.Rs[buf ^ 1][kb + kk][hs * 4]);
+              la[0] = __fmaf_rn(e, u.x, la[0]);
+              la[1] = __fmaf_rn(e, u.y, la[1]);
+              la[2] = __fmaf_rn(e, u.z, la[2]);
+              la[3] = __fmaf_rn(e, u.w, la[3]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm.red2[gh][hr][hs * 4 + j] = la[j];
+        }
+      }
     }
     if (tr) tr[4] = clock64();
     cur = nxt;
     if (tr) tr[5] = clock64();
-    // the barrier at the top of the next iteration orders Dm / Qs / leaf reuse
+    // the barrier at the top of the next iteration orders Dm / Qs / leaf / red2 reuse
   }
 }
 
