@@ -157,6 +157,13 @@ int slk_argsort_f64(const double* keys, int64_t n, int64_t* order, void* stream)
 int slk_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* idx, int scatter,
                          float* dst, void* stream);
 
+/* The two passes on either side of the sweep, fused (one pass over W each):
+ * scatter 0: dst[:, j] = src[:, idx[j]] / s[row]            scaling.py:73 + obq.py:202
+ * scatter 1: dst[:, idx[j]] = src[:, j] / (1 / s[row])      obq.py:212-213 + scaling.py:80
+ * idx may be NULL (identity).  Same separately rounded divides as slk_scale_axis_f32. */
+int slk_scale_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* idx,
+                               const float* s, int scatter, float* dst, void* stream);
+
 /* ---- K2: damp + permute + fp64 factor of the inverse --------------------------
  * H_opt = H + dampval*I; H_opt[order][:, order]; compute_hessian_chol
  *                                                             obq.py:198-205, 38-55

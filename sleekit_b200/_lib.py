@@ -69,6 +69,7 @@ SIGNATURES = {
     "slk_order_keys": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "slk_argsort_f64": (_INT, [_P, _I64, _P, _P]),
     "slk_permute_cols_f32": (_INT, [_P, _I64, _I64, _P, _INT, _P, _P]),
+    "slk_scale_permute_cols_f32": (_INT, [_P, _I64, _I64, _P, _P, _INT, _P, _P]),
     "slk_hinv_ws_bytes": (_SZ, [_I64]),
     "slk_hinv_from_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P, _P, _P]),
     "slk_hinv_from_f64": (_INT, [_P, _I64, _P, _SZ, _P, _P, _P, _P]),

@@ -283,6 +283,29 @@ __global__ void __launch_bounds__(256) permute_cols_kernel(const float* __restri
   }
 }
 
+// Row scaling fused with the column permutation (the two passes on either side of the sweep):
+//   gather : dst[row, j]      = src[row, idx[j]] / s[row]            scaling.py:73 then obq.py:202
+//   scatter: dst[row, idx[j]] = src[row, j] / (1 / s[row])           obq.py:212-213 then scaling.py:80
+// Same separately rounded divides as slk_scale_axis_f32; one pass over W instead of two.
+__global__ void __launch_bounds__(256) scale_permute_cols_kernel(const float* __restrict__ src, int64_t r, int64_t n,
+                                                                 const int64_t* __restrict__ idx,
+                                                                 const float* __restrict__ s, int scatter,
+                                                                 float* __restrict__ dst) {
+  const int64_t total = r * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t row = i / n, j = i - row * n;
+    const int64_t k = idx ? __ldg(idx + j) : j;
+    float d = __ldg(s + row);
+    if (scatter) {
+      d = __fdiv_rn(1.0f, d);
+      dst[row * n + k] = __fdiv_rn(src[i], d);
+    } else {
+      dst[i] = __fdiv_rn(__ldg(src + row * n + k), d);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // ordering helpers
 // ---------------------------------------------------------------------------
@@ -542,6 +565,16 @@ int slk_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* 
   if (r * n == 0) return SLK_OK;
   SLK_REQUIRE(src && idx && dst && src != dst, "bad pointers");
   permute_cols_kernel<<<stream_grid(r * n, 256), 256, 0, (cudaStream_t)stream>>>(src, r, n, idx, scatter, dst);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_scale_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* idx, const float* s, int scatter,
+                               float* dst, void* stream) {
+  SLK_REQUIRE(r >= 0 && n >= 0, "negative extent");
+  if (r * n == 0) return SLK_OK;
+  SLK_REQUIRE(src && s && dst && src != dst, "bad pointers");
+  scale_permute_cols_kernel<<<stream_grid(r * n, 256), 256, 0, (cudaStream_t)stream>>>(src, r, n, idx, s, scatter, dst);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

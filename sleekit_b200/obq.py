@@ -162,13 +162,18 @@ def _quantize_opt_core(Q, E, Hinv, quantizer):
 
 
 def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
-                check=False, colsum_reduce=None):
+                check=False, colsum_reduce=None, row_scale=None):
     """quantize_opt on device tensors (fp32 W [r,n], fp32 H [n,n]); returns quantized values [r,n].
     The whole chain -- damp, keys, argsort, gather, fp64 factor, sweep, scatter, local search --
     is enqueued on the current stream without a host round trip.  colsum_reduce: optional callable
     applied to the column residual sums of the err / sqerr orderings (row-sharded runs all-reduce
-    them there, dist.allreduce_column_sums)."""
+    them there, dist.allreduce_column_sums).  row_scale: Wd is then the UNSCALED matrix; the division
+    by the row scales and the de-scaling of the result are fused into the two column-permutation
+    passes (quantize_with_scaling's scaling.py:73 and :80) and the de-scaled weights are returned."""
     dampval = ops.damp_value(Hd, damp)                                   # obq.py:198
+    fuse = row_scale is not None and act_order in ("diag", "none") and not nb_ls_moves
+    if row_scale is not None and not fuse:
+        Wd = ops.scale_rows(Wd, row_scale, 0)                            # scaling.py:73
     if act_order == "none":
         order = None
     elif act_order in ("diag", "err", "sqerr"):
@@ -183,7 +188,10 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
         hopt = Hd.to(torch.float64)
         hopt.diagonal().add_(dampval.to(torch.float64))
         order = _device_order(Wd, hopt, quantizer, act_order, hopt_diag)
-    Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
+    if fuse:
+        Q = ops.scale_permute_cols(Wd, order, row_scale)                  # scaling.py:73 + obq.py:202-203
+    else:
+        Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
     if _sweep_leaf(min_block_size) == MAX_LEAF and USE_CHOL_FORM:
         # factor only (no triangular inverse): H_opt = R R^T, sweep from R
         r32, rt32, ud32, info = ops.chol_factor(Hd, order, dampval)       # obq.py:204 (dpotrf part)
@@ -191,12 +199,19 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
     else:
         u64, u32, info = ops.hinv(Hd, order, dampval)                     # obq.py:204-205
         ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209
+    if fuse:
+        Q = ops.scale_permute_cols(Q, order, row_scale, scatter=True)     # obq.py:212-213 + scaling.py:80
+        if check:
+            _raise_if_not_pd(info)
+        return Q
     if order is not None:
         Q = ops.permute_cols(Q, order, scatter=True)                      # obq.py:212-213
     if check:
         _raise_if_not_pd(info)
     if nb_ls_moves:
         ops.local_search(Wd, Q, Hd, quantizer, nb_ls_moves)               # obq.py:216
+    if row_scale is not None:
+        Q = ops.scale_rows(Q, row_scale, 1)                               # scaling.py:80
     return Q
 
 

@@ -364,6 +364,20 @@ def permute_cols(src, idx, scatter=False):
     return dst
 
 
+@_timed("permute_cols")
+def scale_permute_cols(src, idx, s, scatter=False):
+    """Row scaling fused with the column permutation: gather -> src[:, idx] / s[:, None];
+    scatter -> dst[:, idx] = src / (1 / s)[:, None].  idx may be None."""
+    _chk(src, torch.float32)
+    _chk(s, torch.float32)
+    if idx is not None:
+        _chk(idx, torch.int64)
+    dst = torch.empty_like(src)
+    _lib.call("slk_scale_permute_cols_f32", _ptr(src), src.shape[0], src.shape[1], _ptr(idx), _ptr(s),
+              1 if scatter else 0, _ptr(dst), _stream())
+    return dst
+
+
 # ---------------------------------------------------------------------------
 # K2 / K3 / K7
 # ---------------------------------------------------------------------------
