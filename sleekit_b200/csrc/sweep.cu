@@ -493,12 +493,22 @@ extern "C" int slk_gptq_sweep_f32(float* q, float* e, int64_t r, int64_t n, cons
 // of its remaining columns -- so the dependent chain never crosses a lane; (B) the 8 residuals are
 // shuffled to the row's lanes and the lanes that own later columns apply them (64 independent
 // FMAs).  obq.py:110-118 in the R form; D = W - q goes to shared memory and to HBM.
-template <bool FASTQ>
+// MODE 0: any codebook (grid_value); 1: uniform codebook, exact-reciprocal arithmetic;
+// 2: uniform codebook of <= 8 entries through its exact breakpoints X (idx >= k <=> w >= X[k], found
+//    by bisection with the reference's op chain at kernel start) and values V: a 3-level compare /
+//    select tree, 6 dependent instructions instead of 12 on the column chain, identical results.
+template <int MODE>
 __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh, const DevGrid<float>& g,
                                            const FastDivF& fstep, int width, int part, int lane, bool rowok,
                                            float* __restrict__ qrow, float* __restrict__ drow,
                                            float* __restrict__ dhi, float* __restrict__ dlo,
-                                           const float (&w0)[8], float* __restrict__ dsm) {
+                                           const float (&w0)[8], float* __restrict__ dsm,
+                                           const float* __restrict__ XV = nullptr) {
+  float X[8], V[8];
+  if (MODE == 2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { X[k] = XV[k]; V[k] = XV[8 + k]; }
+  }
   const float top = (float)(g.size - 1);
 #pragma unroll 1
   for (int p = 0; p < 4; ++p) {
@@ -510,7 +520,16 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
         const int i = p * 8 + t;
         const float w = q[t];
         float qq;
-        if (FASTQ) {
+        if (MODE == 2) {
+          const bool b2 = w >= X[4];
+          const float t1 = b2 ? X[6] : X[2];
+          const float xa = b2 ? X[7] : X[3], xb = b2 ? X[5] : X[1];
+          const float va = b2 ? V[7] : V[3], vb = b2 ? V[5] : V[1], vc = b2 ? V[6] : V[2], vd = b2 ? V[4] : V[0];
+          const bool b1 = w >= t1;
+          const float t0 = b1 ? xa : xb;
+          const float c1 = b1 ? va : vb, c0 = b1 ? vc : vd;
+          qq = (w >= t0) ? c1 : c0;
+        } else if (MODE == 1) {
           // codebook.py:60-64 with the divide by the step through the exact reciprocal scheme and
           // rint through the 1.5*2^23 constant (identical after the clip for every finite input)
           const float tt = fastdiv_core(__fsub_rn(w, g.zero), fstep.d, fstep.y);
@@ -561,6 +580,35 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
   }
 }
 
+// Breakpoints X[1..C-1] (X[k] = min{x : slot(x) >= k}, full bisection over the ordered fp32 values with
+// the reference's own op chain, codebook.py:60-62; +inf beyond) and values V[0..7] of a uniform
+// codebook of <= 8 entries; entry k of 0..7 is computed by one thread.
+__device__ __forceinline__ void codebook_xv(const DevGrid<float>& g, const FastDivF& fstep, int k, float* XV) {
+  const float top = (float)(g.size - 1);
+  float xk = __int_as_float(0x7f800000);
+  if (k >= 1 && k < g.size) {
+    auto ord = [](float x) { const int i = __float_as_int(x); return i >= 0 ? i : (int)(0x80000000u - (unsigned)i); };
+    auto unord = [](int o) { return __int_as_float(o >= 0 ? o : (int)(0x80000000u - (unsigned)o)); };
+    long long blo = ord(-3.402823466e+38f), bhi = ord(3.402823466e+38f);
+    while (bhi - blo > 1) {
+      const long long mid = blo + ((bhi - blo) >> 1);
+      float kk = rintf(fastdiv_core(__fsub_rn(unord((int)mid), g.zero), fstep.d, fstep.y));
+      kk = kk < 0.0f ? 0.0f : kk;
+      kk = kk > top ? top : kk;
+      if (kk >= (float)k) bhi = mid; else blo = mid;
+    }
+    xk = unord((int)bhi);
+  }
+  XV[k] = xk;
+  const int kv = k < g.size ? k : g.size - 1;
+  XV[8 + k] = __fadd_rn(__fmul_rn((float)kv, g.step), g.zero);                 // codebook.py:63-64
+}
+
+__global__ void __launch_bounds__(32) codebook_xv_kernel(DevGrid<float> g, float* __restrict__ XV) {
+  const FastDivF fstep = make_fastdiv(g.step);
+  if (threadIdx.x < 8) codebook_xv(g, fstep, threadIdx.x, XV);
+}
+
 constexpr int MB_COLS = 256;
 constexpr int MB_PITCH = MB_COLS + 4;
 __device__ long long* g_sweep_trace = nullptr;   // development aid: per-block phase clocks of CTA 0
@@ -577,6 +625,7 @@ struct MacroSmem {
   float Rs[2][MB_COLS - 32][32];            // R[c0 + k][a + col], k < a - c0
   float red[KG][R][33];
   float red2[KGH][R][33];                   // look-ahead part of the next block's product
+  float XV[16];                             // codebook breakpoints X[0..7] (X[0] unused) and values V[0..7]
   float Qs[R][33];
   float W0[R][33];
   LeafShared32 leaf;
@@ -587,7 +636,7 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
                                                          const float* __restrict__ Rf, const float* __restrict__ Ud,
                                                          DevGrid<float> g, int64_t c0, int64_t c1,
                                                          const float* __restrict__ Pacc, float* __restrict__ Dhi,
-                                                         float* __restrict__ Dlo) {
+                                                         float* __restrict__ Dlo, const float* __restrict__ XVg) {
   typedef MacroSmem<R> SM;
   constexpr int KG = SM::KG;
   extern __shared__ __align__(16) unsigned char macro_raw[];
@@ -638,6 +687,14 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
   //   (3) leaf on 4R threads  ||  the other threads form the next block's product over all
   //       columns of D that already exist (look-ahead), so only 32 k-steps remain on the chain
   for (int t = tid; t < SM::KGH * R * 33; t += FT) (&sm.red2[0][0][0])[t] = 0.0f;
+  const bool tree = fastq && g.size <= 8;
+  if (tree && tid >= FT - 16) {
+    // breakpoints and values of the codebook: computed once per sweep (codebook_xv_kernel) when a
+    // workspace is available, else here
+    const int k = tid - (FT - 16);
+    if (XVg) sm.XV[k] = __ldg(XVg + k);
+    else if (k < 8) codebook_xv(g, fstep, k, sm.XV);
+  }
   Pre cur, nxt;
   fetch(c0, cur);
   int buf = 0;
@@ -729,8 +786,9 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
       float* dsm = &sm.Dm[lr][ka];
       float* dhi = Dhi ? Dhi + (row0 + lr) * n + a : nullptr;
       float* dlo = Dhi ? Dlo + (row0 + lr) * n + a : nullptr;
-      if (fastq) leaf_rows4<true>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
-      else leaf_rows4<false>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
+      if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, sm.XV);
+      else if (fastq) leaf_rows4<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
+      else leaf_rows4<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
     } else if (has_next) {
       // ---- (3b) look-ahead: D[:, c0:a] R[c0:a, J+1] on the threads the leaf does not use -----------
       const int h = tid - SM::NLEAF;
@@ -772,14 +830,15 @@ extern "C" int slk_debug_sweep_trace(void* buf) {
 
 template <int R>
 static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
-                        cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) {
+                        cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo,
+                        const float* xv) {
   auto kern = sweep_macro_kernel<R>;
   static bool attr_done = false;
   if (!attr_done) {
     SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MacroSmem<R>)));
     attr_done = true;
   }
-  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo);
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo, xv);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -826,11 +885,12 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
     want_env = ev ? atoll(ev) : 0;
   }
   const int64_t want = want_env > 0 ? want_env : ((int64_t)sm_count() / 48) * 16;   // 48 on a B200: 768 rows -> 16 per CTA
+  const float* xv = nullptr;
   auto fused = [&](int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) -> int {
     if (n % 4 == 0 && c1 - c0 <= MB_COLS && (((uintptr_t)r32) & 15) == 0) {
-      if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
-      if (r >= 16 * want) return launch_macro<16>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
-      return launch_macro<8>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo);
+      if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
+      if (r >= 16 * want) return launch_macro<16>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
+      return launch_macro<8>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
     }
     if (r >= 32 * want) return launch_fused<32, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
     if (r >= 16 * want) return launch_fused<16, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
@@ -841,6 +901,12 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
   float* pacc = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   float* dhi = pacc + (size_t)r * n;
   float* dlo = dhi + (size_t)r * n;
+  if (g.kind == 0 && g.size <= 8) {             // codebook breakpoints for the leaf's compare tree, once per sweep
+    float* xvw = dlo + (size_t)r * n;
+    codebook_xv_kernel<<<1, 32, 0, st>>>(g, xvw);
+    SLK_LAUNCH_CHECK();
+    xv = xvw;
+  }
   SLK_CUDA(cudaMemsetAsync(pacc, 0, (size_t)r * n * sizeof(float), st));
   auto push = [&](int64_t k0, int64_t k1, int64_t c0, int64_t c1) -> int {   // Pacc[:, c0:c1] += D[:, k0:k1] R[k0:k1, c0:c1]
     TcParams p;
