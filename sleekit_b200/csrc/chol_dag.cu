@@ -512,14 +512,15 @@ static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const 
   const int64_t ntasks = (int64_t)T * (T + 1) / 2;
   // CTAs: a small factorisation is bound by the chain of diagonal tiles, not by the number of CTAs
   // (n = 768: the same 0.28 ms with 11 to 26 CTAs), and every CTA beyond the useful ones only holds
-  // an SM slot while it spins; larger ones get 1.5 CTAs per tile row (n = 3072: 1.14 ms with 2 per
-  // row, 1.29 ms with 1.5, 1.65 ms with 1).  SLK_CHOL_GRID overrides the percentage (experiments).
+  // an SM slot while it spins; mid-sized ones get 1.5 CTAs per tile row (n = 3072: 1.14 ms with 2 per
+  // row, 1.29 ms with 1.5, 1.65 ms with 1), n >= 4096 -- bound by the FP64 pipe, and big enough to
+  // own the GPU -- 2 per row.  SLK_CHOL_GRID overrides the percentage (experiments).
   static int grid_pct = -1;
   if (grid_pct < 0) {
     const char* ev = getenv("SLK_CHOL_GRID");
     grid_pct = ev ? atoi(ev) : 0;
   }
-  const int pct = grid_pct >= 50 ? grid_pct : (T <= 16 ? 100 : 150);
+  const int pct = grid_pct >= 50 ? grid_pct : (T <= 16 ? 100 : (T < 64 ? 150 : 200));
   int64_t grid = (int64_t)T * pct / 100 + 2;
   if (grid > ntasks) grid = ntasks;
   if (grid > 2 * (int64_t)sm_count()) grid = 2 * (int64_t)sm_count();
