@@ -143,41 +143,34 @@ __device__ __forceinline__ void chol_panel8(double* M, double* rd, int b, int la
   }
 }
 
-// Rank-8 update of the 8x8 tiles (ti, tk), b < tk <= ti, by the panel b just factored.  A warp owns
-// up to four tiles (linear index warp + 8m in the row-major enumeration of the triangle); their
-// operands are all loaded before the first DMMA so that the shared-memory latencies overlap.
-__device__ __forceinline__ void chol_trailing8(double* M, int b, int warp, int lane) {
+// Rank-8 update of one 8x8 tile (ti, tk), b < tk <= ti, by the panel b just factored (two DMMAs).
+__device__ __forceinline__ void chol_trailing8_tile(double* M, int abase, int ti, int tk, int fr, int fk) {
+  double* cp = &M[(8 * tk + 2 * fk) * CP + 8 * ti + fr];
+  double c[2] = {cp[0], cp[CP]};
+  const double a0 = M[abase + 8 * ti], a1 = M[abase + 8 * ti + 4 * CP];
+  const double b0 = M[abase + 8 * tk], b1 = M[abase + 8 * tk + 4 * CP];
+  cd_dmma(c, -a0, b0);
+  cd_dmma(c, -a1, b1);
+  cp[0] = c[0];
+  cp[CP] = c[1];
+}
+
+// wr = rank of this warp among the 7 helper warps.  first: only the column block of panel b+1 (tile
+// (b+1+wr, b+1)); else: the remaining tiles (tk >= b+2), dealt round-robin.
+__device__ __forceinline__ void chol_trailing8_part(double* M, int b, bool first, int wr, int lane) {
   const int fr = lane >> 2, fk = lane & 3;
-  const int m = 7 - b, ntile = m * (m + 1) / 2;
   const int abase = (8 * b + fk) * CP + fr;
-  int co[4], ao[4], bo[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int t = warp + 8 * q;
-    int ti = 0, rem = t < ntile ? t : 0;                 // inactive slots alias tile 0 (loads only)
-    while (rem > ti) { rem -= ti + 1; ++ti; }           // row ti holds ti + 1 tiles
-    const int gi = 8 * (b + 1 + ti), gk = 8 * (b + 1 + rem);
-    co[q] = (gk + 2 * fk) * CP + gi + fr;
-    ao[q] = abase + gi;
-    bo[q] = abase + gk;
+  if (first) {
+    const int ti = b + 1 + wr;
+    if (ti < 8) chol_trailing8_tile(M, abase, ti, b + 1, fr, fk);
+    return;
   }
-  double c[4][2], a0[4], a1[4], b0[4], b1[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    c[q][0] = M[co[q]]; c[q][1] = M[co[q] + CP];
-    a0[q] = M[ao[q]]; a1[q] = M[ao[q] + 4 * CP];
-    b0[q] = M[bo[q]]; b1[q] = M[bo[q] + 4 * CP];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    cd_dmma(c[q], -a0[q], b0[q]);
-    cd_dmma(c[q], -a1[q], b1[q]);
-    if (warp + 8 * q < ntile) {
-      M[co[q]] = c[q][0];
-      M[co[q] + CP] = c[q][1];
+  int cm = 0;
+  for (int ti = b + 2; ti < 8; ++ti)
+    for (int tk = b + 2; tk <= ti; ++tk) {
+      if (cm == wr) chol_trailing8_tile(M, abase, ti, tk, fr, fk);
+      if (++cm == 7) cm = 0;
     }
-  }
 }
 
 // C(i, n) = alpha * sum_k A(i, k) B(k, n) on 8x8 DMMA tiles in shared memory, `nprob` independent
@@ -210,15 +203,19 @@ __device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t*
   double* X = sm.f.X;
   for (int t = tid; t < CT * CP; t += CTH) X[t] = 0.0;
   long long tp = 0, tt = 0, c0 = tr ? clock64() : 0;
-  for (int b = 0; b < 8; ++b) {
-    if (warp == 0) chol_panel8(M, sm.rd, b, lane, info, gcol0);
+  // Look-ahead schedule: after panel b, warps 1..7 first update only the column block of panel b+1
+  // (one tile each), then warp 0 factors panel b+1 while warps 1..7 apply panel b to the remaining
+  // tiles -- the bulk of the trailing update runs beside the rsqrt chain instead of after it.
+  if (warp == 0) chol_panel8(M, sm.rd, 0, lane, info, gcol0);
+  __syncthreads();
+  for (int b = 0; b < 7; ++b) {
+    if (warp > 0) chol_trailing8_part(M, b, true, warp - 1, lane);
+    __syncthreads();
+    if (tr) { const long long c1 = clock64(); tt += c1 - c0; c0 = c1; }
+    if (warp == 0) chol_panel8(M, sm.rd, b + 1, lane, info, gcol0);
+    else if (b < 6) chol_trailing8_part(M, b, false, warp - 1, lane);
     __syncthreads();
     if (tr) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
-    if (b < 7) {
-      chol_trailing8(M, b, warp, lane);
-      __syncthreads();
-      if (tr) { const long long c1 = clock64(); tt += c1 - c0; c0 = c1; }
-    }
   }
   if (tr) { tr[8] = tp; tr[9] = tt; tr[10] = clock64(); }
   // inverses of the 8x8 diagonal blocks: thread c solves L_bb x = e_cc by forward substitution
