@@ -174,23 +174,42 @@ __device__ __forceinline__ void chol_trailing8_part(double* M, int b, bool first
 }
 
 // C(i, n) = alpha * sum_k A(i, k) B(k, n) on 8x8 DMMA tiles in shared memory, `nprob` independent
-// problems of size s x s x s laid out with the given strides; tiles are dealt to the 8 warps.
+// problems of size s x s x s (s = 8 << lg) laid out with the given strides.  Tiles are dealt to the
+// 8 warps; a warp that owns two tiles runs them interleaved (two independent accumulator chains).
 __device__ __forceinline__ void smem_mm_batched(double* C, int sci, int scn, int spc, const double* A, int sai, int sak,
-                                                int spa, const double* B, int sbk, int sbn, int spb, int s, int nprob,
+                                                int spa, const double* B, int sbk, int sbn, int spb, int lg, int nprob,
                                                 double alpha, int warp, int lane) {
   const int fr = lane >> 2, fk = lane & 3;
-  const int tn = s >> 3, tiles = tn * tn;
-  for (int t = warp; t < tiles * nprob; t += CTH / 32) {
-    const int p = t / tiles, tt = t - p * tiles;
-    const int i0 = (tt / tn) * 8, n0 = (tt % tn) * 8;
-    const double* Ap = A + p * spa + (i0 + fr) * sai + fk * sak;
-    const double* Bp = B + p * spb + fk * sbk + (n0 + fr) * sbn;
-    double c[2] = {0.0, 0.0};
-#pragma unroll 8
-    for (int k0 = 0; k0 < s; k0 += 4) cd_dmma(c, Ap[k0 * sak], Bp[k0 * sbk]);
-    double* cp = C + p * spc + (i0 + fr) * sci + (n0 + 2 * fk) * scn;
-    cp[0] = __dmul_rn(alpha, c[0]);
-    cp[scn] = __dmul_rn(alpha, c[1]);
+  const int s = 8 << lg, tmask = (1 << lg) - 1;          // tiles per side = 1 << lg
+  const int total = nprob << (2 * lg);
+  auto setup = [&](int t, const double*& Ap, const double*& Bp, double*& Cp) {
+    const int p = t >> (2 * lg), tt = t & ((1 << (2 * lg)) - 1);
+    const int i0 = (tt >> lg) * 8, n0 = (tt & tmask) * 8;
+    Ap = A + p * spa + (i0 + fr) * sai + fk * sak;
+    Bp = B + p * spb + fk * sbk + (n0 + fr) * sbn;
+    Cp = C + p * spc + (i0 + fr) * sci + (n0 + 2 * fk) * scn;
+  };
+  for (int t = warp; t < total; t += 2 * (CTH / 32)) {
+    const int t2 = t + CTH / 32;
+    const bool two = t2 < total;
+    const double *A0, *B0, *A1, *B1;
+    double *C0, *C1;
+    setup(t, A0, B0, C0);
+    setup(two ? t2 : t, A1, B1, C1);
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll 4
+    for (int k0 = 0; k0 < s; k0 += 4) {
+      const double a0 = A0[k0 * sak], b0 = B0[k0 * sbk];
+      const double a1 = A1[k0 * sak], b1 = B1[k0 * sbk];
+      cd_dmma(c0, a0, b0);
+      cd_dmma(c1, a1, b1);
+    }
+    C0[0] = __dmul_rn(alpha, c0[0]);
+    C0[scn] = __dmul_rn(alpha, c0[1]);
+    if (two) {
+      C1[0] = __dmul_rn(alpha, c1[0]);
+      C1[scn] = __dmul_rn(alpha, c1[1]);
+    }
   }
 }
 
@@ -234,15 +253,15 @@ __device__ __forceinline__ void chol_factor_tile(CholSmem& sm, int tid, int32_t*
   __syncthreads();
   if (tr) tr[11] = clock64();
   // doubling: inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]]
-  for (int s = 8; s < CT; s *= 2) {
-    const int pairs = CT / (2 * s);
+  for (int lg = 0; lg < 3; ++lg) {
+    const int s = 8 << lg, pairs = CT / (2 * s);
     // T_p = L21 X11
-    smem_mm_batched(sm.f.T, CP, 1, s * CP, M + s, 1, CP, 2 * s * (CP + 1), X, CP, 1, 2 * s * (CP + 1), s, pairs, 1.0,
+    smem_mm_batched(sm.f.T, CP, 1, s * CP, M + s, 1, CP, 2 * s * (CP + 1), X, CP, 1, 2 * s * (CP + 1), lg, pairs, 1.0,
                     warp, lane);
     __syncthreads();
     // X21 = -X22 T_p
     smem_mm_batched(X + s * CP, CP, 1, 2 * s * (CP + 1), X + s * (CP + 1), CP, 1, 2 * s * (CP + 1), sm.f.T, CP, 1, s * CP,
-                    s, pairs, -1.0, warp, lane);
+                    lg, pairs, -1.0, warp, lane);
     __syncthreads();
   }
   if (tr) tr[12] = clock64();
