@@ -100,6 +100,12 @@ int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const slk_codeboo
  * default (exact threshold tables for uniform codebooks of <= 16 entries; identical results). */
 int slk_debug_scale_search_direct(int on);
 
+/* Host-only (no CUDA call): the exact breakpoints of a uniform codebook of <= 16 entries in the
+ * scaled domain, X[k] = min{x : quantize_index(x) >= k} (codebook.py:43-54), k = 1..size-1, +inf
+ * elsewhere; out16_host is a HOST array of 16 floats.  The scale-search tables and the sweep's
+ * leaf round through these (idx >= k <=> x >= X[k]). */
+int slk_codebook_breaks_host(const slk_codebook* cb_host, float* out16_host);
+
 /* ---- K6: H-weighted error ---------------------------------------------------
  * channelwise_error  ((W-Q) @ H * (W-Q)).sum(-1)            obq.py:89-95
  * _compute_mse with a 2-D H                                 scaling.py:91-95

@@ -76,6 +76,7 @@ SIGNATURES = {
     "slk_chol_factor_ws_bytes": (_SZ, [_I64]),
     "slk_chol_factor_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
     "slk_gptq_sweep_r_ws_bytes": (_SZ, [_I64, _I64]),
+    "slk_codebook_breaks_host": (_INT, [_CB, _P]),
     "slk_debug_chol_trace": (_INT, [_P]),
     "slk_debug_sweep_trace": (_INT, [_P]),
     "slk_debug_scale_search_direct": (_INT, [_INT]),

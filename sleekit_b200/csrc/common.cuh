@@ -241,6 +241,44 @@ __device__ __forceinline__ float uniform_value_fast(const DevGrid<float>& g, con
 }
 
 // ---------------------------------------------------------------------------
+// Breakpoints of a uniform codebook in the scaled domain: X[k] = min{x : slot(x) >= k} for
+// slot(x) = clip(rint((x - zero) / step), 0, C-1)   (codebook.py:60-62), k = 1..C-1, +inf beyond.
+// slot() is a composition of monotone correctly rounded fp32 operations, so X[k] is found exactly
+// by bisection over the ordered fp32 values.  It runs on the HOST, once per call (15 x 32 steps):
+// IEEE fp32 subtract / divide / nearbyint there give the same results as the device chain (whose
+// reciprocal-based divide is the correctly rounded quotient), and the table travels to the
+// kernels by value.
+// ---------------------------------------------------------------------------
+struct GridBreaks { float X[16]; };
+
+static inline GridBreaks make_breaks(const slk_codebook* cb) {
+  GridBreaks b;
+  const float inf = __builtin_inff();
+  for (int k = 0; k < 16; ++k) b.X[k] = inf;
+  if (cb->kind != 0 || cb->size > 16) return b;
+  const volatile float zero = (float)cb->lo, step = (float)cb->step;
+  const float top = (float)(cb->size - 1);
+  auto ord = [](float x) { int32_t i; __builtin_memcpy(&i, &x, 4); return (int64_t)(i >= 0 ? i : (int32_t)(0x80000000u - (uint32_t)i)); };
+  auto unord = [](int64_t o) { int32_t i = (int32_t)o; i = i >= 0 ? i : (int32_t)(0x80000000u - (uint32_t)i); float x; __builtin_memcpy(&x, &i, 4); return x; };
+  auto slot = [&](float x) {
+    volatile float d = x - zero;          // volatile: one rounding per operation, no contraction
+    volatile float t = d / step;
+    float kk = __builtin_nearbyintf(t);
+    kk = kk < 0.0f ? 0.0f : kk;
+    return kk > top ? top : kk;
+  };
+  for (int k = 1; k < cb->size; ++k) {
+    int64_t lo = ord(-3.402823466e+38f), hi = ord(3.402823466e+38f);   // slots 0 and C-1
+    while (hi - lo > 1) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (slot(unord(mid)) >= (float)k) hi = mid; else lo = mid;
+    }
+    b.X[k] = unord(hi);
+  }
+  return b;
+}
+
+// ---------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------
 template <typename T>

@@ -579,6 +579,16 @@ int slk_scale_permute_cols_f32(const float* src, int64_t r, int64_t n, const int
   return SLK_OK;
 }
 
+/* host-only: the exact breakpoints the kernels use for a uniform codebook (tests) */
+int slk_codebook_breaks_host(const slk_codebook* cb, float* out16_host) {
+  int rc = check_codebook(cb);
+  if (rc) return rc;
+  SLK_REQUIRE(out16_host != nullptr, "NULL output");
+  const GridBreaks b = make_breaks(cb);
+  for (int k = 0; k < 16; ++k) out16_host[k] = b.X[k];
+  return SLK_OK;
+}
+
 int slk_mean_f32(const float* v, int64_t count, float* out, void* stream) {
   SLK_REQUIRE(v && out && count >= 1, "bad arguments");
   mean_kernel_f32<<<1, 256, 0, (cudaStream_t)stream>>>(v, count, out);

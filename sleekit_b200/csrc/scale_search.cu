@@ -93,9 +93,9 @@ struct TabSmem {
 
 template <bool HAS_H, int TAB_WPT>
 __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const float* __restrict__ w, int64_t r, int64_t n,
-                                                                       DevGrid<float> g, float cb_min, float cb_max,
-                                                                       const float* __restrict__ factors, int G,
-                                                                       const float* __restrict__ hdiag,
+                                                                       DevGrid<float> g, GridBreaks brk, float cb_min,
+                                                                       float cb_max, const float* __restrict__ factors,
+                                                                       int G, const float* __restrict__ hdiag,
                                                                        float* __restrict__ out_scale,
                                                                        float* __restrict__ out_err,
                                                                        float* __restrict__ out_init) {
@@ -106,22 +106,8 @@ __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const flo
   const float top = (float)(C - 1);
   const FastDivF fstep = make_fastdiv(g.step);
 
-  // breakpoints of the codebook in the scaled domain, once per CTA: full bisection over all floats
-  if (tid >= 1 && tid < C) {
-    const float fk = (float)tid;
-    auto slot_x = [&](float x) -> float {
-      const float d = __fsub_rn(x, g.zero);
-      float kk = rintf(fstep.ok ? fastdiv_core(d, fstep.d, fstep.y) : __fdiv_rn(d, g.step));            // codebook.py:60-62
-      kk = kk < 0.0f ? 0.0f : kk;
-      return kk > top ? top : kk;
-    };
-    long long blo = f32_ord(-3.402823466e+38f), bhi = f32_ord(3.402823466e+38f);   // slots 0 and C-1
-    while (bhi - blo > 1) {
-      const long long mid = blo + ((bhi - blo) >> 1);
-      if (slot_x(f32_unord((int)mid)) >= fk) bhi = mid; else blo = mid;
-    }
-    sm.X[tid] = f32_unord((int)bhi);
-  }
+  // breakpoints of the codebook in the scaled domain (exact; found on the host, make_breaks)
+  if (tid < TAB_MAXC) sm.X[tid] = brk.X[tid];
   __syncthreads();
 
   for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
@@ -355,6 +341,7 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
     // threshold-table form; grid: every SM holds several CTAs so that one CTA's (latency-bound) table
     // construction overlaps the others' (throughput-bound) main loops
     const int tgrid = (int)(r < (int64_t)sm_count() * 12 ? r : (int64_t)sm_count() * 12);
+    const GridBreaks brk = make_breaks(cb);
     // weights per thread and chunk: the candidate with the least padding
     int wpt = 8;
     {
@@ -367,7 +354,7 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
     }
 #define SLK_LAUNCH_TAB(HAS, WPT)                                                                                     \
     scale_search_tab_kernel<HAS, WPT><<<tgrid, TAB_THREADS, sizeof(TabSmem), st>>>(                                    \
-        w, r, n, g, cmin, cmax, factors, G, (const float*)hdiag, out_scale, out_err, out_init)
+        w, r, n, g, brk, cmin, cmax, factors, G, (const float*)hdiag, out_scale, out_err, out_init)
     if (h_dtype == 1) {
       if (wpt == 8) SLK_LAUNCH_TAB(true, 8); else if (wpt == 6) SLK_LAUNCH_TAB(true, 6); else SLK_LAUNCH_TAB(true, 4);
     } else {

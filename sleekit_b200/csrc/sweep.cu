@@ -580,35 +580,6 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
   }
 }
 
-// Breakpoints X[1..C-1] (X[k] = min{x : slot(x) >= k}, full bisection over the ordered fp32 values with
-// the reference's own op chain, codebook.py:60-62; +inf beyond) and values V[0..7] of a uniform
-// codebook of <= 8 entries; entry k of 0..7 is computed by one thread.
-__device__ __forceinline__ void codebook_xv(const DevGrid<float>& g, const FastDivF& fstep, int k, float* XV) {
-  const float top = (float)(g.size - 1);
-  float xk = __int_as_float(0x7f800000);
-  if (k >= 1 && k < g.size) {
-    auto ord = [](float x) { const int i = __float_as_int(x); return i >= 0 ? i : (int)(0x80000000u - (unsigned)i); };
-    auto unord = [](int o) { return __int_as_float(o >= 0 ? o : (int)(0x80000000u - (unsigned)o)); };
-    long long blo = ord(-3.402823466e+38f), bhi = ord(3.402823466e+38f);
-    while (bhi - blo > 1) {
-      const long long mid = blo + ((bhi - blo) >> 1);
-      float kk = rintf(fastdiv_core(__fsub_rn(unord((int)mid), g.zero), fstep.d, fstep.y));
-      kk = kk < 0.0f ? 0.0f : kk;
-      kk = kk > top ? top : kk;
-      if (kk >= (float)k) bhi = mid; else blo = mid;
-    }
-    xk = unord((int)bhi);
-  }
-  XV[k] = xk;
-  const int kv = k < g.size ? k : g.size - 1;
-  XV[8 + k] = __fadd_rn(__fmul_rn((float)kv, g.step), g.zero);                 // codebook.py:63-64
-}
-
-__global__ void __launch_bounds__(32) codebook_xv_kernel(DevGrid<float> g, float* __restrict__ XV) {
-  const FastDivF fstep = make_fastdiv(g.step);
-  if (threadIdx.x < 8) codebook_xv(g, fstep, threadIdx.x, XV);
-}
-
 constexpr int MB_COLS = 256;
 constexpr int MB_PITCH = MB_COLS + 4;
 __device__ long long* g_sweep_trace = nullptr;   // development aid: per-block phase clocks of CTA 0
@@ -636,7 +607,7 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
                                                          const float* __restrict__ Rf, const float* __restrict__ Ud,
                                                          DevGrid<float> g, int64_t c0, int64_t c1,
                                                          const float* __restrict__ Pacc, float* __restrict__ Dhi,
-                                                         float* __restrict__ Dlo, const float* __restrict__ XVg) {
+                                                         float* __restrict__ Dlo, GridBreaks brk) {
   typedef MacroSmem<R> SM;
   constexpr int KG = SM::KG;
   extern __shared__ __align__(16) unsigned char macro_raw[];
@@ -688,12 +659,12 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
   //       columns of D that already exist (look-ahead), so only 32 k-steps remain on the chain
   for (int t = tid; t < SM::KGH * R * 33; t += FT) (&sm.red2[0][0][0])[t] = 0.0f;
   const bool tree = fastq && g.size <= 8;
-  if (tree && tid >= FT - 16) {
-    // breakpoints and values of the codebook: computed once per sweep (codebook_xv_kernel) when a
-    // workspace is available, else here
-    const int k = tid - (FT - 16);
-    if (XVg) sm.XV[k] = __ldg(XVg + k);
-    else if (k < 8) codebook_xv(g, fstep, k, sm.XV);
+  if (tree && tid >= FT - 8) {
+    // breakpoints (exact; found on the host, make_breaks) and values (codebook.py:63-64) of the codebook
+    const int k = tid - (FT - 8);
+    sm.XV[k] = brk.X[k];
+    const int kv = k < g.size ? k : g.size - 1;
+    sm.XV[8 + k] = __fadd_rn(__fmul_rn((float)kv, g.step), g.zero);
   }
   Pre cur, nxt;
   fetch(c0, cur);
@@ -831,7 +802,7 @@ extern "C" int slk_debug_sweep_trace(void* buf) {
 template <int R>
 static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
                         cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo,
-                        const float* xv) {
+                        const GridBreaks& xv) {
   auto kern = sweep_macro_kernel<R>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -885,7 +856,7 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
     want_env = ev ? atoll(ev) : 0;
   }
   const int64_t want = want_env > 0 ? want_env : ((int64_t)sm_count() / 48) * 16;   // 48 on a B200: 768 rows -> 16 per CTA
-  const float* xv = nullptr;
+  const GridBreaks xv = make_breaks(cb);        // codebook breakpoints for the leaf's compare tree
   auto fused = [&](int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) -> int {
     if (n % 4 == 0 && c1 - c0 <= MB_COLS && (((uintptr_t)r32) & 15) == 0) {
       if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
@@ -901,12 +872,6 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
   float* pacc = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   float* dhi = pacc + (size_t)r * n;
   float* dlo = dhi + (size_t)r * n;
-  if (g.kind == 0 && g.size <= 8) {             // codebook breakpoints for the leaf's compare tree, once per sweep
-    float* xvw = dlo + (size_t)r * n;
-    codebook_xv_kernel<<<1, 32, 0, st>>>(g, xvw);
-    SLK_LAUNCH_CHECK();
-    xv = xvw;
-  }
   SLK_CUDA(cudaMemsetAsync(pacc, 0, (size_t)r * n * sizeof(float), st));
   auto push = [&](int64_t k0, int64_t k1, int64_t c0, int64_t c1) -> int {   // Pacc[:, c0:c1] += D[:, k0:k1] R[k0:k1, c0:c1]
     TcParams p;

@@ -131,3 +131,37 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     text = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_codebook_breakpoints_are_exact_on_the_host():
+    """The kernels round through X[k] = min{x : index(x) >= k}, found on the host by bisection with
+    IEEE fp32 ops; check against the oracle's quantize_index (codebook.py:43-54) on both sides of
+    every breakpoint and on random values -- pure host code, no CUDA call."""
+    import ctypes as C
+
+    import numpy as np
+
+    from oracle import sleekit_oracle as orc
+    from sleekit_b200 import _lib
+    from sleekit_b200._lib import SlkCodebook
+
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for c, lo, hi in [(2, -1, 1), (3, -1, 1), (4, -1, 1), (8, -1, 1), (16, -1, 1), (9, -2, 2), (7, -0.5, 3.0)]:
+        step = (hi - lo) / (c - 1)
+        cb = SlkCodebook(0, c, lo, hi, step, None, None)
+        out = (C.c_float * 16)()
+        assert lib.slk_codebook_breaks_host(C.byref(cb), out) == 0
+        X = np.array(out[:], dtype=np.float32)
+        grid = orc.UniformGrid(c, lo, hi)
+        assert np.all(np.isinf(X[c:])) and np.isinf(X[0])
+        assert np.all(np.diff(X[1:c]) > 0)
+        for k in range(1, c):
+            at = X[k]
+            below = np.nextafter(at, np.float32(-np.inf))
+            assert grid.index(np.array([at], np.float32))[0] >= k
+            assert grid.index(np.array([below], np.float32))[0] < k
+        x = (rng.standard_normal(200000) * (hi - lo)).astype(np.float32)
+        want = grid.index(x).astype(np.int64)
+        got = (x[:, None] >= X[None, 1:c]).sum(axis=1)
+        np.testing.assert_array_equal(got, want)
