@@ -159,6 +159,11 @@ int slk_order_keys(const float* h, int64_t n, const float* dampval, const float*
                    double* keys, void* stream);
 /* stable ascending argsort of fp64 keys -> int64 order        obq.py:64,69,81 */
 int slk_argsort_f64(const double* keys, int64_t n, int64_t* order, void* stream);
+/* act_order = "pivot": greedy pivoted-Cholesky ordering of an fp64 matrix    obq.py:140-166
+ * (same fp64 operations on the same operands as the reference, hence the same order). */
+size_t slk_pivot_order_ws_bytes(int64_t n);
+int slk_pivot_order_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, int64_t* order,
+                        void* stream);
 /* dst[:, j] = src[:, idx[j]] (gather) or dst[:, idx[j]] = src[:, j] (scatter)  obq.py:202,212-213 */
 int slk_permute_cols_f32(const float* src, int64_t r, int64_t n, const int64_t* idx, int scatter,
                          float* dst, void* stream);

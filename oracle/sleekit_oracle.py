@@ -201,6 +201,22 @@ def inverse_upper_factor(H):
     return np.ascontiguousarray(low_inv[::-1, ::-1])
 
 
+def greedy_pivot_order(H):
+    """Greedy pivoted-Cholesky ordering: at every step the remaining variable with the largest
+    conditional variance comes next (ref: obq.py:140-166)."""
+    n = H.shape[0]
+    M = np.array(H, dtype=np.float64, copy=True)
+    perm = np.arange(n)
+    for step in range(n):
+        best = step + int(np.argmax(np.abs(M.diagonal()[step:])))
+        M[[step, best], :] = M[[best, step], :]
+        M[:, [step, best]] = M[:, [best, step]]
+        perm[[step, best]] = perm[[best, step]]
+        row = M[step, step + 1:]
+        M[step + 1:, step + 1:] -= np.outer(row, row) / M[step, step]
+    return perm
+
+
 def column_order(W, H, grid, rule):
     """ref: obq.py:58-86 (the four rules the hot path uses)."""
     d = H.diagonal()
@@ -216,6 +232,8 @@ def column_order(W, H, grid, rule):
         return np.linalg.inv(H).diagonal().argsort()
     if rule == "combined_diag":
         return (-d / np.linalg.inv(H).diagonal()).argsort()
+    if rule == "pivot":
+        return greedy_pivot_order(H)
     raise RuntimeError(f"Invalid act_order value {rule}")
 
 

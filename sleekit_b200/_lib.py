@@ -68,6 +68,8 @@ SIGNATURES = {
     "slk_col_resid_sums_f32": (_INT, [_P, _I64, _I64, _CB, _INT, _P, _P]),
     "slk_order_keys": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "slk_argsort_f64": (_INT, [_P, _I64, _P, _P]),
+    "slk_pivot_order_ws_bytes": (_SZ, [_I64]),
+    "slk_pivot_order_f64": (_INT, [_P, _I64, _P, _SZ, _P, _P]),
     "slk_permute_cols_f32": (_INT, [_P, _I64, _I64, _P, _INT, _P, _P]),
     "slk_scale_permute_cols_f32": (_INT, [_P, _I64, _I64, _P, _P, _INT, _P, _P]),
     "slk_hinv_ws_bytes": (_SZ, [_I64]),

@@ -375,6 +375,75 @@ __global__ void __launch_bounds__(256) argsort_rank_kernel(const double* __restr
   if (lane == 0) order[cnt] = j;
 }
 
+// ---------------------------------------------------------------------------
+// act_order = "pivot": greedy pivoted-Cholesky ordering                         obq.py:140-166
+// The reference swaps rows and columns of a working copy; here the matrix stays in place and only
+// the order array is swapped: position p holds index order[p], the pivot is the first position
+// p >= k with the largest |L[order[p]][order[p]]| (np.argmax), and the trailing update
+//     L[i][j] -= (L[piv][i] * L[piv][j]) / L[piv][piv]        (obq.py:160-161, three roundings)
+// runs over the still-active indices.  Same fp64 operations on the same operands as numpy, hence
+// the same order.  Two launches per step (select: one CTA; update: the grid).
+// ---------------------------------------------------------------------------
+struct PivotState { int piv; int pad; double lpp; };
+
+__global__ void __launch_bounds__(256) pivot_init_kernel(const double* __restrict__ h, int64_t n, double* __restrict__ L,
+                                                         int64_t* __restrict__ order, int* __restrict__ active) {
+  const int64_t total = n * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    L[t] = h[t];
+    if (t < n) { order[t] = t; active[t] = 1; }
+  }
+}
+
+__global__ void __launch_bounds__(1024) pivot_select_kernel(const double* __restrict__ L, int64_t n, int64_t k,
+                                                            int64_t* __restrict__ order, int* __restrict__ active,
+                                                            PivotState* __restrict__ stp) {
+  __shared__ double bv[32];
+  __shared__ int64_t bp[32];
+  double best = -1.0;
+  int64_t bpos = INT64_MAX;
+  for (int64_t p = k + threadIdx.x; p < n; p += blockDim.x) {
+    const int64_t i = order[p];
+    const double v = fabs(L[i * n + i]);
+    if (bpos == INT64_MAX || v > best) { best = v; bpos = p; }     // p ascends: the first maximum stays
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long op = __shfl_xor_sync(0xffffffffu, (long long)bpos, o);
+    if (op != INT64_MAX && (bpos == INT64_MAX || ov > best || (ov == best && op < bpos))) { best = ov; bpos = op; }
+  }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bp[threadIdx.x >> 5] = bpos; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (bp[w] != INT64_MAX && (bpos == INT64_MAX || bv[w] > best || (bv[w] == best && bp[w] < bpos))) { best = bv[w]; bpos = bp[w]; }
+    const int64_t piv = order[bpos];
+    order[bpos] = order[k];                      // obq.py:157
+    order[k] = piv;
+    active[piv] = 0;
+    stp->piv = (int)piv;
+    stp->lpp = L[piv * n + piv];
+  }
+}
+
+__global__ void __launch_bounds__(256) pivot_update_kernel(double* __restrict__ L, int64_t n, const int* __restrict__ active,
+                                                           const PivotState* __restrict__ stp) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t piv = stp->piv;
+  const double lpp = stp->lpp;
+  const bool jact = j < n && active[j];
+  const double bj = jact ? L[piv * n + j] : 0.0;
+  const int64_t i0 = (int64_t)blockIdx.y * 16;
+  for (int64_t i = i0; i < i0 + 16 && i < n; ++i) {
+    if (!active[i] || !jact) continue;
+    const double bi = L[piv * n + i];
+    const double t = __ddiv_rn(__dmul_rn(bi, bj), lpp);                      // np.outer(b, b) / L[k, k]
+    L[i * n + j] = __dsub_rn(L[i * n + j], t);
+  }
+}
+
 // Exhaustive check of fastdiv_core against the IEEE divide: for each divisor, all 2^32 dividends.
 // Counted: results that differ (sign of zero ignored) while the true quotient is zero or has an
 // exponent in [-100, 100].  (Below 2^-102 the residual a - d*q is not representable and the
@@ -576,6 +645,31 @@ int slk_scale_permute_cols_f32(const float* src, int64_t r, int64_t n, const int
   SLK_REQUIRE(src && s && dst && src != dst, "bad pointers");
   scale_permute_cols_kernel<<<stream_grid(r * n, 256), 256, 0, (cudaStream_t)stream>>>(src, r, n, idx, s, scatter, dst);
   SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+size_t slk_pivot_order_ws_bytes(int64_t n) {
+  return (size_t)n * n * sizeof(double) + (size_t)n * sizeof(int) + sizeof(PivotState) + 512;
+}
+
+int slk_pivot_order_f64(const double* h, int64_t n, void* ws, size_t ws_bytes, int64_t* order, void* stream) {
+  SLK_REQUIRE(h && order && n >= 1, "bad arguments");
+  SLK_REQUIRE(ws && ws_bytes >= slk_pivot_order_ws_bytes(n), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* L = (double*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  PivotState* stp = (PivotState*)(L + n * n);
+  int* active = (int*)(stp + 1);
+  pivot_init_kernel<<<stream_grid(n * n, 256), 256, 0, st>>>(h, n, L, order, active);
+  SLK_LAUNCH_CHECK();
+  const dim3 ugrid((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n, 16));
+  for (int64_t k = 0; k < n; ++k) {
+    pivot_select_kernel<<<1, 1024, 0, st>>>(L, n, k, order, active, stp);
+    SLK_LAUNCH_CHECK();
+    if (k + 1 < n) {
+      pivot_update_kernel<<<ugrid, 256, 0, st>>>(L, n, active, stp);
+      SLK_LAUNCH_CHECK();
+    }
+  }
   return SLK_OK;
 }
 

@@ -91,8 +91,7 @@ def _device_order(Wd, Hd, quantizer, act_order, diag64=None):
         inv_diag = (u64 * u64).sum(dim=0)  # diag(U^T U)
         keys = inv_diag if act_order == "inv_diag" else -d / inv_diag
     elif act_order == "pivot":
-        raise NotImplementedError(
-            "act_order='pivot' (obq.py:140-166) is outside the accelerated hot path (SURVEY 8f-4)")
+        return ops.pivot_order(Hd.to(torch.float64).contiguous())       # obq.py:140-166
     else:
         raise RuntimeError(f"Invalid act_order value {act_order}")
     return ops.argsort(keys.contiguous())

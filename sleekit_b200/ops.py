@@ -354,6 +354,17 @@ def argsort(keys):
     return order
 
 
+def pivot_order(h64):
+    """Greedy pivoted-Cholesky ordering of an fp64 matrix (obq.py:140-166); int64 order."""
+    _chk(h64, torch.float64)
+    n = h64.shape[0]
+    nbytes = _lib.load().slk_pivot_order_ws_bytes(n)
+    ws = _ws(nbytes, h64.device)
+    order = torch.empty(n, dtype=torch.int64, device=h64.device)
+    _lib.call("slk_pivot_order_f64", _ptr(h64), n, _ptr(ws), nbytes, _ptr(order), _stream())
+    return order
+
+
 @_timed("permute_cols")
 def permute_cols(src, idx, scatter=False):
     _chk(src, torch.float32)

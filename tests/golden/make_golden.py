@@ -146,6 +146,20 @@ def factor_and_sweep():
     np.savez_compressed(os.path.join(OUT, "sweep.npz"), **out)
 
 
+def pivot_ordering():
+    """act_order = "pivot" (obq.py:140-166): the order itself and GPTQ with it."""
+    out = {}
+    W, H, m, _ = layer(31, 24, 96)
+    cb = UniformCodebook(8, -1, 1)
+    sc = rsc.compute_non_saturating_scaling(W, cb, 0)
+    Ws = rsc.apply_scaling(W, sc, 0).astype(np.float32)
+    Hd = H + 0.01 * H.diagonal().mean() * np.eye(H.shape[0])
+    out.update(W=W, H=H, Ws=Ws, Hd=Hd)
+    out["order_pivot"] = robq.compute_hessian_order(Ws, Hd, cb, "pivot")
+    out["gptq_pivot"] = robq.quantize_opt(Ws, H, cb, act_order="pivot", damp=0.01)
+    np.savez_compressed(os.path.join(OUT, "pivot.npz"), **out)
+
+
 def local_search():
     out = {}
     W, H, m, X = layer(31, 12, 64)
@@ -202,6 +216,10 @@ def statistics():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pivot":      # added later: only this fixture
+        pivot_ordering()
+        print("golden pivot vector written to", OUT)
+        sys.exit(0)
     rounding()
     scales()
     factor_and_sweep()

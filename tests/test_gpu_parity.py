@@ -333,6 +333,20 @@ def test_ordering_vs_golden(slk):
                                       orc.column_order(g["Ws"], g["Hd"], orc.UniformGrid(8, -1, 1), rule))
 
 
+def test_pivot_ordering_vs_golden_and_oracle(slk):
+    """act_order = "pivot": the device ordering performs the reference's fp64 operations on the same
+    operands (obq.py:140-166), so the permutation is the reference's; GPTQ with it agrees as usual."""
+    g = load_golden("pivot")
+    cb, grid = slk.codebook.UniformCodebook(8, -1, 1), orc.UniformGrid(8, -1, 1)
+    np.testing.assert_array_equal(slk.obq.compute_hessian_order(g["Ws"], g["Hd"], cb, "pivot"), g["order_pivot"])
+    got = slk.obq.quantize_opt(g["Ws"], g["H"], cb, act_order="pivot", damp=0.01)
+    assert agree(got, g["gptq_pivot"]) >= 0.995
+    _, H, _ = wl.synthetic_layer(4, 300, 17, samples=1024)
+    Hd = H.astype(np.float64) + 0.01 * H.diagonal().mean() * np.eye(300)
+    W = np.zeros((2, 300), np.float32)
+    np.testing.assert_array_equal(slk.obq.compute_hessian_order(W, Hd, cb, "pivot"), orc.greedy_pivot_order(Hd))
+
+
 # ---------------------------------------------------------------------------
 # K3 sweep / GPTQ
 # ---------------------------------------------------------------------------

@@ -183,3 +183,11 @@ def test_synthetic_layer_is_deterministic():
         np.testing.assert_array_equal(x, y)
     assert len(wl.layer_shapes("opt-125m")) == 72
     assert sum(r * n for r, n in wl.layer_shapes("opt-125m")) == 84934656
+
+
+def test_pivot_ordering_vs_golden():
+    """act_order = "pivot" (obq.py:140-166): the oracle's greedy pivoted-Cholesky order and GPTQ with it."""
+    g = load_golden("pivot")
+    grid = orc.UniformGrid(8, -1, 1)
+    np.testing.assert_array_equal(orc.column_order(g["Ws"], g["Hd"], grid, "pivot"), g["order_pivot"])
+    np.testing.assert_array_equal(orc.gptq(g["Ws"], g["H"], grid, rule="pivot", damp=0.01), g["gptq_pivot"])
