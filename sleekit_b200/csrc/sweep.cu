@@ -1,11 +1,18 @@
 // K3: the GPTQ / OBQ column sweep.
 //   _quantize_opt_core   (leaf, <= 32 columns)      obq.py:106-118
 //   _quantize_opt_block  (8-ary lazy batching)      obq.py:121-137
-// Leaf: one thread per row with its 32 columns in registers.  Column i is quantised, its scaled
-// residual r = (w - q) / U[i,i] is formed in fp64 (as numpy does: the divisor is an fp64 scalar)
-// and columns j > i take q_j <- fp32(fp64(q_j) - r * U[i,j]) -- the exact op sequence of
-// obq.py:114-118, so given the same fp64 U a leaf is bit-identical to the reference.  Trailing updates Q[:, b:end] -= E[:, a:b] @ U[a:b, b:end] are fp32 GEMMs
-// with exact-product fmaf accumulation on the fp32 rounding of U (parity-safe).
+// Two entry points:
+//  * slk_gptq_sweep_r_f32 (what quantize_opt / compute_obq_scaling / Sleekit.quantize run): the
+//    sweep from the Cholesky factor R (H_opt = R R^T, chol_dag.cu) -- macro blocks of 256 columns
+//    swept by sweep_macro_kernel (shared-memory resident, four lanes per row, look-ahead product),
+//    one tcgen05 GEMM per macro block (two levels for n > 4096) pushing D = W - Q to the later
+//    columns.  All fp32 (parity-safe).
+//  * slk_gptq_sweep_f32 (the public _quantize_opt_core/_block with a given Hinv): the sweep from
+//    the inverse factor U; exact_leaf = 1 reproduces the reference's mixed fp64/fp32 leaf bit for
+//    bit: column i is quantised, its scaled residual r = (w - q) / U[i,i] is formed in fp64 (as
+//    numpy does: the divisor is an fp64 scalar) and columns j > i take
+//    q_j <- fp32(fp64(q_j) - r * U[i,j]) -- the op sequence of obq.py:114-118; trailing updates
+//    Q[:, b:end] -= E[:, a:b] @ U[a:b, b:end] are fp32 GEMMs with exact-product fmaf accumulation.
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 
