@@ -73,6 +73,13 @@ __global__ void __launch_bounds__(256) round_f32_vec4_kernel(const float4* __res
                                                              float4* __restrict__ out_val,
                                                              uint32_t* __restrict__ out_idx8) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // the divide by the codebook step goes through the exact reciprocal scheme (common.cuh: the
+  // correctly rounded quotient, 5 FMA-pipe operations instead of the ~20 of the IEEE divide
+  // sequence), which is what keeps this kernel on the HBM roofline instead of the ALU
+  const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
+  const float slo = mode == SLK_UP ? 1.0f : 0.0f;
+  const float shi = (float)(g.size - (mode == SLK_DOWN ? 2 : 1));
+  const float shift = mode == SLK_UP ? 1.0f : (mode == SLK_DOWN ? -1.0f : 0.0f);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     float4 v = __ldcs(x + i);
     float in[4] = {v.x, v.y, v.z, v.w};
@@ -80,7 +87,15 @@ __global__ void __launch_bounds__(256) round_f32_vec4_kernel(const float4* __res
     uint32_t packed = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (g.kind == 0) {
+      if (g.kind == 0 && fstep.ok) {
+        float t = fastdiv_core(__fsub_rn(in[k], g.zero), fstep.d, fstep.y);     // codebook.py:47,60,71,83
+        if (mode != SLK_NEAREST) t = __fadd_rn(t, shift);                        // codebook.py:73,85
+        float s = rintf(t);
+        s = s < slo ? slo : s;      // np.clip: NaN propagates, like the comparisons here
+        s = s > shi ? shi : s;
+        val[k] = uniform_value_of_slot<float>(g, s);
+        packed |= ((uint32_t)s & 0xffu) << (8 * k);
+      } else if (g.kind == 0) {
         float s = uniform_slot<float>(g, in[k], mode);
         val[k] = uniform_value_of_slot<float>(g, s);
         packed |= ((uint32_t)s & 0xffu) << (8 * k);

@@ -104,6 +104,17 @@ def main():
             Hd = torch.randn(n, n, device=dev)
             t = timeit(lambda: ops.hweighted_error(Wd, Qd, Hd))
             print(f"[{r}x{n}] hweighted_error {t:9.1f} us  {2 * r * n * n / t / 1e6:8.2f} TFLOP/s")
+    if what in ("round", "all"):
+        for count in (1 << 24, 1 << 27):
+            x = torch.randn(count, device=dev) * 0.6
+            t = timeit(lambda: ops.round_to_codebook(x, cb)[0])
+            print(f"round value  n={count}: {t:9.1f} us  {8 * count / t / 1e3:8.1f} GB/s (4 B read + 4 B written per weight)")
+            t = timeit(lambda: ops.round_to_codebook(x, cb, want_val=False, want_idx=True)[1])
+            print(f"round index  n={count}: {t:9.1f} us  {5 * count / t / 1e3:8.1f} GB/s (4 B read + 1 B written per weight)")
+            w2 = x.view(-1, 4096)
+            s_ = torch.rand(w2.shape[0], device=dev) + 0.5
+            t = timeit(lambda: ops.scale_rows(w2, s_, 0))
+            print(f"scale rows   n={count}: {t:9.1f} us  {8 * count / t / 1e3:8.1f} GB/s")
     if what in ("xtx", "all"):
         for S, n in ((2048, 768), (2048, 3072), (8192, 4096)):
             X = torch.randn(S, n, device=dev)
