@@ -364,6 +364,16 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * weights / (ms_per_step * 1e-3)
     layer_err = float(errs.mean().item())
+    # the timed pass takes each layer's error from the sweep's residuals (sum E^2 - damp * sum D^2,
+    # obq.gptq_device); check it here, untimed, against the explicit ((W-Q) H (W-Q)^T) product (K6)
+    errs_fused = errs.clone()
+    errs_k6 = torch.zeros_like(errs)
+    obq.USE_SWEEP_ERROR = False
+    serial(Wd, Hd, errs_out=errs_k6, keep_outputs=False)
+    obq.USE_SWEEP_ERROR = True
+    torch.cuda.synchronize()
+    err_check = {"max_rel_diff_vs_product": float(((errs_fused - errs_k6).abs() / errs_k6.abs()).max().item()),
+                 "layers": L, "note": "layer error from the sweep residuals vs the explicit K6 product, per layer"}
 
     # ---- end to end with HOST buffers: H2D and D2H inside the timed region -----------------------
     # (a) the layer-set plan: inputs in page-locked host memory, every layer a graph branch
@@ -514,6 +524,7 @@ def run_ours(args):
                    "l2": "inputs (W+H ~0.93 GB per rank) are larger than the 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "e2e_numpy_api": e2e_numpy, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "layer_error_mean": layer_err,
+        "layer_error_check": err_check,
         "serial_phases_ms_per_step": {k: round(v[0], 3) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
         "xtx": {"tflops": xtx_flop / (xtx_ms * 1e-3) / 1e12 if xtx_ms else None, "ms_total": xtx_ms,
                 "note": ("K1 X^T X over the 72 calibration matrices (S=2048), algorithmic 2*S*n^2 flop; tcgen05 3xTF32, "

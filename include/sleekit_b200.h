@@ -228,6 +228,19 @@ size_t slk_gptq_sweep_r_ws_bytes(int64_t r, int64_t n);
 int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32,
                          const float* rt_hi, const float* rt_lo, const float* ud32,
                          const slk_codebook* cb_host, void* ws, size_t ws_bytes, void* stream);
+/* The same sweep, also returning err_sums [r, 2] = per row (sum_i E_i^2, sum_i (W-Q)_i^2), E_i =
+ * obq.py:114's scaled residual.  Since W - Q = E U and U H_opt U^T = I, (W-Q) H_opt (W-Q)^T =
+ * sum E^2 exactly, so channelwise_error (obq.py:89-95) under the undamped H the factor came from is
+ * sum E^2 - damp_abs * sum (W-Q)^2: the layer error falls out of the sweep without the 2 r n^2
+ * product.  slk_sweep_error_f32 finishes it: rows_out[row] = row_scale[row]^2 * (that)  (the error
+ * of the de-scaled weights; row_scale may be NULL), mean_out = their mean (quantization_error,
+ * obq.py:98-103); damp_abs is the device scalar of slk_damp_value_f32 (NULL: 0). */
+int slk_gptq_sweep_r_err_f32(float* q, float* d, int64_t r, int64_t n, const float* r32,
+                             const float* rt_hi, const float* rt_lo, const float* ud32,
+                             const slk_codebook* cb_host, void* ws, size_t ws_bytes,
+                             float* err_sums, void* stream);
+int slk_sweep_error_f32(const float* err_sums, const float* row_scale, const float* damp_abs,
+                        int64_t r, float* rows_out, float* mean_out, void* stream);
 
 /* ---- K7: best-first local search ------------------------------------------------
  * quantize_local_search / LocalSearchQuantizer                obq.py:234-358

@@ -124,7 +124,8 @@ template <int WIN>
 __device__ __forceinline__ void leaf_phase32(float (&q)[32], const LeafShared32& sh, int i0, int width,
                                              const DevGrid<float>& g, const FastDivF& fstep, bool fastq,
                                              float* __restrict__ qrow, float* __restrict__ erow,
-                                             const float* __restrict__ w0 = nullptr, float* dsm = nullptr) {
+                                             const float* __restrict__ w0 = nullptr, float* dsm = nullptr,
+                                             float* esd = nullptr) {
 #pragma unroll 1
   for (int t = 0; t < 8; ++t) {
     const int i = i0 + t;
@@ -143,6 +144,10 @@ __device__ __forceinline__ void leaf_phase32(float (&q)[32], const LeafShared32&
     const float dv = w0 ? __fsub_rn(w0[i], qq) : res;   // R form: D = W - Q of the ORIGINAL weight
     erow[i] = dv;
     if (dsm) dsm[i] = dv;
+    if (esd) {                                         // row sums of res^2 and D^2 (error identity, below)
+      esd[0] = __fmaf_rn(res, res, esd[0]);
+      esd[1] = __fmaf_rn(dv, dv, esd[1]);
+    }
     const float* urow = &sh.U[i][i];
 #pragma unroll
     for (int j = 1; j < WIN; ++j) q[j - 1] = __fmaf_rn(-res, urow[j], q[j]);
@@ -242,7 +247,7 @@ template <int R, bool RFORM>
 __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, float* __restrict__ E, int64_t r, int64_t n,
                                                          const float* __restrict__ U, const float* __restrict__ Ud,
                                                          DevGrid<float> g, int64_t c0, int64_t c1,
-                                                         const float* __restrict__ Pacc) {
+                                                         const float* __restrict__ Pacc, float* __restrict__ Esum) {
   typedef FusedSmem<R> SM;
   constexpr int KG = SM::KG;
   constexpr int KSUP = 32 * KG;                       // k covered by one ring stage
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
   const bool aligned = (n % 4 == 0) && ((((uintptr_t)E) & 15) == 0) && ((((uintptr_t)U) & 15) == 0);
   const FastDivF fstep = make_fastdiv(g.kind == 0 ? g.step : 1.0f);
   const bool fastq = (g.kind == 0) && fstep.ok;
+  float esd[2] = {0.f, 0.f};                            // this row's sums of res^2 and D^2 (leaf threads)
 
   for (int64_t a = c0; a < c1; a += 32) {
     const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
@@ -391,18 +397,30 @@ __global__ void __launch_bounds__(FT) sweep_fused_kernel(float* __restrict__ Q, 
       float* qrow = Q + (row0 + tid) * n + a;
       float* erow = E + (row0 + tid) * n + a;
       const float* w0 = RFORM ? &sm.W0[tid][0] : nullptr;
-      leaf_phase32<32>(q, sm.leaf, 0, width, g, fstep, fastq, qrow, erow, w0);
-      leaf_phase32<24>(q, sm.leaf, 8, width, g, fstep, fastq, qrow, erow, w0);
-      leaf_phase32<16>(q, sm.leaf, 16, width, g, fstep, fastq, qrow, erow, w0);
-      leaf_phase32<8>(q, sm.leaf, 24, width, g, fstep, fastq, qrow, erow, w0);
+      float* ep = (RFORM && Esum) ? esd : nullptr;
+      leaf_phase32<32>(q, sm.leaf, 0, width, g, fstep, fastq, qrow, erow, w0, nullptr, ep);
+      leaf_phase32<24>(q, sm.leaf, 8, width, g, fstep, fastq, qrow, erow, w0, nullptr, ep);
+      leaf_phase32<16>(q, sm.leaf, 16, width, g, fstep, fastq, qrow, erow, w0, nullptr, ep);
+      leaf_phase32<8>(q, sm.leaf, 24, width, g, fstep, fastq, qrow, erow, w0, nullptr, ep);
     }
     __syncthreads();   // E of this block is visible to the whole CTA before the next block reads it
+  }
+  if (RFORM && Esum && tid < R && row0 + tid < r) {
+    // launches of one sweep follow each other on one stream and every row has one writer: plain
+    // read-modify-write, fixed order, deterministic
+    float2* p = reinterpret_cast<float2*>(Esum) + (row0 + tid);
+    float2 v = make_float2(0.f, 0.f);
+    if (c0 > 0) v = *p;
+    v.x = __fadd_rn(v.x, esd[0]);
+    v.y = __fadd_rn(v.y, esd[1]);
+    *p = v;
   }
 }
 
 template <int R, bool RFORM>
 static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u32, const float* ud, const DevGrid<float>& g,
-                        cudaStream_t st, int64_t c0 = 0, int64_t c1 = -1, const float* pacc = nullptr) {
+                        cudaStream_t st, int64_t c0 = 0, int64_t c1 = -1, const float* pacc = nullptr,
+                        float* esum = nullptr) {
   if (c1 < 0) c1 = n;
   auto kern = sweep_fused_kernel<R, RFORM>;
   static bool attr_done = false;
@@ -410,7 +428,7 @@ static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u
     SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<R>)));
     attr_done = true;
   }
-  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, ud, g, c0, c1, pacc);
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, ud, g, c0, c1, pacc, esum);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -509,9 +527,10 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
                                            const FastDivF& fstep, int width, int part, int lane, bool rowok,
                                            float* __restrict__ qrow, float* __restrict__ drow,
                                            float* __restrict__ dhi, float* __restrict__ dlo,
-                                           const float (&w0)[8], float* __restrict__ dsm,
+                                           const float (&w0)[8], float* __restrict__ dsm, float* __restrict__ esm,
                                            const float* __restrict__ XV = nullptr) {
   float X[8], V[8];
+  float se = 0.0f;
   if (MODE == 2) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { X[k] = XV[k]; V[k] = XV[8 + k]; }
@@ -547,7 +566,7 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
           qq = grid_value(g, w);
         }
         const float res = __fmul_rn(__fsub_rn(w, qq), sh.Uy[i]);
-        resv[t] = res;
+        resv[t] = (i < width) ? res : 0.0f;              // padding columns carry nothing (and add nothing to se)
         if (t < 7) {
           const float4 ua = *reinterpret_cast<const float4*>(&sh.U[i][p * 8]);
           const float4 ub = *reinterpret_cast<const float4*>(&sh.U[i][p * 8 + 4]);
@@ -574,6 +593,10 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
     const int owner_lane = (lane & ~3) | p;
 #pragma unroll
     for (int t = 0; t < 8; ++t) resv[t] = __shfl_sync(0xffffffffu, resv[t], owner_lane);
+    // error identity (slk_gptq_sweep_r_err_f32): sum of res^2, off the owner's chain -- every lane of
+    // the row holds the 8 residuals now and keeps the same running sum
+#pragma unroll
+    for (int t = 0; t < 8; ++t) se = __fmaf_rn(resv[t], resv[t], se);
     if (part > p) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
@@ -585,6 +608,7 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
       }
     }
   }
+  esm[0] = __fadd_rn(esm[0], se);                        // this lane's own shared-memory slot
 }
 
 constexpr int MB_COLS = 256;
@@ -606,6 +630,7 @@ struct MacroSmem {
   float XV[16];                             // codebook breakpoints X[0..7] (X[0] unused) and values V[0..7]
   float Qs[R][33];
   float W0[R][33];
+  float esd[NLEAF];                         // per leaf lane: running sum of res^2 of its row
   LeafShared32 leaf;
 };
 
@@ -614,7 +639,8 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
                                                          const float* __restrict__ Rf, const float* __restrict__ Ud,
                                                          DevGrid<float> g, int64_t c0, int64_t c1,
                                                          const float* __restrict__ Pacc, float* __restrict__ Dhi,
-                                                         float* __restrict__ Dlo, GridBreaks brk) {
+                                                         float* __restrict__ Dlo, GridBreaks brk,
+                                                         float* __restrict__ Esum) {
   typedef MacroSmem<R> SM;
   constexpr int KG = SM::KG;
   extern __shared__ __align__(16) unsigned char macro_raw[];
@@ -676,6 +702,7 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
   Pre cur, nxt;
   fetch(c0, cur);
   int buf = 0;
+  if (tid < SM::NLEAF) sm.esd[tid] = 0.0f;             // only ever touched by its own lane
   for (int64_t a = c0; a < c1; a += 32, buf ^= 1) {
     const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
     const int ka = (int)(a - c0);                      // columns of D that exist when this block starts
@@ -764,9 +791,9 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
       float* dsm = &sm.Dm[lr][ka];
       float* dhi = Dhi ? Dhi + (row0 + lr) * n + a : nullptr;
       float* dlo = Dhi ? Dlo + (row0 + lr) * n + a : nullptr;
-      if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, sm.XV);
-      else if (fastq) leaf_rows4<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
-      else leaf_rows4<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm);
+      if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid], sm.XV);
+      else if (fastq) leaf_rows4<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
+      else leaf_rows4<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
     } else if (has_next) {
       // ---- (3b) look-ahead: D[:, c0:a] R[c0:a, J+1] on the threads the leaf does not use -----------
       const int h = tid - SM::NLEAF;
@@ -798,6 +825,36 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
     if (tr) tr[5] = clock64();
     // the barrier at the top of the next iteration orders Dm / Qs / leaf / red2 reuse
   }
+  if (Esum) {
+    // sum of res^2: lane 0 of each row's four leaf lanes holds it.  sum of D^2: the macro block's D is
+    // still in shared memory -- FT / R threads per row, fixed-order shuffle tree.  One writer per row
+    // and value; the macro-block launches of a sweep follow each other on one stream, so a plain
+    // read-modify-write is deterministic.
+    __syncthreads();
+    if (tid < SM::NLEAF && (tid & 3) == 0) {
+      const int64_t row = row0 + (tid >> 2);
+      if (row < r) {
+        float* p = Esum + 2 * row;
+        const float prev = c0 > 0 ? *p : 0.0f;
+        *p = __fadd_rn(prev, sm.esd[tid]);
+      }
+    }
+    constexpr int TPR = FT / R;                        // 32, 16 or 8 threads per row
+    const int drow_ = tid / TPR, sub = tid % TPR;
+    const int cols = (int)(c1 - c0);
+    float sd = 0.0f;
+    for (int c = sub; c < cols; c += TPR) {
+      const float dv = sm.Dm[drow_][c];
+      sd = __fmaf_rn(dv, dv, sd);
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) sd = __fadd_rn(sd, __shfl_xor_sync(0xffffffffu, sd, o));
+    if (sub == 0 && row0 + drow_ < r) {
+      float* p = Esum + 2 * (row0 + drow_) + 1;
+      const float prev = c0 > 0 ? *p : 0.0f;
+      *p = __fadd_rn(prev, sd);
+    }
+  }
 }
 
 extern "C" int slk_debug_sweep_trace(void* buf) {
@@ -809,14 +866,15 @@ extern "C" int slk_debug_sweep_trace(void* buf) {
 template <int R>
 static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
                         cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo,
-                        const GridBreaks& xv) {
+                        const GridBreaks& xv, float* esum) {
   auto kern = sweep_macro_kernel<R>;
   static bool attr_done = false;
   if (!attr_done) {
     SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MacroSmem<R>)));
     attr_done = true;
   }
-  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo, xv);
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo, xv,
+                                                                  esum);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -847,6 +905,17 @@ extern "C" size_t slk_gptq_sweep_r_ws_bytes(int64_t r, int64_t n) {
 extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* rt_hi,
                                     const float* rt_lo, const float* ud32, const slk_codebook* cb, void* ws,
                                     size_t ws_bytes, void* stream) {
+  return slk_gptq_sweep_r_err_f32(q, d, r, n, r32, rt_hi, rt_lo, ud32, cb, ws, ws_bytes, nullptr, stream);
+}
+
+// The same sweep, also returning per row the sums err_sums[row] = (sum_i res_i^2, sum_i D_i^2).  With
+// res_i = (w'_i - q_i) R_ii = obq.py:114's scaled residual E_i one has W - Q = E U and U H_opt U^T = I,
+// hence  (W-Q) H_opt (W-Q)^T = sum_i E_i^2  exactly, and the layer error of obq.py:89-95 under the
+// UNDAMPED H the factor was formed from is  sum_i E_i^2 - damp_abs * sum_i D_i^2
+// (slk_sweep_error_f32): the 2 r n^2 flop product of K6 is not needed after a sweep.
+extern "C" int slk_gptq_sweep_r_err_f32(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* rt_hi,
+                                        const float* rt_lo, const float* ud32, const slk_codebook* cb, void* ws,
+                                        size_t ws_bytes, float* err_sums, void* stream) {
   int rc = check_codebook(cb);
   if (rc) return rc;
   SLK_REQUIRE(r >= 0 && n >= 1, "bad shape");
@@ -866,13 +935,13 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
   const GridBreaks xv = make_breaks(cb);        // codebook breakpoints for the leaf's compare tree
   auto fused = [&](int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) -> int {
     if (n % 4 == 0 && c1 - c0 <= MB_COLS && (((uintptr_t)r32) & 15) == 0) {
-      if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
-      if (r >= 16 * want) return launch_macro<16>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
-      return launch_macro<8>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv);
+      if (r >= 32 * want) return launch_macro<32>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv, err_sums);
+      if (r >= 16 * want) return launch_macro<16>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv, err_sums);
+      return launch_macro<8>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, dhi, dlo, xv, err_sums);
     }
-    if (r >= 32 * want) return launch_fused<32, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
-    if (r >= 16 * want) return launch_fused<16, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
-    return launch_fused<8, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc);
+    if (r >= 32 * want) return launch_fused<32, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, err_sums);
+    if (r >= 16 * want) return launch_fused<16, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, err_sums);
+    return launch_fused<8, true>(q, d, r, n, r32, ud32, g, st, c0, c1, pacc, err_sums);
   };
   if (!sweep_macro_ok(r, n, d, rt_hi, rt_lo) || !ws || ws_bytes < slk_gptq_sweep_r_ws_bytes(r, n))
     return fused(0, n, nullptr, nullptr, nullptr);
@@ -901,5 +970,39 @@ extern "C" int slk_gptq_sweep_r_f32(float* q, float* d, int64_t r, int64_t n, co
     }
     if (S1 < n && (rc = push(S0, S1, S1, n))) return rc;
   }
+  return SLK_OK;
+}
+
+// ---- layer error from the sweep's row sums ----------------------------------------------------------
+// rows_out[row] = scale[row]^2 * (sum E^2 - damp_abs * sum D^2)   (channelwise_error, obq.py:89-95, of the
+// de-scaled result: W - Q_descaled = scale * D);  mean_out = their mean (quantization_error, obq.py:98-103).
+namespace slk {
+__global__ void __launch_bounds__(256) sweep_error_kernel(const float2* __restrict__ sums, const float* __restrict__ scale,
+                                                          const float* __restrict__ dampval, int64_t r,
+                                                          float* __restrict__ rows_out, float* __restrict__ mean_out) {
+  __shared__ double scratch[32];
+  const float lam = dampval ? __ldg(dampval) : 0.0f;
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < r; j += blockDim.x) {
+    const float2 v = sums[j];
+    float e = __fsub_rn(v.x, __fmul_rn(lam, v.y));
+    if (scale) {
+      const float s = scale[j];
+      e = __fmul_rn(e, __fmul_rn(s, s));
+    }
+    if (rows_out) rows_out[j] = e;
+    acc += (double)e;
+  }
+  acc = block_sum<double>(acc, scratch);
+  if (threadIdx.x == 0 && mean_out) mean_out[0] = __fdiv_rn((float)acc, (float)r);
+}
+}  // namespace slk
+
+extern "C" int slk_sweep_error_f32(const float* err_sums, const float* row_scale, const float* damp_abs, int64_t r,
+                                   float* rows_out, float* mean_out, void* stream) {
+  SLK_REQUIRE(err_sums && r >= 1 && (rows_out || mean_out), "bad arguments");
+  sweep_error_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(err_sums), row_scale, damp_abs, r,
+                                                          rows_out, mean_out);
+  SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

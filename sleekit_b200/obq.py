@@ -22,6 +22,8 @@ MAX_LEAF = 32  # widest column block the leaf kernel sweeps (one lane per column
 import os as _os
 
 USE_CHOL_FORM = _os.environ.get("SLK_CHOL_FORM", "1") != "0"
+# layer error of the fused path from the sweep's own residuals (gptq_device, want_err); 0: always the K6 product
+USE_SWEEP_ERROR = _os.environ.get("SLK_SWEEP_ERROR", "1") != "0"
 
 
 def random_psd_matrix(size, rank, damp=0.0):
@@ -161,15 +163,20 @@ def _quantize_opt_core(Q, E, Hinv, quantizer):
 
 
 def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
-                check=False, colsum_reduce=None, row_scale=None):
+                check=False, colsum_reduce=None, row_scale=None, want_err=False):
     """quantize_opt on device tensors (fp32 W [r,n], fp32 H [n,n]); returns quantized values [r,n].
     The whole chain -- damp, keys, argsort, gather, fp64 factor, sweep, scatter, local search --
     is enqueued on the current stream without a host round trip.  colsum_reduce: optional callable
     applied to the column residual sums of the err / sqerr orderings (row-sharded runs all-reduce
     them there, dist.allreduce_column_sums).  row_scale: Wd is then the UNSCALED matrix; the division
     by the row scales and the de-scaling of the result are fused into the two column-permutation
-    passes (quantize_with_scaling's scaling.py:73 and :80) and the de-scaled weights are returned."""
+    passes (quantize_with_scaling's scaling.py:73 and :80) and the de-scaled weights are returned.
+    want_err: also return (mean layer error [1], row errors [r]) = quantization_error / channelwise_error
+    (obq.py:89-103) of the returned weights against Wd under Hd, taken from the sweep's residuals
+    (sum E^2 - damp * sum (W-Q)^2, ops.sweep_error) when the factor-form sweep ran and no local-search
+    move follows, from the K6 product otherwise."""
     dampval = ops.damp_value(Hd, damp)                                   # obq.py:198
+    W_in = Wd
     fuse = row_scale is not None and act_order in ("diag", "none") and not nb_ls_moves
     if row_scale is not None and not fuse:
         Wd = ops.scale_rows(Wd, row_scale, 0)                            # scaling.py:73
@@ -194,14 +201,22 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
     if _sweep_leaf(min_block_size) == MAX_LEAF and USE_CHOL_FORM:
         # factor only (no triangular inverse): H_opt = R R^T, sweep from R
         r32, rt32, ud32, info = ops.chol_factor(Hd, order, dampval)       # obq.py:204 (dpotrf part)
-        ops.gptq_sweep_r(Q, r32, rt32, ud32, quantizer)                   # obq.py:208-209
+        sums = None
+        if want_err and not nb_ls_moves and USE_SWEEP_ERROR:
+            sums = torch.empty((Q.shape[0], 2), dtype=torch.float32, device=Q.device)
+        ops.gptq_sweep_r(Q, r32, rt32, ud32, quantizer, err_sums=sums)    # obq.py:208-209
+        if sums is not None:
+            err = ops.sweep_error(sums, row_scale, dampval, want_rows=True)
     else:
+        sums = None
         u64, u32, info = ops.hinv(Hd, order, dampval)                     # obq.py:204-205
         ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209
     if fuse:
         Q = ops.scale_permute_cols(Q, order, row_scale, scatter=True)     # obq.py:212-213 + scaling.py:80
         if check:
             _raise_if_not_pd(info)
+        if want_err:
+            return Q, (err if sums is not None else _k6_error(W_in, Q, Hd))
         return Q
     if order is not None:
         Q = ops.permute_cols(Q, order, scatter=True)                      # obq.py:212-213
@@ -211,7 +226,14 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
         ops.local_search(Wd, Q, Hd, quantizer, nb_ls_moves)               # obq.py:216
     if row_scale is not None:
         Q = ops.scale_rows(Q, row_scale, 1)                               # scaling.py:80
+    if want_err:
+        return Q, (err if sums is not None else _k6_error(W_in, Q, Hd))
     return Q
+
+
+def _k6_error(Wd, Qd, Hd):
+    rows = ops.hweighted_error(Wd, Qd, Hd)                                # obq.py:89-95
+    return ops.mean(rows), rows                                           # obq.py:98-103
 
 
 def quantize_opt(W, H, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8):

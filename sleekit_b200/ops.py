@@ -438,20 +438,37 @@ def chol_factor(h, order=None, dampval=None, want_rt=True):
 
 
 @_timed("gptq_sweep")
-def gptq_sweep_r(q, r32, rt, ud32, cb, d=None):
-    """In place on q; the sweep from the Cholesky factor (chol_factor); returns (q, d = W - Q)."""
+def gptq_sweep_r(q, r32, rt, ud32, cb, d=None, err_sums=None):
+    """In place on q; the sweep from the Cholesky factor (chol_factor); returns (q, d = W - Q).
+    err_sums: optional [rows, 2] fp32 out -- per row (sum E^2, sum (W-Q)^2), see sweep_error."""
     cb = device_codebook(cb)
     _chk(q, torch.float32)
     _chk(r32, torch.float32)
     _chk(ud32, torch.float32)
     if d is None:
         d = torch.empty_like(q)
+    if err_sums is not None:
+        _chk(err_sums, torch.float32)
+        assert err_sums.shape == (q.shape[0], 2)
     nbytes = _lib.load().slk_gptq_sweep_r_ws_bytes(q.shape[0], q.shape[1]) if rt is not None else 0
     ws = _ws(nbytes, q.device) if nbytes else None
-    _lib.call("slk_gptq_sweep_r_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32),
+    _lib.call("slk_gptq_sweep_r_err_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32),
               _ptr(rt[0]) if rt is not None else None, _ptr(rt[1]) if rt is not None else None, _ptr(ud32),
-              cb.ref, _ptr(ws), nbytes, _stream())
+              cb.ref, _ptr(ws), nbytes, _ptr(err_sums), _stream())
     return q, d
+
+
+@_timed("sweep_error")
+def sweep_error(err_sums, row_scale=None, dampval=None, want_rows=False):
+    """Layer error from the sweep's row sums (slk_sweep_error_f32): mean over rows of
+    scale^2 * (sum E^2 - damp * sum (W-Q)^2) = quantization_error(W, Q_descaled, H) (obq.py:89-103)
+    for the H the sweep's factor was formed from.  Returns (mean [1], rows or None)."""
+    _chk(err_sums, torch.float32)
+    r = err_sums.shape[0]
+    out = torch.empty(1, dtype=torch.float32, device=err_sums.device)
+    rows = torch.empty(r, dtype=torch.float32, device=err_sums.device) if want_rows else None
+    _lib.call("slk_sweep_error_f32", _ptr(err_sums), _ptr(row_scale), _ptr(dampval), r, _ptr(rows), _ptr(out), _stream())
+    return out, rows
 
 
 @_timed("gptq_sweep")

@@ -31,8 +31,9 @@ class LayerSetQuantizer:
 
     def _one(self, W, H):
         sc = _device_scaling(W, self.cb, H, self.scaling_mode, self.grid_size, self.min_factor, self.max_factor)
-        q = quantize_scaled_device(W, sc, self.cb, H, self.act_order, self.damp, self.nb_ls_moves)
-        err = ops.mean(ops.hweighted_error(W, q, H))
+        # layer error (obq.py:89-103): from the sweep's own residuals when possible (gptq_device)
+        q, (err, _) = quantize_scaled_device(W, sc, self.cb, H, self.act_order, self.damp, self.nb_ls_moves,
+                                             want_err=True)
         return q, sc, err
 
     def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True, _in_capture=False, _pre=None, _post=None):
@@ -181,8 +182,8 @@ def quantize_layer_sharded(W_rows, X_rows, codebook, scaling_mode="diag", act_or
     Hq = ops.remove_input_bias(H, mean) if bias_correction else H
     sc = _device_scaling(W_rows, codebook, Hq, scaling_mode, grid_size, min_factor, max_factor)
     reduce_cols = (lambda c: sdist.allreduce_column_sums(c, group)) if act_order in ("err", "sqerr") else None
-    q = quantize_scaled_device(W_rows, sc, codebook, Hq, act_order, damp, nb_ls_moves, colsum_reduce=reduce_cols)
-    rows_err = ops.hweighted_error(W_rows, q, Hq)
+    q, (_, rows_err) = quantize_scaled_device(W_rows, sc, codebook, Hq, act_order, damp, nb_ls_moves,
+                                              colsum_reduce=reduce_cols, want_err=True)
     total_rows = torch.tensor([W_rows.shape[0]], dtype=torch.int64, device=dev)
     if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
         tdist.all_reduce(total_rows, group=group)

@@ -89,6 +89,22 @@ def main():
             t_r = timeit(lambda: ops.gptq_sweep_r(Ws.clone(), r32, rt32, ud32, cb), reps=5)
             print(f"[{r}x{n}] hinv {t_h:9.1f} us   sweep {t_s:9.1f} us   argsort {t_a:7.1f} us  info={int(info.item())}"
                   f"   chol {t_c:9.1f} us  sweep_r {t_r:9.1f} us  info={int(info2.item())}")
+    if what == "sweepr":
+        for r, n in ((768, 768), (3072, 768), (768, 3072), (1024, 4096)):
+            W, H, _ = wl.synthetic_layer(r, n, 0, samples=2048)
+            Wd, Hd = torch.from_numpy(W).to(dev), torch.from_numpy(H).to(dev)
+            damp = ops.damp_value(Hd, 0.01)
+            order = ops.argsort(ops.order_keys(Hd, damp, None))
+            r32, rt32, ud32, info2 = ops.chol_factor(Hd, order, damp)
+            sc = ops.scale_search(Wd, cb, torch.linspace(0.05, 1, 100, device=dev), Hd.diagonal().contiguous())[0]
+            Ws = ops.scale_rows(Wd, sc, 0)
+            sums = torch.empty((r, 2), device=dev)
+            dd = torch.empty_like(Ws)
+            t_c = timeit(lambda: Ws.clone(), reps=20)
+            t_0 = timeit(lambda: ops.gptq_sweep_r(Ws.clone(), r32, rt32, ud32, cb, d=dd), reps=20)
+            t_1 = timeit(lambda: ops.gptq_sweep_r(Ws.clone(), r32, rt32, ud32, cb, d=dd, err_sums=sums), reps=20)
+            print(f"[{r}x{n}] sweep_r {t_0 - t_c:9.1f} us   with err_sums {t_1 - t_c:9.1f} us")
+        return
     if what in ("search", "all"):
         for r, n in ((768, 768), (3072, 768), (768, 3072)):
             W, H, _ = wl.synthetic_layer(r, n, 0, samples=256)
