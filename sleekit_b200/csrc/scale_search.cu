@@ -66,10 +66,21 @@ __device__ __forceinline__ HT row_error(const float* __restrict__ rowp, int64_t 
 // up, and accumulates h*(v-w)^2:  ~13 issue slots instead of the ~36 of three exact divides, split
 // over the FMA, ALU and LSU pipes.  Every weight receives exactly the value the reference's chain
 // gives it (non-NaN inputs), so the chosen grid point is unchanged.
+//
+// Walk form of the main loop (default).  Along an ascending grid the thresholds move away from zero
+// (T_k ~ X_k * scale), so the exact index of a weight w >= 0 can only step DOWN towards the centre and
+// that of a weight w < 0 only UP, and by at most one per grid point when the grid is fine enough.
+// Both facts are statements about the exact tables and are CHECKED on them per row (four comparisons
+// per (grid point, code): see `walk conditions` below; a row that fails uses the estimate loop).
+// The thread then keeps, per weight, a pointer to the table entry that decides its next move --
+// T[g][k] for w >= 0, T[g][k+1] for w < 0 -- found once at the first grid point with the estimate;
+// per (weight, grid point): one threshold load, one compare, a predicated pointer step, the value
+// load, sub, mul, fma: 8-9 issue slots instead of 14.  The 16 per-grid-point partial sums of a block
+// of grid points are reduced across the warp by recursive halving (16 shuffles for 16 sums instead
+// of 80).  Same exact indices, hence the same values and the same chosen grid point.
 constexpr int TAB_MAXC = 16;
-constexpr int TAB_PITCH = 18;     // T[0..C] then padding; all lanes read one grid point's table -> distinct banks
 constexpr int TAB_THREADS = 128;
-constexpr int TAB_MAXG = 128;    // grid points per row held in shared memory (23 KB per CTA: 9 CTAs per SM)
+constexpr int TAB_MAXG = 128;     // grid points per row held in shared memory
 
 __device__ __forceinline__ int f32_ord(float x) {
   const int i = __float_as_int(x);
@@ -79,32 +90,76 @@ __device__ __forceinline__ float f32_unord(int o) {
   return __int_as_float(o >= 0 ? o : (int)(0x80000000u - (unsigned)o));
 }
 
-struct TabSmem {
-  float T[TAB_MAXG][TAB_PITCH];   // T[g][k], k = 1..C-1 breakpoints, T[g][C] = +inf
-  float D[TAB_MAXG][TAB_PITCH];   // D[g][k] = de-quantised value of code k
+// Shared memory: a fixed header, then two table regions of G rows each (dynamic, sized by G).
+// Row g of a region: T[0..C] (T[0] = -inf, T[C] = +inf) then, PITCH floats later, the C values.
+// Region 0 serves the weights w >= 0 as they are.  Region 1 serves the weights w < 0 MIRRORED:
+// the thread holds w' = -w > 0, and with  T'[j] = nextup(-T[C-j]),  D'[j] = -D[C-1-j]  one has
+//   idx'(w') = C-1-idx(w)   (idx(w) >= k <=> w >= T[k] <=> w' <= -T[k] <=> not (w' >= nextup(-T[k])))
+//   D'[idx'(w')] - w' = -(D[idx(w)] - w)                       -- the same square, bit for bit.
+// Both classes therefore run the same code: the index only ever steps DOWN along an ascending grid,
+// the move test is w' < T*[g][k], and the value sits at a compile-time offset from the threshold.
+// PITCH = 9 (C <= 8) or 17 (C <= 16); region 1 starts 16 banks away from region 0, so that for
+// C <= 8 the two classes of one warp never collide on a bank.
+struct TabHead {
   float ea[TAB_MAXG], eb[TAB_MAXG];     // index estimate t_a = w*ea + eb  (eb already holds the -0.5 bias)
-  float scale[TAB_MAXG], rs[TAB_MAXG];
+  float scale[TAB_MAXG], rs[TAB_MAXG];  // rs = RN(1/scale): scaling.py:80's factor AND the reciprocal for dividing by scale
+  float rr[TAB_MAXG];                   // RN(1/rs): reciprocal for dividing by rs
+  int ok[TAB_MAXG];                     // bit 0 / 1: the exact-reciprocal scheme applies to scale / rs (common.cuh)
   float errs[TAB_THREADS / 32][TAB_MAXG];
   float X[TAB_MAXC];              // X[k] = min{x : slot(x) >= k}: breakpoints of the codebook itself
   float red_lo[4], red_hi[4];
   float init;
   int bad;                         // some grid point of this row cannot use the estimate -> direct form
+  int nowalk;                      // the walk conditions do not hold for this row -> estimate loop
+  int pad[5];
 };
+static_assert(sizeof(TabHead) % 128 == 0, "table regions must start on a bank-0 boundary");
 
-template <bool HAS_H, int TAB_WPT>
-__global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const float* __restrict__ w, int64_t r, int64_t n,
-                                                                       DevGrid<float> g, GridBreaks brk, float cb_min,
-                                                                       float cb_max, const float* __restrict__ factors,
-                                                                       int G, const float* __restrict__ hdiag,
-                                                                       float* __restrict__ out_scale,
-                                                                       float* __restrict__ out_err,
-                                                                       float* __restrict__ out_init) {
-  extern __shared__ __align__(16) unsigned char tab_raw[];
-  TabSmem& sm = *reinterpret_cast<TabSmem*>(tab_raw);
+template <int PITCH>
+__host__ __device__ constexpr int tab_region_floats(int G) {
+  // G rows of 2*PITCH floats, rounded so that the next region starts 16 banks further
+  return ((G * 2 * PITCH + 31) / 32) * 32 + 16;
+}
+template <int PITCH>
+static size_t tab_smem_bytes(int G) { return sizeof(TabHead) + (size_t)2 * tab_region_floats<PITCH>(G) * sizeof(float); }
+
+// Sum over the warp of 16 values per lane by recursive halving: returns, in every lane, the total of
+// v[lane & 15] over the 32 lanes.  Fixed order: deterministic.
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, h));
+    }
+  }
+  return __fadd_rn(v[0], __shfl_xor_sync(0xffffffffu, v[0], 16));
+}
+
+template <bool HAS_H, int TAB_WPT, int PITCH>
+__global__ void __launch_bounds__(TAB_THREADS, 8) scale_search_tab_kernel(const float* __restrict__ w, int64_t r, int64_t n,
+                                                                          DevGrid<float> g, GridBreaks brk, float cb_min,
+                                                                          float cb_max, const float* __restrict__ factors,
+                                                                          int G, const float* __restrict__ hdiag,
+                                                                          float* __restrict__ out_scale,
+                                                                          float* __restrict__ out_err,
+                                                                          float* __restrict__ out_init, int walk_allowed) {
+  extern __shared__ __align__(128) unsigned char tab_raw[];
+  TabHead& sm = *reinterpret_cast<TabHead*>(tab_raw);
+  constexpr int RP = 2 * PITCH;                         // floats per table row
+  float* const tab0 = reinterpret_cast<float*>(tab_raw + sizeof(TabHead));
+  float* const tab1 = tab0 + tab_region_floats<PITCH>(G);
+  auto T0 = [&](int gi, int k) -> float& { return tab0[gi * RP + k]; };
+  auto D0 = [&](int gi, int k) -> float& { return tab0[gi * RP + PITCH + k]; };
+  auto T1 = [&](int gi, int k) -> float& { return tab1[gi * RP + k]; };
+  auto D1 = [&](int gi, int k) -> float& { return tab1[gi * RP + PITCH + k]; };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = g.size;
-  const float top = (float)(C - 1);
   const FastDivF fstep = make_fastdiv(g.step);
+  const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
 
   // breakpoints of the codebook in the scaled domain (exact; found on the host, make_breaks)
   if (tid < TAB_MAXC) sm.X[tid] = brk.X[tid];
@@ -121,7 +176,7 @@ __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const flo
     }
     lo = warp_min(lo); hi = warp_max(hi);
     if (lane == 0) { sm.red_lo[warp] = lo; sm.red_hi[warp] = hi; }
-    if (tid == 0) sm.bad = 0;
+    if (tid == 0) { sm.bad = 0; sm.nowalk = walk_allowed ? 0 : 1; }
     __syncthreads();
     lo = fminf(fminf(sm.red_lo[0], sm.red_lo[1]), fminf(sm.red_lo[2], sm.red_lo[3]));
     hi = fmaxf(fmaxf(sm.red_hi[0], sm.red_hi[1]), fmaxf(sm.red_hi[2], sm.red_hi[3]));
@@ -138,13 +193,19 @@ __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const flo
       const float rsv = __fdiv_rn(1.0f, scale);                          // scaling.py:80
       sm.scale[gi] = scale;
       sm.rs[gi] = rsv;
+      {
+        const FastDivF fs = make_fastdiv(scale), fr = make_fastdiv(rsv);   // fs.y == rsv
+        sm.rr[gi] = fr.y;
+        sm.ok[gi] = fs.ok | (fr.ok << 1);
+      }
       const float ea = __fdiv_rn(1.0f, __fmul_rn(scale, g.step));
       const float eb = __fsub_rn(__fdiv_rn(-g.zero, g.step), 0.5f);
       sm.ea[gi] = ea;
       sm.eb[gi] = eb;
       const float reach = __fadd_rn(__fmul_rn(wmax, fabsf(ea)), fabsf(eb));
       if (!(scale > 0.0f) || !(reach < 2.0e6f)) sm.bad = 1;             // also catches NaN / inf
-      sm.T[gi][C] = __int_as_float(0x7f800000);
+      T0(gi, C) = pinf; T0(gi, 0) = ninf;
+      T1(gi, C) = pinf; T1(gi, 0) = ninf;
       for (int wp = 0; wp < TAB_THREADS / 32; ++wp) sm.errs[wp][gi] = 0.0f;
     }
     __syncthreads();
@@ -161,32 +222,137 @@ __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const flo
       // ---- pass 2b: exact tables, one (grid point, code) task at a time ----------------------------
       // idx(w) >= k  <=>  RN(w/scale) >= X[k], so T[k] = min{w : RN(w/scale) >= X[k]}: it lies within a
       // few ulps of X[k]*scale; bracket, verify, bisect (full range if the bracket ever fails).
-      for (int task = tid; task < G * C; task += TAB_THREADS) {
-        const int k = task / G, gi = task - k * G;          // heavy and light codes spread over the threads
-        const float scale = sm.scale[gi];
-        const FastDivF fs = make_fastdiv(scale), fr = make_fastdiv(sm.rs[gi]);
+      // Task (gi, k): k = 0 only de-quantises.  CP2 = 8 or 16 codes per grid point slot, so that the task
+      // index splits by shifts; the code of a thread rotates with the round (k = 0 tasks are light).
+      constexpr int CP2 = PITCH - 1, CSH = (CP2 == 8 ? 3 : 4);
+      for (int t0 = 0; t0 < G * CP2; t0 += TAB_THREADS) {
+        const int gi = (t0 + tid) >> CSH, k = (tid + (t0 / TAB_THREADS)) & (CP2 - 1);
+        if (gi >= G || k >= C) continue;
+        const float scale = sm.scale[gi], rsv = sm.rs[gi], rrv = sm.rr[gi];
+        const int okb = sm.ok[gi];
         const float v = __fadd_rn(__fmul_rn((float)k, g.step), g.zero);                                 // codebook.py:63-64
-        sm.D[gi][k] = fr.ok ? fastdiv_core(v, fr.d, fr.y) : __fdiv_rn(v, fr.d);                         // scaling.py:80
+        const float dqv = (okb & 2) ? fastdiv_core(v, rsv, rrv) : __fdiv_rn(v, rsv);                    // scaling.py:80
+        D0(gi, k) = dqv;
+        D1(gi, C - 1 - k) = -dqv;
         if (k == 0) continue;
         const float xk = sm.X[k];
-        auto reaches = [&](float x0) -> bool {
-          return (fs.ok ? fastdiv_core(x0, fs.d, fs.y) : __fdiv_rn(x0, fs.d)) >= xk;                    // scaling.py:73
+        auto reaches = [&](int o) -> bool {
+          const float x0 = f32_unord(o);
+          return ((okb & 1) ? fastdiv_core(x0, scale, rsv) : __fdiv_rn(x0, scale)) >= xk;               // scaling.py:73
         };
-        const int og = f32_ord(__fmul_rn(xk, scale));
-        long long blo = (long long)og - 4, bhi = (long long)og + 4;
-        if (blo < f32_ord(-3.402823466e+38f) || bhi > f32_ord(3.402823466e+38f) ||
-            reaches(f32_unord((int)blo)) || !reaches(f32_unord((int)bhi))) {
-          blo = f32_ord(-3.402823466e+38f);
-          bhi = f32_ord(3.402823466e+38f);
+        // `reaches` is monotone in the ordered-integer key; the threshold lies within an ulp or two of
+        // X[k]*scale: step from there (typically two evaluations), full bisection if that ever fails
+        const int omin = f32_ord(-3.402823466e+38f), omax = f32_ord(3.402823466e+38f);
+        int o = f32_ord(__fmul_rn(xk, scale));
+        bool found = false;
+        if (o > omin + 8 && o < omax - 8) {
+          if (reaches(o)) {
+            int steps = 0;
+            while (steps < 6 && reaches(o - 1)) { --o; ++steps; }
+            found = steps < 6;
+          } else {
+            int steps = 0;
+            while (steps < 6 && !reaches(o + 1)) { ++o; ++steps; }
+            ++o;
+            found = steps < 6;
+          }
         }
-        while (bhi - blo > 1) {
-          const long long mid = blo + ((bhi - blo) >> 1);
-          if (reaches(f32_unord((int)mid))) bhi = mid; else blo = mid;
+        if (!found) {
+          long long blo = omin, bhi = omax;
+          while (bhi - blo > 1) {
+            const long long mid = blo + ((bhi - blo) >> 1);
+            if (reaches((int)mid)) bhi = mid; else blo = mid;
+          }
+          o = (int)bhi;
         }
-        sm.T[gi][k] = f32_unord((int)bhi);
+        const float tk = f32_unord(o);
+        T0(gi, k) = tk;
+        // mirrored threshold: the smallest float above -T[k] (in the ordered-integer domain -0 and +0
+        // coincide, so the successor of the key of -T[k] is the next larger VALUE)
+        const int om = f32_ord(-tk);
+        T1(gi, C - k) = om == 0x7f7fffff ? pinf : f32_unord(om + 1);
       }
       __syncthreads();
-      // ---- pass 2c: weights in registers, walk the grid points -----------------------------------------
+      // ---- walk conditions, on the exact tables of both classes (idx_g(x) = max{j : T[g][j] <= x}) -----
+      //   x >= 0:  idx_{g+1}(x) in {idx_g(x) - 1, idx_g(x)}     <=  (a) T[g][j] <= 0 or T[g+1][j] >= T[g][j]
+      //                                                            (b) T[g+1][j-1] <= max(T[g][j], 0)
+      if (!sm.nowalk) {
+        for (int task = tid; task < 2 * (G - 1); task += TAB_THREADS) {
+          const int gi = task >> 1;
+          const float* tb = (task & 1) ? tab1 : tab0;
+          bool ok = true;
+          for (int j = 1; j < C; ++j) {
+            const float tg = tb[gi * RP + j], tn = tb[(gi + 1) * RP + j];
+            ok = ok && (tg <= 0.0f || tn >= tg) && (tb[(gi + 1) * RP + j - 1] <= fmaxf(tg, 0.0f));
+          }
+          if (!ok) sm.nowalk = 1;
+        }
+      }
+      __syncthreads();
+      if (!sm.nowalk) {
+        // ---- pass 2c (walk form): weights and table pointers in registers ------------------------------
+        // shared-memory BYTE addresses are tracked directly, so that the table loads are
+        // LDS [register + immediate] with the grid point (and the value offset) folded into the immediate
+        const uint32_t base0 = (uint32_t)__cvta_generic_to_shared(tab0);
+        const uint32_t base1 = (uint32_t)__cvta_generic_to_shared(tab1);
+        auto lds = [](uint32_t addr) -> float {
+          float v;
+          asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));   // tables are read-only in this phase
+          return v;
+        };
+        constexpr int GP = RP * 4;                            // bytes between consecutive grid points
+        constexpr int DQ = PITCH * 4;                         // bytes from a threshold to its value
+        for (int64_t c0 = 0; c0 < n; c0 += (int64_t)TAB_THREADS * TAB_WPT) {
+          float wv[TAB_WPT], hv[TAB_WPT];
+          uint32_t pt[TAB_WPT];         // &T*[g][k] of the weight's class at the block's first grid point
+#pragma unroll
+          for (int m = 0; m < TAB_WPT; ++m) {
+            const int64_t j = c0 + tid + (int64_t)m * TAB_THREADS;
+            const bool in = j < n;
+            const float wj = in ? __ldg(grow + j) : 0.0f;
+            hv[m] = in ? (HAS_H ? __ldg(hdiag + j) : 1.0f) : 0.0f;
+            // exact index at the first grid point (estimate + one comparison, as in the estimate loop)
+            const float ta = __fmaf_rn(wj, sm.ea[0], sm.eb[0]);
+            int ka = __float_as_int(__fadd_rn(ta, 12582912.0f)) - 0x4B400000;
+            ka = __vimin_s32_relu(ka, C - 1);
+            const int kx = (wj >= T0(0, ka + 1)) ? ka + 1 : ka;
+            const bool neg = wj < 0.0f;
+            wv[m] = neg ? -wj : wj;
+            pt[m] = neg ? base1 + 4u * (uint32_t)(C - 1 - kx) : base0 + 4u * (uint32_t)kx;
+          }
+          auto eval = [&](int m, int u, float acc) -> float {
+            const float t = lds(pt[m] + u * GP);
+            if (wv[m] < t) pt[m] -= 4;                                           // one step towards the centre
+            const float e = __fsub_rn(lds(pt[m] + (u * GP + DQ)), wv[m]);        // scaling.py:130 (sign-mirrored for w < 0)
+            return __fmaf_rn(__fmul_rn(e, e), hv[m], acc);
+          };
+          int gb = 0;
+          for (; gb + 16 <= G; gb += 16) {
+            float part[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              float acc = 0.0f;
+#pragma unroll
+              for (int m = 0; m < TAB_WPT; ++m) acc = eval(m, u, acc);
+              part[u] = acc;
+            }
+#pragma unroll
+            for (int m = 0; m < TAB_WPT; ++m) pt[m] += 16 * GP;
+            const float tot = warp_sum16(part, lane);
+            if (lane < 16) sm.errs[warp][gb + lane] += tot;
+          }
+          for (; gb < G; ++gb) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int m = 0; m < TAB_WPT; ++m) acc = eval(m, 0, acc);
+#pragma unroll
+            for (int m = 0; m < TAB_WPT; ++m) pt[m] += GP;
+            acc = warp_sum(acc);
+            if (lane == 0) sm.errs[warp][gb] += acc;
+          }
+        }
+      } else
+      // ---- pass 2c (estimate form): weights in registers, walk the grid points ------------------------
       for (int64_t c0 = 0; c0 < n; c0 += (int64_t)TAB_THREADS * TAB_WPT) {
         float wv[TAB_WPT], hv[TAB_WPT];
 #pragma unroll
@@ -199,8 +365,8 @@ __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const flo
 #pragma unroll 2
         for (int gi = 0; gi < G; ++gi) {
           const float ea = sm.ea[gi], eb = sm.eb[gi];
-          const float* Tg = sm.T[gi];
-          const float* Dg = sm.D[gi];
+          const float* Tg = &T0(gi, 0);
+          const float* Dg = &D0(gi, 0);
           float part = 0.0f;
 #pragma unroll
           for (int m = 0; m < TAB_WPT; ++m) {
@@ -219,16 +385,28 @@ __global__ void __launch_bounds__(TAB_THREADS) scale_search_tab_kernel(const flo
     }
     __syncthreads();
     // ---- pass 3: first strict minimum in grid order, best kept in fp32 (scaling.py:125-134) --------
-    if (tid == 0) {
-      float best = __int_as_float(0x7f800000), pick = __int_as_float(0x7f800000);
-      for (int gi = 0; gi < G; ++gi) {
+    if (warp == 0) {
+      // every lane scans its grid points in ascending order (strict <), then the lanes are merged:
+      // smaller error wins, equal errors -> smaller grid index = the first strict minimum in grid order
+      float best = pinf;
+      int bi = 0x7fffffff;
+      for (int gi = lane; gi < G; gi += 32) {
         const float e = direct ? sm.errs[0][gi]
                                : __fadd_rn(__fadd_rn(sm.errs[0][gi], sm.errs[1][gi]), __fadd_rn(sm.errs[2][gi], sm.errs[3][gi]));
-        if (e < best) { best = e; pick = __ldg(factors + gi); }
+        if (e < best) { best = e; bi = gi; }
       }
-      out_scale[row] = __fmul_rn(init, pick);
-      if (out_err) out_err[row] = best;
-      if (out_init) out_init[row] = init;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float eo = __shfl_xor_sync(0xffffffffu, best, o);
+        const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (eo < best || (eo == best && io < bi)) { best = eo; bi = io; }
+      }
+      if (lane == 0) {
+        const float pick = bi < G ? __ldg(factors + bi) : pinf;     // no finite error at all: inf, as the serial scan
+        out_scale[row] = __fmul_rn(init, pick);
+        if (out_err) out_err[row] = best;
+        if (out_init) out_init[row] = init;
+      }
     }
     __syncthreads();
   }
@@ -306,9 +484,10 @@ using namespace slk;
 
 static int g_search_direct = -1;
 
-/* development aid / tests: 1 forces the direct op-chain kernel, 0 the default (threshold tables) */
+/* development aid / tests: 1 forces the direct op-chain kernel, 2 the threshold tables with the
+   estimate loop (no walk), 0 the default (threshold tables, walk form) */
 extern "C" int slk_debug_scale_search_direct(int on) {
-  g_search_direct = on ? 1 : 0;
+  g_search_direct = on == 2 ? 2 : (on ? 1 : 0);
   return SLK_OK;
 }
 
@@ -336,7 +515,8 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
     const char* ev = getenv("SLK_SEARCH_TABLE");
     g_search_direct = (ev && ev[0] == '0') ? 1 : 0;
   }
-  const int steps_off = g_search_direct;
+  const int steps_off = g_search_direct == 1;
+  const int walk_allowed = g_search_direct == 0;
   if (!steps_off && cb->kind == 0 && cb->size <= TAB_MAXC && G <= TAB_MAXG && h_dtype != 2) {
     // threshold-table form; grid: every SM holds several CTAs so that one CTA's (latency-bound) table
     // construction overlaps the others' (throughput-bound) main loops
@@ -352,14 +532,26 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
         if (best_waste < 0 || waste < best_waste) { best_waste = waste; wpt = cand; }
       }
     }
+#define SLK_LAUNCH_TAB2(HAS, WPT, PITCH)                                                                             \
+    do {                                                                                                             \
+      const size_t tb = tab_smem_bytes<PITCH>(G);                                                                    \
+      static size_t attr = 0;                                                                                        \
+      if (tb > 48 * 1024 && tb > attr) {                                                                             \
+        SLK_CUDA(cudaFuncSetAttribute(scale_search_tab_kernel<HAS, WPT, PITCH>,                                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));                        \
+        attr = tb;                                                                                                   \
+      }                                                                                                              \
+      scale_search_tab_kernel<HAS, WPT, PITCH><<<tgrid, TAB_THREADS, tb, st>>>(                                      \
+          w, r, n, g, brk, cmin, cmax, factors, G, (const float*)hdiag, out_scale, out_err, out_init, walk_allowed); \
+    } while (0)
 #define SLK_LAUNCH_TAB(HAS, WPT)                                                                                     \
-    scale_search_tab_kernel<HAS, WPT><<<tgrid, TAB_THREADS, sizeof(TabSmem), st>>>(                                    \
-        w, r, n, g, brk, cmin, cmax, factors, G, (const float*)hdiag, out_scale, out_err, out_init)
+    do { if (cb->size <= 8) SLK_LAUNCH_TAB2(HAS, WPT, 9); else SLK_LAUNCH_TAB2(HAS, WPT, 17); } while (0)
     if (h_dtype == 1) {
       if (wpt == 8) SLK_LAUNCH_TAB(true, 8); else if (wpt == 6) SLK_LAUNCH_TAB(true, 6); else SLK_LAUNCH_TAB(true, 4);
     } else {
       if (wpt == 8) SLK_LAUNCH_TAB(false, 8); else if (wpt == 6) SLK_LAUNCH_TAB(false, 6); else SLK_LAUNCH_TAB(false, 4);
     }
+#undef SLK_LAUNCH_TAB2
 #undef SLK_LAUNCH_TAB
     SLK_LAUNCH_CHECK();
     return SLK_OK;

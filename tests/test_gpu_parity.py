@@ -196,17 +196,53 @@ def test_scale_search_table_form_equals_direct_form(slk, c, diag):
     f = torch.linspace(0.05, 1.0, 100, device="cuda")
     hd = torch.from_numpy(np.ascontiguousarray(H.diagonal())).cuda() if diag else None
     out = {}
-    for direct in (1, 0):
+    for direct in (1, 2, 0):         # direct op chain / tables + estimate loop / tables + walk (default)
         _lib.call("slk_debug_scale_search_direct", direct)
         try:
             sc, err, init = ops.scale_search(Wd, cb, f, hd, want_err=True, want_init=True)
             out[direct] = (sc.cpu().numpy(), err.cpu().numpy(), init.cpu().numpy())
         finally:
             _lib.call("slk_debug_scale_search_direct", 0)
-    np.testing.assert_array_equal(out[0][2], out[1][2])
+    for form in (0, 2):
+        np.testing.assert_array_equal(out[form][2], out[1][2])
+        same = float((out[form][0] == out[1][0]).mean())
+        print(f"c={c} diag={diag} form={form}: same grid point in {same:.4f} of rows")
+        assert same >= 0.995          # ties between near-equal errors may flip with summation order
+        np.testing.assert_allclose(out[form][1], out[1][1], rtol=2e-5)
+
+
+@pytest.mark.parametrize("c,grid", [(8, "g16"), (8, "g17"), (8, "g15"), (8, "g128"), (16, "coarse"), (4, "descending"),
+                                    (8, "wide"), (3, "g33")])
+def test_scale_search_walk_form_grids(slk, c, grid):
+    """The walk form of the table kernel (index tracked along the grid, conditions checked on the exact
+    tables) against the direct op chain on grids that exercise the 16-point blocks, the tail, and the
+    rows that must fall back to the estimate loop (steps of more than one code per grid point,
+    non-ascending grids)."""
+    from sleekit_b200 import _lib, ops
+
+    r, n = 130, 1000
+    W, H, m = wl.synthetic_layer(r, n, 11, samples=256)
+    W[3, :] = 0
+    W[4, :9] *= 60
+    W[5] = -np.abs(W[5])
+    cb = slk.codebook.UniformCodebook(c, -1, 1)
+    f = {"g16": np.linspace(0.05, 1.0, 16), "g17": np.linspace(0.3, 1.0, 17), "g15": np.linspace(0.3, 1.0, 15),
+         "g128": np.linspace(0.05, 1.0, 128), "coarse": np.linspace(0.02, 1.0, 9),
+         "descending": np.linspace(1.0, 0.05, 40), "wide": np.linspace(0.01, 3.0, 100),
+         "g33": np.linspace(0.05, 1.0, 33)}[grid].astype(np.float32)
+    Wd, fd = torch.from_numpy(W).cuda(), torch.from_numpy(f).cuda()
+    hd = torch.from_numpy(np.ascontiguousarray(H.diagonal())).cuda()
+    out = {}
+    for direct in (1, 0):
+        _lib.call("slk_debug_scale_search_direct", direct)
+        try:
+            sc, err, init = ops.scale_search(Wd, cb, fd, hd, want_err=True, want_init=True)
+            out[direct] = (sc.cpu().numpy(), err.cpu().numpy())
+        finally:
+            _lib.call("slk_debug_scale_search_direct", 0)
     same = float((out[0][0] == out[1][0]).mean())
-    print(f"c={c} diag={diag}: same grid point in {same:.4f} of rows")
-    assert same >= 0.995          # ties between near-equal errors may flip with summation order
+    print(f"c={c} grid={grid}: same grid point in {same:.4f} of rows")
+    assert same >= 0.99
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=2e-5)
 
 
