@@ -106,6 +106,15 @@ int slk_debug_scale_search_direct(int on);
  * leaf round through these (idx >= k <=> x >= X[k]). */
 int slk_codebook_breaks_host(const slk_codebook* cb_host, float* out16_host);
 
+/* ---- host -> device upload of a symmetric Hessian ------------------------------------------
+ * The experiments hand every layer's H = X^T X / n (statistics.py:87, read back from the data/ tree at
+ * experiments/compare.py:37-53) to the hot path as a host array; it is symmetric, so only its block
+ * upper triangle needs to cross PCIe.  h_host: page-locked [n, n]; h_dev: [n, n]; bs: rows per block
+ * row, a multiple of 32 (bs >= n: plain full copy).  Strided async copies + one mirror kernel on
+ * `stream`; slk_upload_symmetric_bytes returns the bytes that cross the bus. */
+int slk_upload_symmetric_f32(const float* h_host, float* h_dev, int64_t n, int64_t bs, void* stream);
+size_t slk_upload_symmetric_bytes(int64_t n, int64_t bs);
+
 /* ---- K6: H-weighted error ---------------------------------------------------
  * channelwise_error  ((W-Q) @ H * (W-Q)).sum(-1)            obq.py:89-95
  * _compute_mse with a 2-D H                                 scaling.py:91-95

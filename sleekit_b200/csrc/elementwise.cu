@@ -516,6 +516,28 @@ __global__ void __launch_bounds__(256) bias_delta_kernel(const float* __restrict
   }
 }
 
+// H[i][j] = H[j][i] for the 32x32 tiles (ti > tj) that lie below the block diagonal of the symmetric
+// upload (tiles of one copy block share floor(t / tpb)); one CTA per tile pair, transposed through
+// shared memory so that both the read and the write are coalesced.
+__global__ void __launch_bounds__(256) mirror_upper_kernel(float* __restrict__ h, int64_t n, int64_t tpb) {
+  __shared__ float tile[32][33];
+  // linear id -> (ti, tj), ti > tj
+  int64_t ti = 1, rem = blockIdx.x;
+  while (rem >= ti) { rem -= ti; ++ti; }
+  const int64_t tj = rem;
+  if (ti / tpb == tj / tpb) return;                  // inside a diagonal copy block: already there
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t a = tj * 32 + i, b = ti * 32 + tx;  // source: the tile above the diagonal
+    tile[i][tx] = (a < n && b < n) ? h[a * n + b] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t a = ti * 32 + i, b = tj * 32 + tx;
+    if (a < n && b < n) h[a * n + b] = tile[tx][i];
+  }
+}
+
 }  // namespace slk
 
 using namespace slk;
@@ -661,6 +683,33 @@ int slk_scale_permute_cols_f32(const float* src, int64_t r, int64_t n, const int
   scale_permute_cols_kernel<<<stream_grid(r * n, 256), 256, 0, (cudaStream_t)stream>>>(src, r, n, idx, s, scatter, dst);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
+}
+
+/* Upload of a SYMMETRIC host matrix (the Hessian H = X^T X / n, statistics.py:87) moving only what is
+ * needed over PCIe: the matrix is cut into block rows of `bs` rows (bs a multiple of 32); block row b
+ * sends its columns [b*bs, n) -- the diagonal block and everything to its right -- as one strided
+ * copy, and a device kernel mirrors the 32x32 tiles above the block diagonal into the tiles below it.
+ * (nb + 1) / (2 nb) of the bytes cross the bus.  Only enqueues work (capturable in a CUDA graph). */
+int slk_upload_symmetric_f32(const float* h_host, float* h_dev, int64_t n, int64_t bs, void* stream) {
+  SLK_REQUIRE(h_host && h_dev && n >= 1 && bs >= 32 && bs % 32 == 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t r0 = 0; r0 < n; r0 += bs) {
+    const int64_t rows = (r0 + bs < n) ? bs : n - r0;
+    SLK_CUDA(cudaMemcpy2DAsync(h_dev + r0 * n + r0, (size_t)n * 4, h_host + r0 * n + r0, (size_t)n * 4,
+                               (size_t)(n - r0) * 4, (size_t)rows, cudaMemcpyHostToDevice, st));
+  }
+  if (bs < n) {
+    const int64_t nt = (n + 31) / 32;
+    mirror_upper_kernel<<<(unsigned)(nt * (nt - 1) / 2), 256, 0, st>>>(h_dev, n, bs / 32);
+    SLK_LAUNCH_CHECK();
+  }
+  return SLK_OK;
+}
+
+size_t slk_upload_symmetric_bytes(int64_t n, int64_t bs) {
+  size_t total = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += bs) total += (size_t)((r0 + bs < n) ? bs : n - r0) * (size_t)(n - r0) * 4;
+  return total;
 }
 
 size_t slk_pivot_order_ws_bytes(int64_t n) {

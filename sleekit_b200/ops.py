@@ -394,6 +394,24 @@ def scale_permute_cols(src, idx, s, scatter=False):
 # ---------------------------------------------------------------------------
 
 
+def symmetric_block_rows(n):
+    """Rows per block row of the symmetric upload: 4 block rows up to n = 1024, 16 above (multiples of 32)."""
+    nb = 4 if n <= 1024 else 16
+    return max(32, ((n + nb - 1) // nb + 31) // 32 * 32)
+
+
+def upload_symmetric(h_pinned, h_dev):
+    """Enqueue the upload of a symmetric page-locked host matrix into h_dev moving only its block upper
+    triangle over PCIe (slk_upload_symmetric_f32); returns the bytes sent."""
+    assert h_pinned.is_pinned() and h_pinned.dtype == torch.float32 and h_pinned.is_contiguous()
+    _chk(h_dev, torch.float32)
+    n = h_dev.shape[0]
+    assert h_pinned.shape == (n, n) and h_dev.shape == (n, n)
+    bs = symmetric_block_rows(n)
+    _lib.call("slk_upload_symmetric_f32", C.c_void_p(h_pinned.data_ptr()), _ptr(h_dev), n, bs, _stream())
+    return int(_lib.load().slk_upload_symmetric_bytes(n, bs))
+
+
 @_timed("hinv")
 def hinv(h, order=None, dampval=None, want64=False, want32=True):
     """Upper factor U of the inverse of (h + dampval*I)[order][:, order]; returns (u64, u32, info)."""

@@ -685,6 +685,44 @@ def test_host_plan_equals_per_layer_api(slk):
             assert rel(err[i], slk.obq.quantization_error(W, want, H)) < 1e-4
 
 
+@pytest.mark.parametrize("n", [32, 100, 768, 1000, 1100, 3072])
+def test_symmetric_upload_equals_full_copy(slk, n):
+    """slk_upload_symmetric_f32: only the block upper triangle of a symmetric pinned host matrix crosses
+    PCIe, the device mirrors the rest -- the device matrix must equal the host matrix bit for bit."""
+    from sleekit_b200 import ops
+
+    g = np.random.default_rng(n)
+    a = g.standard_normal((n, n)).astype(np.float32)
+    h = torch.from_numpy(a + a.T).pin_memory()
+    d = torch.full((n, n), float("nan"), device="cuda")
+    sent = ops.upload_symmetric(h, d)
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), h)
+    assert sent < 4 * n * n or n <= ops.symmetric_block_rows(n)
+    print(f"n={n}: {sent / (4 * n * n):.3f} of the matrix sent")
+
+
+def test_host_plan_symmetric_upload_equals_full_upload(slk):
+    from sleekit_b200.pipeline import LayerSetQuantizer
+
+    shapes = [(64, 1056), (96, 128), (32, 2080)]
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    lsq = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=0.01, streams=3)
+    outs = []
+    for sym in (True, False):
+        plan = lsq.host_plan(shapes, symmetric_h=sym)
+        for i, (r, n) in enumerate(shapes):
+            W, H, m = wl.synthetic_layer(r, n, 40 + i, samples=512)
+            plan.W[i][...] = W
+            plan.H[i][...] = np.triu(H) + np.triu(H, 1).T          # exactly symmetric input
+        Q, err = plan.run()
+        outs.append(([q.copy() for q in Q], err.copy(), plan.h2d_bytes))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] < outs[1][2]
+
+
 def test_edge_cases(slk):
     cb = slk.codebook.UniformCodebook(4, -1, 1)
     W = np.zeros((3, 40), np.float32)
