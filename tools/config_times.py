@@ -40,8 +40,9 @@ def main():
 
         def one():
             sc = scaling.search_scale_device(Wd, cb, Hs)
-            q = scaling.quantize_scaled_device(Wd, sc, cb, Hq, "diag", 0.01, moves)
-            return ops.mean(ops.hweighted_error(Wd, q, Hq))
+            # layer error from the sweep's residuals when no local-search move follows (obq.gptq_device)
+            q, (err, _) = scaling.quantize_scaled_device(Wd, sc, cb, Hq, "diag", 0.01, moves, want_err=True)
+            return err
 
         one()
         torch.cuda.synchronize()
