@@ -165,3 +165,38 @@ def test_codebook_breakpoints_are_exact_on_the_host():
         want = grid.index(x).astype(np.int64)
         got = (x[:, None] >= X[None, 1:c]).sum(axis=1)
         np.testing.assert_array_equal(got, want)
+
+
+def test_issue_orders_are_permutations_with_the_stated_structure():
+    from sleekit_b200 import workloads as wl
+    from sleekit_b200.pipeline import issue_order
+
+    shapes = wl.layer_shapes("opt-125m")
+    for order in ("big", "interleaved", "model"):
+        idx = issue_order(shapes, order)
+        assert sorted(idx) == list(range(len(shapes)))
+    big = issue_order(shapes, "big")
+    assert [shapes[k][1] for k in big[:12]] == [3072] * 12                  # longest chains first
+    assert [shapes[k] for k in big[12:24]] == [(3072, 768)] * 12            # then more rows first
+    inter = issue_order(shapes, "interleaved")
+    pos = [p for p, k in enumerate(inter) if shapes[k][1] == 3072]
+    assert pos == list(range(0, 72, 6))                                     # one long chain, then five short ones
+    assert issue_order([(8, 16), (8, 16)], "interleaved") == [0, 1]         # nothing to interleave
+    with pytest.raises(ValueError):
+        issue_order(shapes, "random")
+
+
+def test_symmetric_upload_accounting_without_gpu():
+    """slk_upload_symmetric_bytes: bytes of the block upper triangle (host arithmetic only)."""
+    from sleekit_b200 import ops
+
+    lib = _lib.load()
+    for n in (32, 100, 768, 1000, 3072, 28672):
+        bs = ops.symmetric_block_rows(n)
+        assert bs % 32 == 0 and bs >= 32
+        want = sum(min(bs, n - r0) * (n - r0) * 4 for r0 in range(0, n, bs))
+        assert lib.slk_upload_symmetric_bytes(n, bs) == want
+        assert want <= 4 * n * n
+    assert lib.slk_upload_symmetric_bytes(3072, ops.symmetric_block_rows(3072)) / (4 * 3072 * 3072) < 0.54
+    # argument errors are reported, not crashed
+    assert lib.slk_upload_symmetric_f32(None, None, 16, 32, None) != 0
