@@ -68,16 +68,18 @@ __device__ __forceinline__ HT row_error(const float* __restrict__ rowp, int64_t 
 // gives it (non-NaN inputs), so the chosen grid point is unchanged.
 //
 // Walk form of the main loop (default).  Along an ascending grid the thresholds move away from zero
-// (T_k ~ X_k * scale), so the exact index of a weight w >= 0 can only step DOWN towards the centre and
-// that of a weight w < 0 only UP, and by at most one per grid point when the grid is fine enough.
-// Both facts are statements about the exact tables and are CHECKED on them per row (four comparisons
-// per (grid point, code): see `walk conditions` below; a row that fails uses the estimate loop).
-// The thread then keeps, per weight, a pointer to the table entry that decides its next move --
-// T[g][k] for w >= 0, T[g][k+1] for w < 0 -- found once at the first grid point with the estimate;
-// per (weight, grid point): one threshold load, one compare, a predicated pointer step, the value
-// load, sub, mul, fma: 8-9 issue slots instead of 14.  The 16 per-grid-point partial sums of a block
-// of grid points are reduced across the warp by recursive halving (16 shuffles for 16 sums instead
-// of 80).  Same exact indices, hence the same values and the same chosen grid point.
+// (T_k ~ X_k * scale), so the exact index of a weight can only step towards the centre of the
+// codebook, and by at most one code per grid point when the grid is fine enough.  Both facts are
+// statements about the exact tables and are CHECKED on them per row (two comparisons per (grid point,
+// code) and class: see `walk conditions` below; a row that fails uses the estimate loop).  Negative
+// weights are served by a mirrored copy of the tables (below), so that for every weight the index
+// steps DOWN and one code path serves both signs.  The thread keeps, per weight, the shared-memory
+// address of the table entry that decides its next move, found once at the first grid point with the
+// estimate; per (weight, grid point): threshold load, compare, predicated address step, value load
+// (both loads with immediate offsets), sub, mul, fma -- 7 issue slots instead of 14.  The 16
+// per-grid-point partial sums of a block of grid points are reduced across the warp by recursive
+// halving (16 shuffles for 16 sums instead of 80).  Same exact indices, hence the same values and
+// the same chosen grid point.
 constexpr int TAB_MAXC = 16;
 constexpr int TAB_THREADS = 128;
 constexpr int TAB_MAXG = 128;     // grid points per row held in shared memory
