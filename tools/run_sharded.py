@@ -64,6 +64,11 @@ def main():
         sc1 = search_scale_device(W[:rows].contiguous(), cb, H.diagonal().contiguous())
         q1 = quantize_scaled_device(W[:rows].contiguous(), sc1, cb, H)
         ok = bool(torch.equal(sc1, sc[:rows]) and torch.equal(q1, q[:rows]))
+        if world == 1:
+            # the sharded driver takes the row errors from the sweep's residuals: check against the K6 product
+            from sleekit_b200 import ops
+            e6 = float(ops.mean(ops.hweighted_error(W, q, H)))
+            ok = ok and abs(float(err) - e6) <= 1e-4 * abs(e6)
     if rank == 0:
         print(json.dumps({"config": f"[{r},{n}] rows sharded over {world} GPU(s), S={S} samples sharded, "
                                     f"{args.codebook}-entry codebook, diag-H scaling + GPTQ + layer error",
