@@ -191,3 +191,99 @@ def test_pivot_ordering_vs_golden():
     grid = orc.UniformGrid(8, -1, 1)
     np.testing.assert_array_equal(orc.column_order(g["Ws"], g["Hd"], grid, "pivot"), g["order_pivot"])
     np.testing.assert_array_equal(orc.gptq(g["Ws"], g["H"], grid, rule="pivot", damp=0.01), g["gptq_pivot"])
+
+
+# ---------------------------------------------------------------------------
+# The reference's own property tests (tests/test_obq.py), restated on the oracle: they pin the
+# factor, the blocked sweep, the bias removal and the gain formula independently of the golden
+# vectors.
+# ---------------------------------------------------------------------------
+
+
+def _wishart(size, rank, damp=0.0, seed=0):
+    # ref: obq.py:4-11 (random_psd_matrix), seeded here
+    X = np.random.default_rng(seed).standard_normal((size, rank))
+    return X @ X.T / rank + damp * np.eye(size)
+
+
+def test_factor_is_the_cholesky_of_the_inverse():
+    # reference tests/test_obq.py:21-32
+    H = _wishart(4, 6, 1.0e-6, seed=1)
+    gptq_way = np.linalg.cholesky(np.linalg.inv(H)).T
+    U = orc.inverse_upper_factor(H)
+    assert np.allclose(U, gptq_way)
+    assert np.allclose(np.linalg.inv(U.T @ U), H)
+    assert np.allclose(U, np.triu(U)) and U.flags["C_CONTIGUOUS"]
+
+
+def test_blocked_sweep_equals_unblocked_sweep():
+    # reference tests/test_obq.py:57-70
+    size = 64
+    H = _wishart(size, 2, 1.0e-6, seed=2)
+    W = 10.0 * np.random.default_rng(3).standard_normal((1, size))
+    round_to_int = lambda x: np.round(x)  # noqa: E731  (the reference's test quantizer)
+    Q = orc.gptq(W, H, round_to_int, rule="none", leaf=1)
+    for leaf in (3, 4, 7, 8, 63, 64):
+        for fanout in (2, 4):
+            assert np.allclose(Q, orc.gptq(W, H, round_to_int, rule="none", leaf=leaf, fanout=fanout))
+
+
+def test_orderings_improve_the_error():
+    # reference tests/test_obq.py:35-54 (smaller, seeded)
+    size = 200
+    H = _wishart(size, 2, 1.0e-6, seed=4)
+    W = 10.0 * np.random.default_rng(5).standard_normal((10, size))
+    round_to_int = lambda x: np.round(x)  # noqa: E731
+    errs = {rule: orc.mean_error(W.astype(np.float32), orc.gptq(W, H, round_to_int, rule=rule, leaf=size), H.astype(np.float32))
+            for rule in ("diag", "none", "pivot")}
+    direct = orc.mean_error(W.astype(np.float32), np.round(W).astype(np.float32), H.astype(np.float32))
+    assert errs["none"] <= direct
+    assert errs["diag"] <= errs["none"]
+    assert errs["pivot"] <= errs["none"]
+
+
+def test_input_bias_removal_equals_centering_the_samples():
+    # reference tests/test_obq.py:73-109 (the averaged form is the library's)
+    g = np.random.default_rng(6)
+    X = g.standard_normal((16, 32))
+    H = X @ X.T / 32
+    m = X.mean(axis=1)
+    centred = (X - m[:, None]) @ (X - m[:, None]).T / 32
+    assert np.allclose(orc.strip_input_bias(H, m), centred)
+    assert (np.linalg.eigvalsh(orc.strip_input_bias(H, m)) >= -1e-12).all()
+
+
+def test_gain_formula_equals_exhaustive_evaluation():
+    # reference tests/test_obq.py:112-140
+    g = np.random.default_rng(7)
+    W = g.standard_normal((10, 16))
+    H = _wishart(16, 10, seed=8)
+    Q = np.round(W)
+    cand = Q + np.square(g.standard_normal((10, 16)))
+    base = orc.rowwise_error(W, Q, H)
+    exhaustive = np.zeros_like(Q)
+    for i in range(16):
+        cur = Q.copy()
+        cur[:, i] = cand[:, i]
+        exhaustive[:, i] = base - orc.rowwise_error(W, cur, H)
+    assert np.allclose(exhaustive, orc.flip_gain(W, Q, H, cand))
+
+
+def test_scaling_quality_and_modes():
+    # reference tests/test_scaling.py:130-163 (seeded): the Hessian-aware searches may not be worse
+    # under the Hessian-weighted error, and every mode string of the dispatcher is accepted
+    g = np.random.default_rng(9)
+    size = 100
+    data = g.standard_normal((20, size)).astype(np.float32)
+    grid = orc.UniformGrid(9, -3, 3)
+    H = _wishart(size, 10, 1.0e-6, seed=10).astype(np.float32)
+    sc = {"base": orc.search_scale(data, grid, 0), "diag": orc.search_scale(data, grid, 0, H=H.diagonal()),
+          "hessian": orc.search_scale(data, grid, 0, H=H), "obq": orc.search_scale_gptq(data, grid, 0, H)}
+    err = {k: orc.mean_error(data, orc.quantize_scaled(data, s, grid, H=H if k == "obq" else None), H)
+           for k, s in sc.items()}
+    assert err["hessian"] <= err["base"] and err["hessian"] <= err["diag"] and err["obq"] <= err["hessian"]
+    for mode in ("norm", "max", "mse", "diag", "hessian", "diag1", "hessian1", "diag1.8", "hessian1.8"):
+        s = orc.choose_scale(data[:, :20], grid, H[:20, :20], mode=mode)
+        assert s.shape == (20,) and np.all(s > 0)
+    with pytest.raises(RuntimeError):
+        orc.choose_scale(data[:, :20], grid, H[:20, :20], mode="bogus")
