@@ -210,6 +210,47 @@ int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const f
                         void* ws, size_t ws_bytes, float* r32, float* rt_hi, float* rt_lo,
                         float* ud32, int32_t* info, void* stream);
 
+/* The same factorisation for `njobs` matrices of ONE size in one launch sequence: the tile tasks of all
+ * matrices share one ticket queue (ticket t -> matrix t % njobs), so a CTA whose next tile is not ready
+ * works on another matrix instead of spinning -- what a layer set of many small, independent Hessians
+ * needs (experiments/compare.py:50-135 loops over layers; obq.py:38-55 per layer).  Every pointer
+ * argument is a HOST array of njobs device pointers (order / dampval / rt_hi / rt_lo: the array or
+ * single entries may be NULL); ws[k] holds slk_chol_factor_ws_bytes(n) bytes. */
+int slk_chol_factor_batched_f32(int32_t njobs, const float* const* h_host, int64_t n,
+                                const int64_t* const* order_host, const float* const* dampval_host,
+                                void* const* ws_host, float* const* r32_host, float* const* rt_hi_host,
+                                float* const* rt_lo_host, float* const* ud32_host,
+                                int32_t* const* info_host, void* stream);
+
+/* One matrix factored by nranks GPUs of a node (one process per GPU; SURVEY 8 f-3, obq.py:38-55 for
+ * the n = 28672 Hessian of BASELINE config 5).  Tile row i belongs to rank i % nranks; a finished tile
+ * is pushed into every peer's workspace by NVLink peer stores + a system-scope flag, so consumers only
+ * read local memory and the transfer overlaps the arithmetic; no collective inside.  Three
+ * stream-ordered steps; the caller puts a barrier over the ranks ON THE SAME STREAM (an all-reduce of
+ * one element) after the gather (every rank's flags are clear before a peer pushes) and after the
+ * factor (all pushes have landed before the export reads).  ws: slk_chol_factor_ws_bytes(n) bytes from
+ * slk_peer_alloc; peer_ws_host: HOST array of nranks device pointers (slk_peer_open), entry `rank`
+ * being ws itself.  Every rank ends up with the complete factor; info must be max-reduced by the caller. */
+int slk_chol_dist_gather_f32(const float* h, int64_t n, const int64_t* order, const float* dampval,
+                             void* ws, size_t ws_bytes, int32_t* info, void* stream);
+int slk_chol_dist_factor(int64_t n, void* ws, int32_t nranks, int32_t rank, void* const* peer_ws_host,
+                         int32_t* info, void* stream);
+int slk_chol_dist_export_f32(int64_t n, void* ws, float* r32, float* rt_hi, float* rt_lo, float* ud32,
+                             void* stream);
+
+/* Peer-visible device memory for slk_chol_dist_* (CUDA IPC): the only calls of this library that own
+ * device memory.  handle_host: 64 bytes (cudaIpcMemHandle_t) exchanged between the ranks' processes. */
+int slk_peer_alloc(size_t bytes, void** dptr_host, void* handle_host);
+int slk_peer_open(const void* handle_host, void** dptr_host);
+int slk_peer_close(void* dptr);
+int slk_peer_free(void* dptr);
+
+/* Block-upper-triangle packing of a symmetric matrix (layout / size of slk_upload_symmetric_bytes):
+ * the exchange format of the sample-sharded statistics (statistics.py:76-87 summed over ranks): pack
+ * scale * H, all-reduce the packed buffer in place, unpack (+ mirror) into H. */
+int slk_sym_pack_f32(const float* h, int64_t n, int64_t bs, float scale, float* packed, void* stream);
+int slk_sym_unpack_f32(const float* packed, int64_t n, int64_t bs, float scale, float* h, void* stream);
+
 /* Development aid: per-tile-task trace of the Cholesky kernel (8 int64 per task); NULL disables. */
 int slk_debug_chol_trace(void* buf);
 /* Same for the macro-block sweep kernel: 8 int64 phase clocks per 32-column block of CTA 0. */

@@ -468,8 +468,9 @@ def search_scale(data, grid, axis=0, H=None, lo=0.05, hi=1.0, points=100):
     )
 
 
-def search_scale_gptq(data, grid, axis, H, damp=0.01, rule="diag", lo=0.05, hi=1.0, points=100):
-    # ref: scaling.py:137-190
+def gptq_scale_evaluator(data, grid, axis, H, damp=0.01, rule="diag"):
+    # ref: scaling.py:137-177 -- (base scales, evaluate) where evaluate(scales) is the per-row error of
+    # one sweep at those scales, with the ordering and the factor shared by all grid points
     rest = tuple(i for i in range(data.ndim) if i != axis)
     W = np.transpose(data, [axis, *rest])
     base = no_clip_scale(W, grid, 0)
@@ -478,7 +479,6 @@ def search_scale_gptq(data, grid, axis, H, damp=0.01, rule="diag", lo=0.05, hi=1
     W = W[:, perm]
     H = H[perm][:, perm]
     U = inverse_upper_factor(Hd[perm][:, perm])
-    factors = np.linspace(lo, hi, points, dtype=np.float32)
 
     def evaluate(s):
         Q = divide_rows(W, s, 0)
@@ -487,6 +487,13 @@ def search_scale_gptq(data, grid, axis, H, damp=0.01, rule="diag", lo=0.05, hi=1
         Q = divide_rows(Q, 1 / s, 0)
         return weighted_sq_error(H, Q - W)
 
+    return base, evaluate
+
+
+def search_scale_gptq(data, grid, axis, H, damp=0.01, rule="diag", lo=0.05, hi=1.0, points=100):
+    # ref: scaling.py:137-190
+    base, evaluate = gptq_scale_evaluator(data, grid, axis, H, damp, rule)
+    factors = np.linspace(lo, hi, points, dtype=np.float32)
     return _grid_argmin(base, factors, evaluate)
 
 

@@ -77,6 +77,16 @@ SIGNATURES = {
     "slk_hinv_from_f64": (_INT, [_P, _I64, _P, _SZ, _P, _P, _P, _P]),
     "slk_chol_factor_ws_bytes": (_SZ, [_I64]),
     "slk_chol_factor_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
+    "slk_chol_factor_batched_f32": (_INT, [_I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "slk_chol_dist_gather_f32": (_INT, [_P, _I64, _P, _P, _P, _SZ, _P, _P]),
+    "slk_chol_dist_factor": (_INT, [_I64, _P, _I32, _I32, _P, _P, _P]),
+    "slk_chol_dist_export_f32": (_INT, [_I64, _P, _P, _P, _P, _P, _P]),
+    "slk_peer_alloc": (_INT, [_SZ, _P, _P]),
+    "slk_peer_open": (_INT, [_P, _P]),
+    "slk_peer_close": (_INT, [_P]),
+    "slk_peer_free": (_INT, [_P]),
+    "slk_sym_pack_f32": (_INT, [_P, _I64, _I64, C.c_float, _P, _P]),
+    "slk_sym_unpack_f32": (_INT, [_P, _I64, _I64, C.c_float, _P, _P]),
     "slk_gptq_sweep_r_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_codebook_breaks_host": (_INT, [_CB, _P]),
     "slk_debug_chol_trace": (_INT, [_P]),

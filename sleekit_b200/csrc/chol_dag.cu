@@ -19,6 +19,20 @@
 // a CTA that is already running, so the scheme cannot deadlock whatever else shares the GPU and
 // however few CTAs are resident (the decoupled look-back argument).  No dependent launches: the
 // n/64-panel launch chain of the right-looking version (hinv.cu) becomes in-kernel flag latency.
+//
+// Two generalisations of the same kernel (round 2):
+//  * BATCH (slk_chol_factor_batched_f32): several matrices of one size share ONE ticket queue, ticket t
+//    -> (matrix t % B, task t / B).  A CTA whose next tile is not ready is then almost always handed a
+//    tile of another matrix instead of spinning: the 72 layers of an OPT-125M pass are bound by the
+//    FP64 pipe instead of by 72 separate chains of diagonal tiles that each hold SM slots while they wait.
+//  * MULTI-GPU (slk_chol_factor_dist_f32): tile row i belongs to rank i % P; a rank runs the tile
+//    tasks of its own rows in the same column-major order and PUSHES every finished tile (and the
+//    inverse of a diagonal tile) into the same place of every peer's workspace through NVLink peer
+//    stores, followed by a system-scope release of the tile's flag on that peer.  Consumers only ever
+//    read local memory and local flags.  No collective inside the factorisation, the transfer of
+//    tile (i, j) overlaps the arithmetic of every other tile, and the deadlock argument above carries
+//    over (a task still only waits for tasks that precede it in the global column-major order, and
+//    every rank works through its own tasks in that order).
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -51,9 +65,38 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void wait_ready(const int* flag) {
-  while (ld_acquire_gpu(flag) == 0) __nanosleep(32);
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <bool MULTI>
+__device__ __forceinline__ void wait_ready(const int* flag) {
+  if (MULTI) { while (ld_acquire_sys(flag) == 0) __nanosleep(64); }
+  else { while (ld_acquire_gpu(flag) == 0) __nanosleep(32); }
+}
+
+constexpr int CHOL_MAXJ = 64;     // matrices per batched launch
+constexpr int CHOL_MAXP = 8;      // ranks of a distributed factorisation
+
+// One launch: `njobs` matrices of T x T tiles (workspaces laid out as chol_ws_layout says), or ONE
+// matrix shared by `nranks` GPUs (peer[q] = base of rank q's workspace, same layout, peer-mapped).
+struct CholDagParams {
+  int njobs, T;
+  int nranks, rank;
+  int64_t ld;
+  int* ticket;
+  double* A[CHOL_MAXJ];
+  double* Dinv[CHOL_MAXJ];
+  int* ready[CHOL_MAXJ];
+  int32_t* info[CHOL_MAXJ];
+  double* peerA[CHOL_MAXP];
+  double* peerDinv[CHOL_MAXP];
+  int* peerReady[CHOL_MAXP];
+};
 __device__ __forceinline__ void cd_cp16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
                : "memory");
@@ -68,16 +111,28 @@ __device__ __forceinline__ void cd_dmma(double (&c)[2], double a, double b) {
 // flipped index i <-> sweep column npad-1-i, so that 32-column sweep blocks coincide with 32-row
 // blocks of the factor for every n.  Also clears the flags, the ticket and info.
 template <typename TS>
-__global__ void __launch_bounds__(256) chol_gather_kernel(const TS* __restrict__ h, int64_t n, int64_t npad,
-                                                          const int64_t* __restrict__ order,
-                                                          const float* __restrict__ dampval, double* __restrict__ A,
-                                                          int* __restrict__ flags, int64_t nflags,
-                                                          int32_t* __restrict__ info) {
+struct CholGatherParams {
+  const TS* h[CHOL_MAXJ];
+  const int64_t* order[CHOL_MAXJ];
+  const float* dampval[CHOL_MAXJ];
+  double* A[CHOL_MAXJ];
+  int* flags[CHOL_MAXJ];
+  int32_t* info[CHOL_MAXJ];
+};
+
+template <typename TS>
+__global__ void __launch_bounds__(256) chol_gather_kernel(const __grid_constant__ CholGatherParams<TS> P, int64_t n,
+                                                          int64_t npad, int64_t nflags) {
+  const int job = blockIdx.y;
+  const TS* __restrict__ h = P.h[job];
+  const int64_t* __restrict__ order = P.order[job];
+  double* __restrict__ A = P.A[job];
+  int* __restrict__ flags = P.flags[job];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t t = t0; t < nflags; t += stride) flags[t] = 0;
-  if (t0 == 0) *info = 0;
-  const double damp = dampval ? (double)dampval[0] : 0.0;
+  if (t0 == 0) *P.info[job] = 0;
+  const double damp = P.dampval[job] ? (double)P.dampval[job][0] : 0.0;
   const int64_t total = npad * npad;
   for (int64_t t = t0; t < total; t += stride) {
     const int64_t i = t / npad, j = t - i * npad;
@@ -277,35 +332,46 @@ __device__ __forceinline__ long long gtimer() {
 }
 
 // ---- the tile-task kernel ----------------------------------------------------------------------------
-// A: [T*64, ld] fp64, lower triangle in, L out.  Dinv: [T, 64, 64] inverses of the diagonal tiles.
-// sync: [T*T] ready flags followed by the ticket counter.
-__global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A, int64_t ld, int T,
-                                                          double* __restrict__ Dinv, int* __restrict__ sync,
-                                                          int32_t* __restrict__ info) {
+// Per matrix: A [T*64, ld] fp64, lower triangle in, L out; Dinv [T, 64, 64] inverses of the diagonal
+// tiles; ready [T*T] flags.  P.ticket: the launch's ticket counter.
+// Ticket t -> matrix t % njobs, local ticket t / njobs; local tickets enumerate, column by column, the
+// tiles (i, j), i >= j, whose row this rank owns (i % nranks == rank; every row when nranks == 1).
+template <bool MULTI>
+__global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant__ CholDagParams P) {
   extern __shared__ __align__(16) unsigned char chol_raw[];
   CholSmem& sm = *reinterpret_cast<CholSmem*>(chol_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;
   const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
-  int* ready = sync;
-  int* ticket = sync + (int64_t)T * T;
-  const int ntasks = T * (T + 1) / 2;
+  const int T = P.T;
+  const int64_t ld = P.ld;
+  const int NR = MULTI ? P.nranks : 1, RK = MULTI ? P.rank : 0;
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
+    if (tid == 0) sm.ticket = atomicAdd(P.ticket, 1);
     __syncthreads();
-    const int t = sm.ticket;
-    if (t >= ntasks) return;
-    int j = 0, rem = t;
-    while (rem >= T - j) { rem -= T - j; ++j; }
-    const int i = j + rem;
+    const int tk = sm.ticket;
+    const int job = MULTI ? 0 : tk % P.njobs;
+    int rem = MULTI ? tk : tk / P.njobs;
+    int j = 0, i = 0;
+    for (;; ++j) {
+      if (j >= T) return;                                   // past this rank's last task
+      int first = j + (RK - j % NR + NR) % NR;              // first owned row at or below the diagonal
+      const int cnt = first < T ? (T - 1 - first) / NR + 1 : 0;
+      if (rem < cnt) { i = first + rem * NR; break; }
+      rem -= cnt;
+    }
     const bool diag = (i == j);
-    long long* tr = (g_chol_trace && tid == 0) ? g_chol_trace + (int64_t)t * 16 : nullptr;
+    double* __restrict__ A = P.A[job];
+    double* __restrict__ Dinv = P.Dinv[job];
+    int* ready = P.ready[job];
+    long long* tr = (g_chol_trace && tid == 0) ? g_chol_trace + (int64_t)tk * 16 : nullptr;
     if (tr) { tr[0] = i; tr[1] = j; tr[2] = gtimer(); tr[4] = clock64(); }
     const double* Ai = A + (int64_t)i * CT * ld;
     const double* Aj = A + (int64_t)j * CT * ld;
-    double* Cij = A + (int64_t)i * CT * ld + (int64_t)j * CT;
+    const int64_t tile_off = (int64_t)i * CT * ld + (int64_t)j * CT;
+    double* Cij = A + tile_off;
 
     // the tile itself, in accumulator-fragment layout (rows wm+8ii+fr, columns wn+8jj+2fk, +1)
     double2 cij[4][2];
@@ -335,8 +401,8 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
     };
     if (nt > 0) {
       if (tid == 0) {
-        wait_ready(ready + (int64_t)i * T);
-        if (!diag) wait_ready(ready + (int64_t)j * T);
+        wait_ready<MULTI>(ready + (int64_t)i * T);
+        if (!diag) wait_ready<MULTI>(ready + (int64_t)j * T);
       }
       __syncthreads();
     }
@@ -347,8 +413,8 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
     for (int s = 0; s < nt; ++s) {
       const int sn = s + CST - 1;
       if (tid == 0 && sn < nt && (sn & 3) == 0) {
-        wait_ready(ready + (int64_t)i * T + (sn >> 2));
-        if (!diag) wait_ready(ready + (int64_t)j * T + (sn >> 2));
+        wait_ready<MULTI>(ready + (int64_t)i * T + (sn >> 2));
+        if (!diag) wait_ready<MULTI>(ready + (int64_t)j * T + (sn >> 2));
       }
       asm volatile("cp.async.wait_group %0;" ::"n"(CST - 2) : "memory");
       __syncthreads();
@@ -383,18 +449,35 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
           sm.f.M[(col + 1) * CP + row] = __dsub_rn(cij[ii][jj].y, acc[ii][jj][1]);
         }
       __syncthreads();
-      chol_factor_tile(sm, tid, info, (int64_t)j * CT, tr);
+      chol_factor_tile(sm, tid, P.info[job], (int64_t)j * CT, tr);
       // X_j is what the panel solves below wait for: publish it first; L(j,j) itself is only read
       // by the export kernel after this launch
-      double* Xg = Dinv + (int64_t)j * CT * CT;
-      for (int e = tid; e < CT * CT; e += CTH) Xg[e] = sm.f.X[(e >> 6) * CP + (e & 63)];
-      // publish: the CTA barrier orders every thread's stores before thread 0's release store, and a
-      // gpu-scope release is cumulative -- no per-thread fence (the pattern of a split-K semaphore)
-      __syncthreads();
-      if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
-      for (int e = tid; e < CT * CT; e += CTH) {
-        const int r = e >> 6, c = e & 63;
-        Cij[(int64_t)r * ld + c] = (r >= c) ? sm.f.M[c * CP + r] : 0.0;
+      const int64_t xoff = (int64_t)j * CT * CT;
+      if (MULTI) {
+        for (int e = tid; e < CT * CT / 2; e += CTH) {
+          const int r = e >> 5, c2 = (e & 31) * 2;
+          const double2 v = *reinterpret_cast<const double2*>(&sm.f.X[r * CP + c2]);
+          for (int q = 0; q < NR; ++q) *reinterpret_cast<double2*>(P.peerDinv[q] + xoff + r * CT + c2) = v;
+        }
+        __threadfence_system();     // every writer orders its peer stores before the flags below
+        __syncthreads();
+        if (tid < NR) st_release_sys(P.peerReady[tid] + (int64_t)i * T + j, 1);
+        for (int e = tid; e < CT * CT; e += CTH) {
+          const int r = e >> 6, c = e & 63;
+          const double v = (r >= c) ? sm.f.M[c * CP + r] : 0.0;
+          for (int q = 0; q < NR; ++q) P.peerA[q][tile_off + (int64_t)r * ld + c] = v;
+        }
+      } else {
+        double* Xg = Dinv + xoff;
+        for (int e = tid; e < CT * CT; e += CTH) Xg[e] = sm.f.X[(e >> 6) * CP + (e & 63)];
+        // publish: the CTA barrier orders every thread's stores before thread 0's release store, and a
+        // gpu-scope release is cumulative -- no per-thread fence (the pattern of a split-K semaphore)
+        __syncthreads();
+        if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
+        for (int e = tid; e < CT * CT; e += CTH) {
+          const int r = e >> 6, c = e & 63;
+          Cij[(int64_t)r * ld + c] = (r >= c) ? sm.f.M[c * CP + r] : 0.0;
+        }
       }
       if (tr) { tr[6] = clock64(); tr[7] = tr[6]; tr[3] = gtimer(); }
       continue;
@@ -410,7 +493,7 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
           v.y = __dsub_rn(cij[ii][jj].y, acc[ii][jj][1]);
           *reinterpret_cast<double2*>(&sm.f.M[row * CP + col]) = v;
         }
-      if (tid == 0) wait_ready(ready + (int64_t)j * T + j);
+      if (tid == 0) wait_ready<MULTI>(ready + (int64_t)j * T + j);
       __syncthreads();
       const double* Xg = Dinv + (int64_t)j * CT * CT;
 #pragma unroll
@@ -438,17 +521,42 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) cd_dmma(out[ii][jj], a[ii], b[jj]);
       }
+      if (MULTI) {
+        // stage the tile in shared memory so that the pushes to the peers are row-contiguous 16-byte
+        // stores (a warp writes one 512-byte row of the tile per instruction)
+        __syncthreads();                                   // every warp is done reading M and X
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
+        for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
-          *reinterpret_cast<double2*>(Cij + (int64_t)row * ld + col) = make_double2(out[ii][jj][0], out[ii][jj][1]);
+          for (int jj = 0; jj < 2; ++jj) {
+            const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+            *reinterpret_cast<double2*>(&sm.f.M[row * CP + col]) = make_double2(out[ii][jj][0], out[ii][jj][1]);
+          }
+        __syncthreads();
+        for (int e = tid; e < CT * CT / 2; e += CTH) {
+          const int r = e >> 5, c2 = (e & 31) * 2;
+          const double2 v = *reinterpret_cast<const double2*>(&sm.f.M[r * CP + c2]);
+          for (int q = 0; q < NR; ++q)
+            *reinterpret_cast<double2*>(P.peerA[q] + tile_off + (int64_t)r * ld + c2) = v;
         }
+        __threadfence_system();
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+            *reinterpret_cast<double2*>(Cij + (int64_t)row * ld + col) = make_double2(out[ii][jj][0], out[ii][jj][1]);
+          }
+      }
     }
     if (tr) tr[6] = clock64();
     __syncthreads();
-    if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
+    if (MULTI) {
+      if (tid < NR) st_release_sys(P.peerReady[tid] + (int64_t)i * T + j, 1);
+    } else {
+      if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
+    }
     if (tr) { tr[7] = clock64(); tr[3] = gtimer(); }
   }
 }
@@ -456,13 +564,27 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(double* __restrict__ A
 // R32[a, b] = L[npad-1-a, npad-1-b] for b >= a (0 below); rt_hi + rt_lo = R32^T on and below its
 // diagonal, split into TF32 parts (the part above is never read and left untouched); Ud[blk][p][q] = inverse of the 32x32 diagonal
 // block R[32blk.., 32blk..] = flip of the matching diagonal block of the tile inverses.
-// One CTA per 32x32 tile pair (ta <= tb); the transpose goes through shared memory so that all
-// global accesses are coalesced.
-__global__ void __launch_bounds__(256) chol_export_kernel(const double* __restrict__ A, int64_t n, int64_t npad,
-                                                          const double* __restrict__ Dinv, float* __restrict__ r32,
-                                                          float* __restrict__ rt_hi, float* __restrict__ rt_lo,
-                                                          float* __restrict__ ud32) {
+// One CTA per 32x32 tile pair (ta <= tb) and matrix (blockIdx.y); the transpose goes through shared
+// memory so that all global accesses are coalesced.
+struct CholExportParams {
+  const double* A[CHOL_MAXJ];
+  const double* Dinv[CHOL_MAXJ];
+  float* r32[CHOL_MAXJ];
+  float* rt_hi[CHOL_MAXJ];
+  float* rt_lo[CHOL_MAXJ];
+  float* ud32[CHOL_MAXJ];
+};
+
+__global__ void __launch_bounds__(256) chol_export_kernel(const __grid_constant__ CholExportParams P, int64_t n,
+                                                          int64_t npad) {
   __shared__ float tile[32][33];
+  const int job = blockIdx.y;
+  const double* __restrict__ A = P.A[job];
+  const double* __restrict__ Dinv = P.Dinv[job];
+  float* __restrict__ r32 = P.r32[job];
+  float* __restrict__ rt_hi = P.rt_hi[job];
+  float* __restrict__ rt_lo = P.rt_lo[job];
+  float* __restrict__ ud32 = P.ud32[job];
   const int64_t nt = (n + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   // linear block id -> (ta, tb), tb >= ta
@@ -504,46 +626,116 @@ __global__ void __launch_bounds__(256) chol_export_kernel(const double* __restri
 
 static inline int64_t cpad64(int64_t n) { return (n + CT - 1) / CT * CT; }
 
-template <typename TS>
-static int chol_factor_impl(const TS* h, int64_t n, const int64_t* order, const float* dampval, void* ws, size_t ws_bytes,
-                            float* r32, float* rt_hi, float* rt_lo, float* ud32, int32_t* info, cudaStream_t st) {
-  SLK_REQUIRE(h && info && r32 && ud32 && n >= 1, "bad arguments");
-  SLK_REQUIRE(ws && ws_bytes >= slk_chol_factor_ws_bytes(n), "workspace too small");
+// workspace of one matrix: A [npad, npad] fp64 | Dinv [T, 64, 64] fp64 | ready [T*T] int | ticket
+struct ChWs { double* A; double* Dinv; int* ready; int* ticket; };
+static inline ChWs chol_ws_layout(void* ws, int64_t n) {
+  const int64_t npad = cpad64(n), T = npad / CT;
+  ChWs w;
+  w.A = (double*)ws;
+  w.Dinv = w.A + npad * npad;
+  w.ready = (int*)(w.Dinv + T * CT * CT);
+  w.ticket = w.ready + T * T;
+  return w;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* ev = getenv(name);
+  return ev ? atoi(ev) : dflt;
+}
+
+// (1) gather: flip + permutation + damp into the fp64 workspaces; clears flags, tickets and info
+static int chol_gather(int njobs, const float* const* h, int64_t n, const int64_t* const* order,
+                       const float* const* dampval, void* const* ws, int32_t* const* info, cudaStream_t st) {
+  const int64_t npad = cpad64(n), T = npad / CT;
+  CholGatherParams<float> G;
+  for (int k = 0; k < njobs; ++k) {
+    const ChWs w = chol_ws_layout(ws[k], n);
+    G.h[k] = h[k]; G.order[k] = order ? order[k] : nullptr; G.dampval[k] = dampval ? dampval[k] : nullptr;
+    G.A[k] = w.A; G.flags[k] = w.ready; G.info[k] = info[k];
+  }
+  const int64_t cap = (int64_t)sm_count() * 16 / (njobs > 16 ? 16 : njobs) + 1;
+  int64_t blocks = ceil_div(npad * npad, 256);
+  dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)njobs);
+  chol_gather_kernel<float><<<grid, 256, 0, st>>>(G, n, npad, T * T + 1);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+// (2) the tile-task kernel over `njobs` matrices (nranks == 1) or one matrix over nranks GPUs
+static int chol_dag(int njobs, int64_t n, void* const* ws, int32_t* const* info, int nranks, int rank,
+                    void* const* peer_ws, cudaStream_t st) {
   const int64_t npad = cpad64(n);
   const int T = (int)(npad / CT);
-  double* A = (double*)ws;
-  double* Dinv = A + npad * npad;
-  int* sync = (int*)(Dinv + (int64_t)T * CT * CT);
-  const int64_t nflags = (int64_t)T * T + 1;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  int64_t blocks = ceil_div(npad * npad, 256);
-  chol_gather_kernel<TS><<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(h, n, npad, order, dampval, A, sync,
-                                                                              nflags, info);
-  SLK_LAUNCH_CHECK();
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLK_CUDA(cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
-    attr_done = true;
+  CholDagParams P;
+  P.njobs = njobs; P.T = T; P.nranks = nranks; P.rank = rank; P.ld = npad;
+  for (int k = 0; k < njobs; ++k) {
+    const ChWs w = chol_ws_layout(ws[k], n);
+    P.A[k] = w.A; P.Dinv[k] = w.Dinv; P.ready[k] = w.ready; P.info[k] = info[k];
+    if (k == 0) P.ticket = w.ticket;
   }
-  const int64_t ntasks = (int64_t)T * (T + 1) / 2;
-  // CTAs: a small factorisation is bound by the chain of diagonal tiles, not by the number of CTAs
-  // (n = 768: the same 0.28 ms with 11 to 26 CTAs), and every CTA beyond the useful ones only holds
-  // an SM slot while it spins; mid-sized ones get 1.5 CTAs per tile row (n = 3072: 1.14 ms with 2 per
-  // row, 1.29 ms with 1.5, 1.65 ms with 1), n >= 4096 -- bound by the FP64 pipe, and big enough to
-  // own the GPU -- 2 per row.  SLK_CHOL_GRID overrides the percentage (experiments).
-  static int grid_pct = -1;
-  if (grid_pct < 0) {
-    const char* ev = getenv("SLK_CHOL_GRID");
-    grid_pct = ev ? atoi(ev) : 0;
+  for (int q = 0; q < nranks && nranks > 1; ++q) {
+    const ChWs w = chol_ws_layout(peer_ws[q], n);
+    P.peerA[q] = w.A; P.peerDinv[q] = w.Dinv; P.peerReady[q] = w.ready;
   }
-  const int pct = grid_pct >= 50 ? grid_pct : (T <= 16 ? 100 : (T < 64 ? 150 : 200));
-  int64_t grid = (int64_t)T * pct / 100 + 2;
+  const int64_t ntasks = (int64_t)njobs * T * (T + 1) / 2;
+  const int64_t sms = sm_count();
+  int64_t grid;
+  size_t smem = sizeof(CholSmem);
+  if (nranks > 1) {
+    // every rank owns ~1/P of the tasks of every column; the FP64 pipe is the bound
+    grid = 2 * sms;
+  } else if (njobs == 1) {
+    // CTAs: a small factorisation is bound by the chain of diagonal tiles, not by the number of CTAs
+    // (n = 768: the same 0.28 ms with 11 to 26 CTAs), and every CTA beyond the useful ones only holds
+    // an SM slot while it spins; mid-sized ones get 1.5 CTAs per tile row (n = 3072: 1.14 ms with 2 per
+    // row, 1.29 ms with 1.5, 1.65 ms with 1), n >= 4096 -- bound by the FP64 pipe, and big enough to
+    // own the GPU -- 2 per row.  SLK_CHOL_GRID overrides the percentage (experiments).
+    static int grid_pct = -2;
+    if (grid_pct == -2) grid_pct = env_int("SLK_CHOL_GRID", 0);
+    const int pct = grid_pct >= 50 ? grid_pct : (T <= 16 ? 100 : (T < 64 ? 150 : 200));
+    grid = (int64_t)T * pct / 100 + 2;
+    if (grid > 2 * sms) grid = 2 * sms;
+  } else {
+    // batch: CTAs do not spin (the next ticket is another matrix's tile), so the grid is a throughput
+    // choice.  Default ONE CTA per SM with the dynamic shared memory padded past half an SM's, which
+    // leaves half of the register file and ~110 KB of shared memory of every SM to the latency-bound
+    // sweeps and the issue-bound scale searches of the other layers that run beside the factorisations
+    // (SLK_CHOL_BATCH_CTAS: CTAs per SM x 100; SLK_CHOL_BATCH_SMEM_KB: dynamic shared memory per CTA).
+    static int ctas_pct = -2, smem_kb = -2;
+    if (ctas_pct == -2) ctas_pct = env_int("SLK_CHOL_BATCH_CTAS", 100);
+    if (smem_kb == -2) smem_kb = env_int("SLK_CHOL_BATCH_SMEM_KB", 116);
+    grid = sms * ctas_pct / 100;
+    if (grid < 1) grid = 1;
+    if ((size_t)smem_kb * 1024 > smem) smem = (size_t)smem_kb * 1024;
+    if (smem > 227 * 1024) smem = 227 * 1024;
+  }
   if (grid > ntasks) grid = ntasks;
-  if (grid > 2 * (int64_t)sm_count()) grid = 2 * (int64_t)sm_count();
-  chol_dag_kernel<<<(unsigned)grid, CTH, sizeof(CholSmem), st>>>(A, npad, T, Dinv, sync, info);
+  if (nranks > 1) {
+    SLK_CUDA(cudaFuncSetAttribute(chol_dag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chol_dag_kernel<true><<<(unsigned)grid, CTH, smem, st>>>(P);
+  } else {
+    SLK_CUDA(cudaFuncSetAttribute(chol_dag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    chol_dag_kernel<false><<<(unsigned)grid, CTH, smem, st>>>(P);
+  }
   SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+// (3) export: R (fp32), R^T as TF32 parts, 32x32 diagonal-block inverses
+static int chol_export(int njobs, int64_t n, void* const* ws, float* const* r32, float* const* rt_hi,
+                       float* const* rt_lo, float* const* ud32, cudaStream_t st) {
+  const int64_t npad = cpad64(n);
+  CholExportParams E;
+  for (int k = 0; k < njobs; ++k) {
+    const ChWs w = chol_ws_layout(ws[k], n);
+    E.A[k] = w.A; E.Dinv[k] = w.Dinv; E.r32[k] = r32[k]; E.ud32[k] = ud32[k];
+    const bool split = rt_hi && rt_lo && rt_hi[k] && rt_lo[k];
+    E.rt_hi[k] = split ? rt_hi[k] : nullptr;
+    E.rt_lo[k] = split ? rt_lo[k] : nullptr;
+  }
   const int64_t nt32 = (n + 31) / 32;
-  chol_export_kernel<<<(unsigned)(nt32 * (nt32 + 1) / 2), 256, 0, st>>>(A, n, npad, Dinv, r32, rt_lo ? rt_hi : nullptr, rt_lo, ud32);
+  dim3 grid((unsigned)(nt32 * (nt32 + 1) / 2), (unsigned)njobs);
+  chol_export_kernel<<<grid, 256, 0, st>>>(E, n, npad);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
@@ -570,7 +762,63 @@ size_t slk_chol_factor_ws_bytes(int64_t n) {
 int slk_chol_factor_f32(const float* h, int64_t n, const int64_t* order, const float* dampval, void* ws,
                         size_t ws_bytes, float* r32, float* rt_hi, float* rt_lo, float* ud32, int32_t* info,
                         void* stream) {
-  return chol_factor_impl<float>(h, n, order, dampval, ws, ws_bytes, r32, rt_hi, rt_lo, ud32, info, (cudaStream_t)stream);
+  SLK_REQUIRE(h && info && r32 && ud32 && n >= 1, "bad arguments");
+  SLK_REQUIRE(ws && ws_bytes >= slk_chol_factor_ws_bytes(n), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = chol_gather(1, &h, n, &order, &dampval, &ws, &info, st))) return rc;
+  if ((rc = chol_dag(1, n, &ws, &info, 1, 0, nullptr, st))) return rc;
+  return chol_export(1, n, &ws, &r32, &rt_hi, &rt_lo, &ud32, st);
+}
+
+/* The same factorisation for `njobs` matrices of ONE size n in one launch sequence (gather, tile-task
+   kernel with a shared ticket queue, export).  Every argument is a HOST array of njobs device pointers
+   (order / dampval / rt_hi / rt_lo: the array or single entries may be NULL); ws[k] holds
+   slk_chol_factor_ws_bytes(n) bytes.  More than 64 matrices are processed in launches of 64. */
+int slk_chol_factor_batched_f32(int32_t njobs, const float* const* h, int64_t n, const int64_t* const* order,
+                                const float* const* dampval, void* const* ws, float* const* r32,
+                                float* const* rt_hi, float* const* rt_lo, float* const* ud32, int32_t* const* info,
+                                void* stream) {
+  SLK_REQUIRE(njobs >= 1 && h && ws && r32 && ud32 && info && n >= 1, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int k0 = 0; k0 < njobs; k0 += CHOL_MAXJ) {
+    const int nb = (njobs - k0) < CHOL_MAXJ ? (njobs - k0) : CHOL_MAXJ;
+    for (int k = k0; k < k0 + nb; ++k) SLK_REQUIRE(h[k] && ws[k] && r32[k] && ud32[k] && info[k], "NULL pointer in job %d", k);
+    int rc;
+    if ((rc = chol_gather(nb, h + k0, n, order ? order + k0 : nullptr, dampval ? dampval + k0 : nullptr, ws + k0, info + k0, st)))
+      return rc;
+    if ((rc = chol_dag(nb, n, ws + k0, info + k0, 1, 0, nullptr, st))) return rc;
+    if ((rc = chol_export(nb, n, ws + k0, r32 + k0, rt_hi ? rt_hi + k0 : nullptr, rt_lo ? rt_lo + k0 : nullptr, ud32 + k0, st)))
+      return rc;
+  }
+  return SLK_OK;
+}
+
+/* One matrix factored by `nranks` GPUs (one process each).  Three stream-ordered steps; the caller
+   separates them with a barrier over the ranks ON THE SAME STREAM (e.g. an NCCL all-reduce of one
+   element): after slk_chol_dist_gather_f32 (every rank's flags are cleared before any peer pushes a
+   tile) and after slk_chol_dist_factor (every peer's pushes have landed before the export reads them).
+   ws: this rank's workspace (slk_chol_factor_ws_bytes(n) bytes) in memory the peers can write
+   (slk_peer_alloc + slk_peer_open); peer_ws: HOST array of nranks device pointers, peer_ws[rank] == ws.
+   Every rank gathers the full matrix, factors the tile rows i with i % nranks == rank, and ends up
+   holding the complete factor, so the export (and everything after it) is local. */
+int slk_chol_dist_gather_f32(const float* h, int64_t n, const int64_t* order, const float* dampval, void* ws,
+                             size_t ws_bytes, int32_t* info, void* stream) {
+  SLK_REQUIRE(h && info && n >= 1, "bad arguments");
+  SLK_REQUIRE(ws && ws_bytes >= slk_chol_factor_ws_bytes(n), "workspace too small");
+  return chol_gather(1, &h, n, &order, &dampval, &ws, &info, (cudaStream_t)stream);
+}
+
+int slk_chol_dist_factor(int64_t n, void* ws, int32_t nranks, int32_t rank, void* const* peer_ws, int32_t* info,
+                         void* stream) {
+  SLK_REQUIRE(ws && info && n >= 1 && nranks >= 1 && nranks <= CHOL_MAXP && rank >= 0 && rank < nranks, "bad arguments");
+  SLK_REQUIRE(nranks == 1 || (peer_ws && peer_ws[rank] == ws), "peer_ws[rank] must be this rank's workspace");
+  return chol_dag(1, n, &ws, &info, nranks, rank, peer_ws, (cudaStream_t)stream);
+}
+
+int slk_chol_dist_export_f32(int64_t n, void* ws, float* r32, float* rt_hi, float* rt_lo, float* ud32, void* stream) {
+  SLK_REQUIRE(ws && r32 && ud32 && n >= 1, "bad arguments");
+  return chol_export(1, n, &ws, &r32, &rt_hi, &rt_lo, &ud32, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -44,7 +44,20 @@ void note_launch();  // bumps the process-wide kernel-launch counter (slk_launch
     }                                                                              \
   } while (0)
 
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device)
+
+// One-time cudaFuncSetAttribute(MaxDynamicSharedMemorySize) PER DEVICE: the attribute belongs to the
+// device's context, so a process that works on several GPUs must set it on each of them.
+#define SLK_SMEM_ATTR_ONCE(kern, bytes)                                                              \
+  do {                                                                                               \
+    static unsigned long long done__ = 0;                                                            \
+    int dev__ = 0;                                                                                   \
+    SLK_CUDA(cudaGetDevice(&dev__));                                                                 \
+    if (!((done__ >> (dev__ & 63)) & 1ull)) {                                                        \
+      SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      done__ |= 1ull << (dev__ & 63);                                                                \
+    }                                                                                                \
+  } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -155,11 +155,7 @@ template <bool B_T, int EPI>
 static inline int dgemm_mma_launch(const GemmParams<double>& p, int batch, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return SLK_OK;
   auto kern = dgemm_mma_kernel<B_T, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DmSmem)));
-    attr_done = true;
-  }
+  SLK_SMEM_ATTR_ONCE(kern, (int)sizeof(DmSmem));
   dim3 grid((unsigned)(p.N / DM_BN), (unsigned)(p.M / DM_BM), (unsigned)batch);
   kern<<<grid, 128, sizeof(DmSmem), st>>>(p);
   SLK_LAUNCH_CHECK();

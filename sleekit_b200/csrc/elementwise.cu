@@ -3,6 +3,7 @@
 // All of them are one pass over their input, 128-bit vectorised where the layout allows,
 // with grids sized in multiples of the SM count.
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <stdarg.h>
 
@@ -21,16 +22,12 @@ static long long g_launches = 0;
 void note_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
-  }
-  return cached;
+  static int cached[64] = {0};
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& c = cached[dev & 63];
+  if (c == 0) c = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  return c;
 }
 
 static inline int stream_grid(int64_t work_items, int per_block, int max_waves = 8) {
@@ -64,6 +61,37 @@ __device__ __forceinline__ void round_one(const DevGrid<T>& g, T x, int mode, VT
       else if (idx_bytes == 2) ((uint16_t*)out_idx)[i] = (uint16_t)k;
       else ((uint32_t*)out_idx)[i] = (uint32_t)k;
     }
+  }
+}
+
+// Index-only nearest rounding through the codebook's exact breakpoints (uniform codebooks of <= 8
+// entries): idx(w) >= k  <=>  w >= X[k]  with X found on the host by bisection over the reference's own
+// op chain (make_breaks), so a 3-level compare tree gives the reference's index bit for bit -- 9
+// instructions per value instead of ~17 (subtract, exact divide, rint, two clips, float->int, pack);
+// NaN compares false everywhere and yields 0, as the conversion of the clipped NaN does.
+// 16 values per thread and step: four 128-bit loads in flight, one 128-bit store.
+__global__ void __launch_bounds__(256) round_f32_index_tree_kernel(const float4* __restrict__ x, int64_t nquad,
+                                                                   GridBreaks brk, int size,
+                                                                   uint4* __restrict__ out_idx8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float X[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) X[k] = (k >= 1 && k < size) ? brk.X[k] : __int_as_float(0x7f800000);   // +inf: never reached
+  auto idx = [&](float w) -> uint32_t {
+    const bool b2 = w >= X[4];
+    const float t1 = b2 ? X[6] : X[2];
+    const float xa = b2 ? X[7] : X[3], xb = b2 ? X[5] : X[1];
+    const bool b1 = w >= t1;
+    const float t0 = b1 ? xa : xb;
+    const bool b0 = w >= t0;
+    return (b2 ? 4u : 0u) + (b1 ? 2u : 0u) + (b0 ? 1u : 0u);
+  };
+  auto pack = [&](const float4& v) -> uint32_t {
+    return idx(v.x) | (idx(v.y) << 8) | (idx(v.z) << 16) | (idx(v.w) << 24);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquad; i += stride) {
+    const float4 a = __ldcs(x + 4 * i), b = __ldcs(x + 4 * i + 1), c = __ldcs(x + 4 * i + 2), d = __ldcs(x + 4 * i + 3);
+    out_idx8[i] = make_uint4(pack(a), pack(b), pack(c), pack(d));
   }
 }
 
@@ -139,12 +167,28 @@ static int round_impl(const T* x, int64_t count, const slk_codebook* cb, int mod
     bool aligned = ((uintptr_t)x % 16 == 0) && (!out_val || (uintptr_t)out_val % 16 == 0) &&
                    (!out_idx || (uintptr_t)out_idx % 4 == 0);
     int64_t nvec = aligned ? count / 4 : 0;
-    if (nvec > 0) {
-      round_f32_vec4_kernel<<<stream_grid(nvec, 256), 256, 0, st>>>(
-          (const float4*)x, nvec, *(DevGrid<float>*)&g, mode, (float4*)out_val, (uint32_t*)out_idx);
-      SLK_LAUNCH_CHECK();
-      done = nvec * 4;
+    int64_t vdone = 0;                       // float4 groups already rounded
+    static int tree = -1;   // SLK_K4_TREE=0: arithmetic index rounding instead of the compare tree (A/B testing)
+    if (tree < 0) {
+      const char* ev = getenv("SLK_K4_TREE");
+      tree = (ev && ev[0] == '0') ? 0 : 1;
     }
+    if (tree && nvec >= 4 && !out_val && out_idx && cb->kind == 0 && cb->size <= 8 && mode == SLK_NEAREST &&
+        (uintptr_t)out_idx % 16 == 0) {
+      // index only: compare tree over the exact breakpoints, 16 values per thread
+      const int64_t nquad = nvec / 4;
+      round_f32_index_tree_kernel<<<stream_grid(nquad, 256), 256, 0, st>>>((const float4*)x, nquad, make_breaks(cb),
+                                                                            (int)cb->size, (uint4*)out_idx);
+      SLK_LAUNCH_CHECK();
+      vdone = nquad * 4;
+    }
+    if (nvec > vdone) {
+      round_f32_vec4_kernel<<<stream_grid(nvec - vdone, 256), 256, 0, st>>>(
+          (const float4*)x + vdone, nvec - vdone, *(DevGrid<float>*)&g, mode,
+          out_val ? (float4*)out_val + vdone : nullptr, out_idx ? (uint32_t*)out_idx + vdone : nullptr);
+      SLK_LAUNCH_CHECK();
+    }
+    done = nvec * 4;
   }
   if (done < count) {
     if (sizeof(T) == 8 && cb->kind == 1)
@@ -538,6 +582,29 @@ __global__ void __launch_bounds__(256) mirror_upper_kernel(float* __restrict__ h
   }
 }
 
+// Block-upper-triangle packing of a symmetric matrix (the exchange format of the sample-sharded
+// statistics, dist.allreduce_statistics): block row b (rows [b*bs, b*bs+rows)) contributes its columns
+// [b*bs, n) as rows x (n - b*bs) contiguous floats, block rows one after the other -- the layout
+// slk_upload_symmetric_f32 sends over PCIe.  pack: packed = scale * H; unpack: H (upper block rows) =
+// scale * packed, the caller mirrors.  blockIdx.y = block row.
+template <bool UNPACK>
+__global__ void __launch_bounds__(256) sym_pack_kernel(float* __restrict__ h, int64_t n, int64_t bs, float scale,
+                                                       float* __restrict__ packed) {
+  const int64_t b = blockIdx.y, r0 = b * bs;
+  const int64_t rows = (r0 + bs < n) ? bs : n - r0, width = n - r0;
+  // offset of this block row in the packed buffer: sum over earlier block rows of bs * (n - b' * bs)
+  const int64_t off = b * bs * n - bs * bs * (b * (b - 1) / 2);
+  const int64_t total = rows * width;
+  float* pk = packed + off;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / width, j = t - i * width;
+    float* hp = h + (r0 + i) * n + r0 + j;
+    if (UNPACK) *hp = __fmul_rn(scale, pk[t]);
+    else pk[t] = __fmul_rn(scale, *hp);
+  }
+}
+
 }  // namespace slk
 
 using namespace slk;
@@ -701,6 +768,34 @@ int slk_upload_symmetric_f32(const float* h_host, float* h_dev, int64_t n, int64
   if (bs < n) {
     const int64_t nt = (n + 31) / 32;
     mirror_upper_kernel<<<(unsigned)(nt * (nt - 1) / 2), 256, 0, st>>>(h_dev, n, bs / 32);
+    SLK_LAUNCH_CHECK();
+  }
+  return SLK_OK;
+}
+
+/* Pack / unpack the block upper triangle of a symmetric device matrix (layout and byte count of
+ * slk_upload_symmetric_bytes) with a scale factor; unpack also mirrors the strictly lower blocks.
+ * Exchange format of the sample-sharded statistics: each rank packs count_rank / count_total * H, ONE
+ * all-reduce (sum) over ~half the bytes of H runs in place on the packed buffer, unpack rebuilds H. */
+int slk_sym_pack_f32(const float* h, int64_t n, int64_t bs, float scale, float* packed, void* stream) {
+  SLK_REQUIRE(h && packed && n >= 1 && bs >= 32 && bs % 32 == 0, "bad arguments");
+  const int64_t nb = ceil_div(n, bs);
+  dim3 grid((unsigned)stream_grid(bs * n, 256, 4), (unsigned)nb);
+  sym_pack_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(h), n, bs, scale, packed);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+int slk_sym_unpack_f32(const float* packed, int64_t n, int64_t bs, float scale, float* h, void* stream) {
+  SLK_REQUIRE(h && packed && n >= 1 && bs >= 32 && bs % 32 == 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nb = ceil_div(n, bs);
+  dim3 grid((unsigned)stream_grid(bs * n, 256, 4), (unsigned)nb);
+  sym_pack_kernel<true><<<grid, 256, 0, st>>>(h, n, bs, scale, const_cast<float*>(packed));
+  SLK_LAUNCH_CHECK();
+  if (bs < n) {
+    const int64_t nt = (n + 31) / 32;
+    mirror_upper_kernel<<<(unsigned)(nt * (nt - 1) / 2), 256, 0, st>>>(h, n, bs / 32);
     SLK_LAUNCH_CHECK();
   }
   return SLK_OK;

@@ -253,11 +253,7 @@ static int hinv_factor_and_invert(double* A, double* Li, double* T, int64_t n, i
   SLK_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
   const int64_t nblk = npad / NB;
   const size_t diag_smem_bytes = (size_t)2 * NB * LDP * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SLK_CUDA(cudaFuncSetAttribute(hinv_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem_bytes));
-    attr_set = true;
-  }
+  SLK_SMEM_ATTR_ONCE(hinv_panel_kernel, (int)diag_smem_bytes);
   for (int64_t k = 0; k < nblk; ++k) {
     const int64_t k0 = k * NB;
     const int64_t rest = npad - (k0 + NB);

@@ -141,7 +141,7 @@ __device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
   return __fadd_rn(v[0], __shfl_xor_sync(0xffffffffu, v[0], 16));
 }
 
-template <bool HAS_H, int TAB_WPT, int PITCH>
+template <bool HAS_H, int TAB_WPT, int PITCH, bool PACK2 = true>
 __global__ void __launch_bounds__(TAB_THREADS, 8) scale_search_tab_kernel(const float* __restrict__ w, int64_t r, int64_t n,
                                                                           DevGrid<float> g, GridBreaks brk, float cb_min,
                                                                           float cb_max, const float* __restrict__ factors,
@@ -328,15 +328,45 @@ __global__ void __launch_bounds__(TAB_THREADS, 8) scale_search_tab_kernel(const 
             const float e = __fsub_rn(lds(pt[m] + (u * GP + DQ)), wv[m]);        // scaling.py:130 (sign-mirrored for w < 0)
             return __fmaf_rn(__fmul_rn(e, e), hv[m], acc);
           };
+          // packed form: two weights per arithmetic instruction (FADD2 / FMUL2 / FFMA2 on sm_100a), the
+          // same per-lane IEEE operations; the thread's partial sum becomes (even weights) + (odd weights)
+          auto pack2 = [](float lo_, float hi_) -> unsigned long long {
+            unsigned long long v;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo_), "f"(hi_));
+            return v;
+          };
+          auto eval2 = [&](int m, int u, unsigned long long acc2) -> unsigned long long {
+            const float t0 = lds(pt[m] + u * GP), t1 = lds(pt[m + 1] + u * GP);
+            if (wv[m] < t0) pt[m] -= 4;
+            if (wv[m + 1] < t1) pt[m + 1] -= 4;
+            const unsigned long long d2 = pack2(lds(pt[m] + (u * GP + DQ)), lds(pt[m + 1] + (u * GP + DQ)));
+            unsigned long long e2, s2, r2;
+            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(e2) : "l"(d2), "l"(pack2(wv[m], wv[m + 1])));
+            asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(s2) : "l"(e2));
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(s2), "l"(pack2(hv[m], hv[m + 1])), "l"(acc2));
+            return r2;
+          };
+          auto sum2 = [](unsigned long long v) -> float {
+            float a_, b_;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a_), "=f"(b_) : "l"(v));
+            return __fadd_rn(a_, b_);
+          };
           int gb = 0;
           for (; gb + 16 <= G; gb += 16) {
             float part[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              float acc = 0.0f;
+              if (PACK2) {
+                unsigned long long acc2 = 0ull;
 #pragma unroll
-              for (int m = 0; m < TAB_WPT; ++m) acc = eval(m, u, acc);
-              part[u] = acc;
+                for (int m = 0; m < TAB_WPT; m += 2) acc2 = eval2(m, u, acc2);
+                part[u] = sum2(acc2);
+              } else {
+                float acc = 0.0f;
+#pragma unroll
+                for (int m = 0; m < TAB_WPT; ++m) acc = eval(m, u, acc);
+                part[u] = acc;
+              }
             }
 #pragma unroll
             for (int m = 0; m < TAB_WPT; ++m) pt[m] += 16 * GP;
@@ -526,6 +556,11 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
     // with 12 CTAs per SM, 92.1 us with 8)
     const int tgrid = (int)(r < (int64_t)sm_count() * 12 ? r : (int64_t)sm_count() * 12);
     const GridBreaks brk = make_breaks(cb);
+    static int pack2 = -1;   // SLK_SEARCH_PACK2=0: scalar walk loop instead of the packed f32x2 one (A/B testing)
+    if (pack2 < 0) {
+      const char* ev = getenv("SLK_SEARCH_PACK2");
+      pack2 = (ev && ev[0] == '0') ? 0 : 1;
+    }
     // weights per thread and chunk: the candidate with the least padding
     int wpt = 8;
     {
@@ -536,18 +571,17 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
         if (best_waste < 0 || waste < best_waste) { best_waste = waste; wpt = cand; }
       }
     }
-#define SLK_LAUNCH_TAB2(HAS, WPT, PITCH)                                                                             \
+#define SLK_LAUNCH_TAB3(HAS, WPT, PITCH, P2)                                                                         \
     do {                                                                                                             \
       const size_t tb = tab_smem_bytes<PITCH>(G);                                                                    \
-      static size_t attr = 0;                                                                                        \
-      if (tb > 48 * 1024 && tb > attr) {                                                                             \
-        SLK_CUDA(cudaFuncSetAttribute(scale_search_tab_kernel<HAS, WPT, PITCH>,                                      \
+      if (tb > 48 * 1024)                                                                                            \
+        SLK_CUDA(cudaFuncSetAttribute(scale_search_tab_kernel<HAS, WPT, PITCH, P2>,                                  \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));                        \
-        attr = tb;                                                                                                   \
-      }                                                                                                              \
-      scale_search_tab_kernel<HAS, WPT, PITCH><<<tgrid, TAB_THREADS, tb, st>>>(                                      \
+      scale_search_tab_kernel<HAS, WPT, PITCH, P2><<<tgrid, TAB_THREADS, tb, st>>>(                                  \
           w, r, n, g, brk, cmin, cmax, factors, G, (const float*)hdiag, out_scale, out_err, out_init, walk_allowed); \
     } while (0)
+#define SLK_LAUNCH_TAB2(HAS, WPT, PITCH)                                                                             \
+    do { if (pack2) SLK_LAUNCH_TAB3(HAS, WPT, PITCH, true); else SLK_LAUNCH_TAB3(HAS, WPT, PITCH, false); } while (0)
 #define SLK_LAUNCH_TAB(HAS, WPT)                                                                                     \
     do { if (cb->size <= 8) SLK_LAUNCH_TAB2(HAS, WPT, 9); else SLK_LAUNCH_TAB2(HAS, WPT, 17); } while (0)
     if (h_dtype == 1) {
@@ -556,6 +590,7 @@ extern "C" int slk_scale_search_f32(const float* w, int64_t r, int64_t n, const 
       if (wpt == 8) SLK_LAUNCH_TAB(false, 8); else if (wpt == 6) SLK_LAUNCH_TAB(false, 6); else SLK_LAUNCH_TAB(false, 4);
     }
 #undef SLK_LAUNCH_TAB2
+#undef SLK_LAUNCH_TAB3
 #undef SLK_LAUNCH_TAB
     SLK_LAUNCH_CHECK();
     return SLK_OK;

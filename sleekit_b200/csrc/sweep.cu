@@ -423,11 +423,7 @@ static int launch_fused(float* q, float* e, int64_t r, int64_t n, const float* u
                         float* esum = nullptr) {
   if (c1 < 0) c1 = n;
   auto kern = sweep_fused_kernel<R, RFORM>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<R>)));
-    attr_done = true;
-  }
+  SLK_SMEM_ATTR_ONCE(kern, (int)sizeof(FusedSmem<R>));
   kern<<<(unsigned)ceil_div(r, R), FT, sizeof(FusedSmem<R>), st>>>(q, e, r, n, u32, ud, g, c0, c1, pacc, esum);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
@@ -615,7 +611,26 @@ constexpr int MB_COLS = 256;
 constexpr int MB_PITCH = MB_COLS + 4;
 __device__ long long* g_sweep_trace = nullptr;   // development aid: per-block phase clocks of CTA 0
 
-template <int R>
+// R panels of the macro kernel.  Default: two full buffers (the look-ahead of block a reads the
+// panel of block a+32 while the tail product of block a reads the last 32 rows of its own panel).
+// COMPACT (SLK_SWEEP_COMPACT=1, prepared at the end of round 1, NOT yet measured on a GPU and off by
+// default): only the last 32 rows of the current panel are ever read again, so one full buffer plus
+// two 32-row tail buffers do -- 20 KB less per CTA (R = 8/16: three CTAs per SM instead of two,
+// R = 32: two instead of one); the prefetch then has to be issued after the barrier that ends the
+// previous look-ahead.
+template <bool COMPACT>
+struct PanelBufs;
+template <>
+struct PanelBufs<false> {
+  float Rs[2][MB_COLS - 32][32];            // R[c0 + k][a + col], k < a - c0
+};
+template <>
+struct PanelBufs<true> {
+  float Rs[1][MB_COLS - 32][32];            // rows k < a - c0 of the NEXT block's panel (look-ahead)
+  float Rt[2][32][32];                      // the last 32 rows of each panel (tail product)
+};
+
+template <int R, bool COMPACT = false>
 struct MacroSmem {
   static constexpr int KG = 32 / R;
   static constexpr int NLEAF = 4 * R;                       // threads of the leaf
@@ -624,7 +639,7 @@ struct MacroSmem {
   static constexpr int KGH = HELP >= NSLOT ? HELP / NSLOT : 1;   // their k groups
   static constexpr int SPT = HELP >= NSLOT ? 1 : NSLOT / HELP;   // slots per helper thread
   float Dm[R][MB_PITCH];                    // D = W - Q of this macro block
-  float Rs[2][MB_COLS - 32][32];            // R[c0 + k][a + col], k < a - c0
+  PanelBufs<COMPACT> pb;
   float red[KG][R][33];
   float red2[KGH][R][33];                   // look-ahead part of the next block's product
   float XV[16];                             // codebook breakpoints X[0..7] (X[0] unused) and values V[0..7]
@@ -634,14 +649,15 @@ struct MacroSmem {
   LeafShared32 leaf;
 };
 
-template <int R>
-__global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int64_t n,
+template <int R, bool COMPACT>
+__global__ void __launch_bounds__(FT, COMPACT ? (R == 32 ? 2 : 3) : 2)
+sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int64_t n,
                                                          const float* __restrict__ Rf, const float* __restrict__ Ud,
                                                          DevGrid<float> g, int64_t c0, int64_t c1,
                                                          const float* __restrict__ Pacc, float* __restrict__ Dhi,
                                                          float* __restrict__ Dlo, GridBreaks brk,
                                                          float* __restrict__ Esum) {
-  typedef MacroSmem<R> SM;
+  typedef MacroSmem<R, COMPACT> SM;
   constexpr int KG = SM::KG;
   extern __shared__ __align__(16) unsigned char macro_raw[];
   SM& sm = *reinterpret_cast<SM*>(macro_raw);
@@ -674,7 +690,9 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
     const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
     for (int t = tid; t < rows * 8; t += FT) {
       const int k = t >> 3, piece = t & 7;
-      float* dst = &sm.Rs[buf][k][piece * 4];
+      float* dst;
+      if constexpr (COMPACT) dst = (k < rows - 32) ? &sm.pb.Rs[0][k][piece * 4] : &sm.pb.Rt[buf][k - (rows - 32)][piece * 4];
+      else dst = &sm.pb.Rs[buf][k][piece * 4];
       const float* src = Rf + (c0 + k) * n + a + piece * 4;
       if (piece * 4 + 4 <= width) cp_async16(dst, src);
       else {
@@ -708,12 +726,16 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
     const int ka = (int)(a - c0);                      // columns of D that exist when this block starts
     const bool has_next = a + 32 < c1;
     if (has_next) {
-      prefetch_panel(a + 32, buf ^ 1);                 // read by the look-ahead below and by the next tail
+      if constexpr (!COMPACT) prefetch_panel(a + 32, buf ^ 1);   // read by the look-ahead below and by the next tail
       fetch(a + 32, nxt);
     }
     long long* tr = (g_sweep_trace && blockIdx.x == 0 && tid == 0) ? g_sweep_trace + ((a - c0) / 32) * 8 : nullptr;
     if (tr) tr[0] = clock64();
     __syncthreads();                                   // previous leaf's D and the look-ahead sums are visible
+    if constexpr (COMPACT) {
+      // the single full buffer was read by the look-ahead that the barrier above has just ended
+      if (has_next) prefetch_panel(a + 32, buf ^ 1);
+    }
     if (tr) tr[1] = clock64();
     // ---- (1) tail: D[:, a-32:a] R[a-32:a, J], the 32 k split over the k groups --------------------
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -723,7 +745,10 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
 #pragma unroll
       for (int kk = 0; kk < KPG; ++kk) {
         const float e = sm.Dm[lrow][kb + kk];
-        const float4 u = *reinterpret_cast<const float4*>(&sm.Rs[buf][kb + kk][seg * 4]);
+        const float* rp;
+        if constexpr (COMPACT) rp = &sm.pb.Rt[buf][kg * KPG + kk][seg * 4];
+        else rp = &sm.pb.Rs[buf][kb + kk][seg * 4];
+        const float4 u = *reinterpret_cast<const float4*>(rp);
         acc[0] = __fmaf_rn(e, u.x, acc[0]);
         acc[1] = __fmaf_rn(e, u.y, acc[1]);
         acc[2] = __fmaf_rn(e, u.z, acc[2]);
@@ -808,7 +833,7 @@ __global__ void __launch_bounds__(FT) sweep_macro_kernel(float* __restrict__ Q, 
 #pragma unroll 8
             for (int kk = 0; kk < 32; ++kk) {
               const float e = sm.Dm[hr][kb + kk];
-              const float4 u = *reinterpret_cast<const float4*>(&sm.Rs[buf ^ 1][kb + kk][hs * 4]);
+              const float4 u = *reinterpret_cast<const float4*>(&sm.pb.Rs[COMPACT ? 0 : (buf ^ 1)][kb + kk][hs * 4]);
               la[0] = __fmaf_rn(e, u.x, la[0]);
               la[1] = __fmaf_rn(e, u.y, la[1]);
               la[2] = __fmaf_rn(e, u.z, la[2]);
@@ -863,20 +888,29 @@ extern "C" int slk_debug_sweep_trace(void* buf) {
   return SLK_OK;
 }
 
+template <int R, bool COMPACT>
+static int launch_macro_v(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
+                          cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo,
+                          const GridBreaks& xv, float* esum) {
+  auto kern = sweep_macro_kernel<R, COMPACT>;
+  SLK_SMEM_ATTR_ONCE(kern, (int)sizeof(MacroSmem<R, COMPACT>));
+  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R, COMPACT>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo,
+                                                                           xv, esum);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
 template <int R>
 static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
                         cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo,
                         const GridBreaks& xv, float* esum) {
-  auto kern = sweep_macro_kernel<R>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MacroSmem<R>)));
-    attr_done = true;
+  static int compact = -1;   // SLK_SWEEP_COMPACT=0/1: double-buffered / single R-panel buffer (PanelBufs)
+  if (compact < 0) {
+    const char* ev = getenv("SLK_SWEEP_COMPACT");
+    compact = (ev && ev[0] == '1') ? 1 : 0;
   }
-  kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo, xv,
-                                                                  esum);
-  SLK_LAUNCH_CHECK();
-  return SLK_OK;
+  if (compact) return launch_macro_v<R, true>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
+  return launch_macro_v<R, false>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
 }
 
 // R form of the sweep: r32 = Cholesky factor R (upper, H_opt = R R^T), rt32 = its transpose, ud32 =

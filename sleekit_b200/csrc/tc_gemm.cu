@@ -423,11 +423,7 @@ static int tc_launch(const float* a_hi, const float* a_lo, int64_t lda, const fl
   if ((rc = make_map(&mb_hi, b_hi, p.N, p.K, ldb, BN))) return rc;
   if ((rc = make_map(&mb_lo, b_lo, p.N, p.K, ldb, BN))) return rc;
   auto kern = tc_gemm_kernel<BN, STAGES, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr_done = true;
-  }
+  SLK_SMEM_ATTR_ONCE(kern, SM::TOTAL);
   dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, TC_BM), (unsigned)splits);
   kern<<<grid, TC_THREADS, SM::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   SLK_LAUNCH_CHECK();

@@ -47,24 +47,41 @@ def layers_of_rank(num_layers, rank, world):
 
 
 def allreduce_statistics(hessian, mean, count, group=None):
-    """Combine per-rank running means (statistics.py:76-87 semantics) into the global ones.
+    """Combine per-rank running means (statistics.py:76-87 semantics) into the global ones, IN PLACE.
 
-    hessian [n, n], mean [n] fp32 are this rank's running means over `count` samples.  Returns
-    (hessian, mean, count) of the union of all ranks' samples, identical on every rank."""
+    hessian [n, n], mean [n] fp32 are this rank's running means over `count` samples; on return they
+    hold the running means over the union of all ranks' samples (identical on every rank).  Returns
+    (hessian, mean, total count).  The sample counts travel first (one scalar all-reduce), every rank
+    then weights its statistics by count / total so that ONE sum all-reduce yields the global means
+    with no temporaries of the size of H.  On CUDA the Hessian -- symmetric -- is exchanged as its block
+    upper triangle (ops.sym_pack / sym_unpack: ~53 % of the bytes, all-reduced in place in the packed
+    buffer); on CPU tensors (gloo tests) the full matrix is reduced in place."""
     rank, world = _world(group)
     if world == 1:
         return hessian, mean, count
     n = mean.numel()
-    buf = torch.empty(n * n + n + 1, dtype=torch.float32, device=hessian.device)
-    c = float(count)
-    buf[: n * n] = (hessian * c).reshape(-1)
-    buf[n * n: n * n + n] = mean * c
-    buf[-1] = c
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    total = float(buf[-1].item())
+    tot = torch.tensor([float(count)], dtype=torch.float64, device=hessian.device)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    total = float(tot.item())
     if total == 0:
-        return torch.zeros_like(hessian), torch.zeros_like(mean), 0
-    return (buf[: n * n] / total).reshape(n, n).clone(), (buf[n * n: n * n + n] / total).clone(), int(round(total))
+        return hessian.zero_(), mean.zero_(), 0
+    w = float(count) / total
+    if hessian.is_cuda:
+        from . import ops
+
+        L = ops.sym_packed_len(n)
+        buf = torch.empty(L + n, dtype=torch.float32, device=hessian.device)
+        ops.sym_pack(hessian, buf, w)
+        torch.mul(mean, w, out=buf[L:])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        ops.sym_unpack(buf, hessian, 1.0)
+        mean.copy_(buf[L:])
+    else:
+        hessian.mul_(w)
+        mean.mul_(w)
+        dist.all_reduce(hessian, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mean, op=dist.ReduceOp.SUM, group=group)
+    return hessian, mean, int(round(total))
 
 
 def allreduce_column_sums(local_sums, group=None):

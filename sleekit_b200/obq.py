@@ -162,8 +162,91 @@ def _quantize_opt_core(Q, E, Hinv, quantizer):
     _quantize_opt_block(Q, E, Hinv, quantizer, MAX_LEAF, 8)
 
 
+class GptqStage:
+    """State between the two halves of gptq_device: everything up to the fp64 factor has been enqueued
+    (damp value, ordering, scaled / permuted weights); the factor and the sweep follow in gptq_finish.
+    The layer-set driver (pipeline.LayerSetQuantizer) runs the first half of many layers, factors
+    their Hessians in batched launches (ops.chol_factor_batched) and then finishes each layer."""
+
+    __slots__ = ("W_in", "Wd", "Hd", "quantizer", "act_order", "dampval", "order", "Q", "fuse", "row_scale",
+                 "nb_ls_moves", "leaf", "num_blocks", "want_err", "chol_form")
+
+
+def gptq_prepare(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
+                 colsum_reduce=None, row_scale=None, want_err=False):
+    """First half of gptq_device: obq.py:198-203 (damp, ordering keys, argsort, permutation)."""
+    st = GptqStage()
+    st.dampval = ops.damp_value(Hd, damp)                                # obq.py:198
+    st.W_in, st.Hd, st.quantizer, st.act_order = Wd, Hd, quantizer, act_order
+    st.row_scale, st.nb_ls_moves, st.want_err = row_scale, nb_ls_moves, want_err
+    st.leaf, st.num_blocks = _sweep_leaf(min_block_size), num_blocks
+    st.chol_form = st.leaf == MAX_LEAF and USE_CHOL_FORM
+    st.fuse = row_scale is not None and act_order in ("diag", "none") and not nb_ls_moves
+    if row_scale is not None and not st.fuse:
+        Wd = ops.scale_rows(Wd, row_scale, 0)                            # scaling.py:73
+    st.Wd = Wd
+    if act_order == "none":
+        order = None
+    elif act_order in ("diag", "err", "sqerr"):
+        col = None
+        if act_order != "diag":
+            col = ops.col_resid_sums(Wd, quantizer, squared=(act_order == "sqerr"))
+            if colsum_reduce is not None:
+                col = colsum_reduce(col)
+        order = ops.argsort(ops.order_keys(Hd, st.dampval, col))         # obq.py:199
+    else:
+        hopt_diag = Hd.diagonal().to(torch.float64) + st.dampval.to(torch.float64)
+        hopt = Hd.to(torch.float64)
+        hopt.diagonal().add_(st.dampval.to(torch.float64))
+        order = _device_order(Wd, hopt, quantizer, act_order, hopt_diag)
+    st.order = order
+    if st.fuse:
+        st.Q = ops.scale_permute_cols(Wd, order, row_scale)               # scaling.py:73 + obq.py:202-203
+    else:
+        st.Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
+    return st
+
+
+def gptq_finish(st, factor=None, check=False):
+    """Second half of gptq_device: fp64 factor (unless `factor` = (r32, rt32, ud32, info) of
+    (Hd + damp)[order][:, order] is handed in), sweep, un-permutation, local search, error."""
+    Q, Hd, quantizer, order, row_scale = st.Q, st.Hd, st.quantizer, st.order, st.row_scale
+    want_err, nb_ls_moves = st.want_err, st.nb_ls_moves
+    sums = None
+    if st.chol_form:
+        # factor only (no triangular inverse): H_opt = R R^T, sweep from R (SURVEY 7.3 H2)
+        r32, rt32, ud32, info = factor if factor is not None else ops.chol_factor(Hd, order, st.dampval)  # obq.py:204
+        if want_err and not nb_ls_moves and USE_SWEEP_ERROR:
+            sums = torch.empty((Q.shape[0], 2), dtype=torch.float32, device=Q.device)
+        ops.gptq_sweep_r(Q, r32, rt32, ud32, quantizer, err_sums=sums)    # obq.py:208-209
+        if sums is not None:
+            err = ops.sweep_error(sums, row_scale, st.dampval, want_rows=True)
+    else:
+        assert factor is None
+        u64, u32, info = ops.hinv(Hd, order, st.dampval)                  # obq.py:204-205
+        ops.gptq_sweep(Q, u64, u32, quantizer, st.leaf, st.num_blocks)    # obq.py:208-209
+    if st.fuse:
+        Q = ops.scale_permute_cols(Q, order, row_scale, scatter=True)     # obq.py:212-213 + scaling.py:80
+        if check:
+            _raise_if_not_pd(info)
+        if want_err:
+            return Q, (err if sums is not None else _k6_error(st.W_in, Q, Hd))
+        return Q
+    if order is not None:
+        Q = ops.permute_cols(Q, order, scatter=True)                      # obq.py:212-213
+    if check:
+        _raise_if_not_pd(info)
+    if nb_ls_moves:
+        ops.local_search(st.Wd, Q, Hd, quantizer, nb_ls_moves)            # obq.py:216
+    if row_scale is not None:
+        Q = ops.scale_rows(Q, row_scale, 1)                               # scaling.py:80
+    if want_err:
+        return Q, (err if sums is not None else _k6_error(st.W_in, Q, Hd))
+    return Q
+
+
 def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
-                check=False, colsum_reduce=None, row_scale=None, want_err=False):
+                check=False, colsum_reduce=None, row_scale=None, want_err=False, factor_fn=None):
     """quantize_opt on device tensors (fp32 W [r,n], fp32 H [n,n]); returns quantized values [r,n].
     The whole chain -- damp, keys, argsort, gather, fp64 factor, sweep, scatter, local search --
     is enqueued on the current stream without a host round trip.  colsum_reduce: optional callable
@@ -174,61 +257,12 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
     want_err: also return (mean layer error [1], row errors [r]) = quantization_error / channelwise_error
     (obq.py:89-103) of the returned weights against Wd under Hd, taken from the sweep's residuals
     (sum E^2 - damp * sum (W-Q)^2, ops.sweep_error) when the factor-form sweep ran and no local-search
-    move follows, from the K6 product otherwise."""
-    dampval = ops.damp_value(Hd, damp)                                   # obq.py:198
-    W_in = Wd
-    fuse = row_scale is not None and act_order in ("diag", "none") and not nb_ls_moves
-    if row_scale is not None and not fuse:
-        Wd = ops.scale_rows(Wd, row_scale, 0)                            # scaling.py:73
-    if act_order == "none":
-        order = None
-    elif act_order in ("diag", "err", "sqerr"):
-        col = None
-        if act_order != "diag":
-            col = ops.col_resid_sums(Wd, quantizer, squared=(act_order == "sqerr"))
-            if colsum_reduce is not None:
-                col = colsum_reduce(col)
-        order = ops.argsort(ops.order_keys(Hd, dampval, col))            # obq.py:199
-    else:
-        hopt_diag = Hd.diagonal().to(torch.float64) + dampval.to(torch.float64)
-        hopt = Hd.to(torch.float64)
-        hopt.diagonal().add_(dampval.to(torch.float64))
-        order = _device_order(Wd, hopt, quantizer, act_order, hopt_diag)
-    if fuse:
-        Q = ops.scale_permute_cols(Wd, order, row_scale)                  # scaling.py:73 + obq.py:202-203
-    else:
-        Q = ops.permute_cols(Wd, order) if order is not None else Wd.clone()  # obq.py:202-203
-    if _sweep_leaf(min_block_size) == MAX_LEAF and USE_CHOL_FORM:
-        # factor only (no triangular inverse): H_opt = R R^T, sweep from R (SURVEY 7.3 H2)
-        r32, rt32, ud32, info = ops.chol_factor(Hd, order, dampval)       # obq.py:204 (dpotrf part)
-        sums = None
-        if want_err and not nb_ls_moves and USE_SWEEP_ERROR:
-            sums = torch.empty((Q.shape[0], 2), dtype=torch.float32, device=Q.device)
-        ops.gptq_sweep_r(Q, r32, rt32, ud32, quantizer, err_sums=sums)    # obq.py:208-209
-        if sums is not None:
-            err = ops.sweep_error(sums, row_scale, dampval, want_rows=True)
-    else:
-        sums = None
-        u64, u32, info = ops.hinv(Hd, order, dampval)                     # obq.py:204-205
-        ops.gptq_sweep(Q, u64, u32, quantizer, _sweep_leaf(min_block_size), num_blocks)  # obq.py:208-209
-    if fuse:
-        Q = ops.scale_permute_cols(Q, order, row_scale, scatter=True)     # obq.py:212-213 + scaling.py:80
-        if check:
-            _raise_if_not_pd(info)
-        if want_err:
-            return Q, (err if sums is not None else _k6_error(W_in, Q, Hd))
-        return Q
-    if order is not None:
-        Q = ops.permute_cols(Q, order, scatter=True)                      # obq.py:212-213
-    if check:
-        _raise_if_not_pd(info)
-    if nb_ls_moves:
-        ops.local_search(Wd, Q, Hd, quantizer, nb_ls_moves)               # obq.py:216
-    if row_scale is not None:
-        Q = ops.scale_rows(Q, row_scale, 1)                               # scaling.py:80
-    if want_err:
-        return Q, (err if sums is not None else _k6_error(W_in, Q, Hd))
-    return Q
+    move follows, from the K6 product otherwise.  factor_fn(Hd, order, dampval) -> (r32, rt32, ud32,
+    info): an alternative producer of the Cholesky factor (the multi-GPU factorisation)."""
+    st = gptq_prepare(Wd, Hd, quantizer, act_order, damp, nb_ls_moves, min_block_size, num_blocks,
+                      colsum_reduce, row_scale, want_err)
+    factor = factor_fn(Hd, st.order, st.dampval) if (factor_fn is not None and st.chol_form) else None
+    return gptq_finish(st, factor, check)
 
 
 def _k6_error(Wd, Qd, Hd):

@@ -70,8 +70,23 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _Target:
+    """Device of the tensors of the call being assembled: _chk() notes it, _stream() takes that
+    device's current stream and _call() makes it the current device around the C call, so a layer
+    that lives on cuda:1 launches there even while cuda:0 is the process's current device."""
+    dev = None
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(_Target.dev).cuda_stream)
+
+
+def _call(name, *args):
+    dev = _Target.dev
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _lib.call(name, *args)
+    return _lib.call(name, *args)
 
 
 def _ws(nbytes, dev):
@@ -80,6 +95,7 @@ def _ws(nbytes, dev):
 
 def _chk(t, dtype=None):
     assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    _Target.dev = t.device
     if dtype is not None:
         assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
     return t
@@ -166,7 +182,7 @@ def round_to_codebook(x, cb, mode=NEAREST, want_val=True, want_idx=False):
     if want_idx:
         idx = torch.empty(x.shape, dtype=cb.index_dtype, device=x.device)
     fn = "slk_round_f32" if x.dtype == torch.float32 else "slk_round_f64"
-    _lib.call(fn, _ptr(x), x.numel(), cb.ref, mode, _ptr(val), _ptr(idx), _stream())
+    _call(fn, _ptr(x), x.numel(), cb.ref, mode, _ptr(val), _ptr(idx), _stream())
     return val, idx
 
 
@@ -178,7 +194,7 @@ def scale_axis(x, s, outer, length, inner, mode=0):
     assert s.numel() == length and x.numel() == outer * length * inner
     out = torch.empty_like(x)
     fn = "slk_scale_axis_f32" if x.dtype == torch.float32 else "slk_scale_axis_f64"
-    _lib.call(fn, _ptr(x), outer, length, inner, _ptr(s), mode, _ptr(out), _stream())
+    _call(fn, _ptr(x), outer, length, inner, _ptr(s), mode, _ptr(out), _stream())
     return out
 
 
@@ -191,7 +207,7 @@ def row_noclip_scale(w2d, cb_min, cb_max):
     _chk(w2d)
     out = torch.empty(w2d.shape[0], dtype=w2d.dtype, device=w2d.device)
     fn = "slk_row_noclip_scale_f32" if w2d.dtype == torch.float32 else "slk_row_noclip_scale_f64"
-    _lib.call(fn, _ptr(w2d), w2d.shape[0], w2d.shape[1], float(cb_min), float(cb_max), _ptr(out), _stream())
+    _call(fn, _ptr(w2d), w2d.shape[0], w2d.shape[1], float(cb_min), float(cb_max), _ptr(out), _stream())
     return out
 
 
@@ -199,7 +215,7 @@ def row_rms_scale(w2d):
     _chk(w2d)
     out = torch.empty(w2d.shape[0], dtype=w2d.dtype, device=w2d.device)
     fn = "slk_row_rms_scale_f32" if w2d.dtype == torch.float32 else "slk_row_rms_scale_f64"
-    _lib.call(fn, _ptr(w2d), w2d.shape[0], w2d.shape[1], _ptr(out), _stream())
+    _call(fn, _ptr(w2d), w2d.shape[0], w2d.shape[1], _ptr(out), _stream())
     return out
 
 
@@ -223,7 +239,7 @@ def scale_search(w, cb, factors, hdiag=None, want_err=False, want_init=False):
     out = torch.empty(r, dtype=torch.float32, device=w.device)
     err = torch.empty(r, dtype=torch.float32, device=w.device) if want_err else None
     init = torch.empty(r, dtype=torch.float32, device=w.device) if want_init else None
-    _lib.call("slk_scale_search_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(hdiag), h_dtype,
+    _call("slk_scale_search_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(hdiag), h_dtype,
               _ptr(out), _ptr(err), _ptr(init), _stream())
     return out, err, init
 
@@ -242,7 +258,7 @@ def scale_search_fullh(w, cb, factors, h, want_err=False):
     ws = _ws(nbytes, w.device)
     out = torch.empty(r, dtype=torch.float32, device=w.device)
     err = torch.empty(r, dtype=torch.float32, device=w.device) if want_err else None
-    _lib.call("slk_scale_search_fullh_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(h), h_dtype,
+    _call("slk_scale_search_fullh_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(h), h_dtype,
               _ptr(ws), nbytes, _ptr(out), _ptr(err), _stream())
     return out, err
 
@@ -266,7 +282,7 @@ def hweighted_error(w, q, h):
     ws = _ws(nbytes, w.device)
     out = torch.empty(r, dtype=w.dtype, device=w.device)
     fn = "slk_hweighted_error_f32" if esz == 4 else "slk_hweighted_error_f64"
-    _lib.call(fn, _ptr(w), _ptr(q), _ptr(h), r, n, _ptr(ws), nbytes, _ptr(out), _stream())
+    _call(fn, _ptr(w), _ptr(q), _ptr(h), r, n, _ptr(ws), nbytes, _ptr(out), _stream())
     return out
 
 
@@ -274,7 +290,7 @@ def mean(v):
     _chk(v)
     out = torch.empty((), dtype=v.dtype, device=v.device)
     fn = "slk_mean_f32" if v.dtype == torch.float32 else "slk_mean_f64"
-    _lib.call(fn, _ptr(v), v.numel(), _ptr(out), _stream())
+    _call(fn, _ptr(v), v.numel(), _ptr(out), _stream())
     return out
 
 
@@ -284,7 +300,7 @@ def gain(w, q, h, cand):
     r, n = w.shape
     out = torch.empty_like(w)
     fn = "slk_gain_f32" if w.dtype == torch.float32 else "slk_gain_f64"
-    _lib.call(fn, _ptr(w), _ptr(q), _ptr(h), _ptr(cand), r, n, _ptr(out), _stream())
+    _call(fn, _ptr(w), _ptr(q), _ptr(h), _ptr(cand), r, n, _ptr(out), _stream())
     return out
 
 
@@ -303,7 +319,7 @@ def hessian_accum(x, hess, mean_vec, keep, new_count):
     assert hess.shape == (n, n) and mean_vec.shape == (n,)
     nbytes = _lib.load().slk_hessian_accum_ws_bytes(S, n)
     ws = _ws(nbytes, x.device)
-    _lib.call("slk_hessian_accum_f32", _ptr(x), S, n, n, _ptr(hess), _ptr(mean_vec), float(keep), float(new_count),
+    _call("slk_hessian_accum_f32", _ptr(x), S, n, n, _ptr(hess), _ptr(mean_vec), float(keep), float(new_count),
               _ptr(ws), nbytes, _stream())
 
 
@@ -313,7 +329,7 @@ def remove_input_bias(h, m):
     _chk(m, h.dtype)
     out = torch.empty_like(h)
     fn = "slk_remove_input_bias_f32" if h.dtype == torch.float32 else "slk_remove_input_bias_f64"
-    _lib.call(fn, _ptr(h), _ptr(m), h.shape[0], _ptr(out), _stream())
+    _call(fn, _ptr(h), _ptr(m), h.shape[0], _ptr(out), _stream())
     return out
 
 
@@ -325,7 +341,7 @@ def remove_input_bias(h, m):
 def damp_value(h, damp):
     _chk(h, torch.float32)
     out = torch.empty(1, dtype=torch.float32, device=h.device)
-    _lib.call("slk_damp_value_f32", _ptr(h), h.shape[0], float(damp), _ptr(out), _stream())
+    _call("slk_damp_value_f32", _ptr(h), h.shape[0], float(damp), _ptr(out), _stream())
     return out
 
 
@@ -334,7 +350,7 @@ def col_resid_sums(w, cb, squared):
     cb = device_codebook(cb)
     _chk(w, torch.float32)
     out = torch.empty(w.shape[1], dtype=torch.float32, device=w.device)
-    _lib.call("slk_col_resid_sums_f32", _ptr(w), w.shape[0], w.shape[1], cb.ref, 1 if squared else 0, _ptr(out),
+    _call("slk_col_resid_sums_f32", _ptr(w), w.shape[0], w.shape[1], cb.ref, 1 if squared else 0, _ptr(out),
               _stream())
     return out
 
@@ -342,7 +358,7 @@ def col_resid_sums(w, cb, squared):
 def order_keys(h, dampval=None, colsum=None):
     _chk(h, torch.float32)
     keys = torch.empty(h.shape[0], dtype=torch.float64, device=h.device)
-    _lib.call("slk_order_keys", _ptr(h), h.shape[0], _ptr(dampval), _ptr(colsum), _ptr(keys), _stream())
+    _call("slk_order_keys", _ptr(h), h.shape[0], _ptr(dampval), _ptr(colsum), _ptr(keys), _stream())
     return keys
 
 
@@ -350,7 +366,7 @@ def order_keys(h, dampval=None, colsum=None):
 def argsort(keys):
     _chk(keys, torch.float64)
     order = torch.empty(keys.numel(), dtype=torch.int64, device=keys.device)
-    _lib.call("slk_argsort_f64", _ptr(keys), keys.numel(), _ptr(order), _stream())
+    _call("slk_argsort_f64", _ptr(keys), keys.numel(), _ptr(order), _stream())
     return order
 
 
@@ -361,7 +377,7 @@ def pivot_order(h64):
     nbytes = _lib.load().slk_pivot_order_ws_bytes(n)
     ws = _ws(nbytes, h64.device)
     order = torch.empty(n, dtype=torch.int64, device=h64.device)
-    _lib.call("slk_pivot_order_f64", _ptr(h64), n, _ptr(ws), nbytes, _ptr(order), _stream())
+    _call("slk_pivot_order_f64", _ptr(h64), n, _ptr(ws), nbytes, _ptr(order), _stream())
     return order
 
 
@@ -370,7 +386,7 @@ def permute_cols(src, idx, scatter=False):
     _chk(src, torch.float32)
     _chk(idx, torch.int64)
     dst = torch.empty_like(src)
-    _lib.call("slk_permute_cols_f32", _ptr(src), src.shape[0], src.shape[1], _ptr(idx), 1 if scatter else 0,
+    _call("slk_permute_cols_f32", _ptr(src), src.shape[0], src.shape[1], _ptr(idx), 1 if scatter else 0,
               _ptr(dst), _stream())
     return dst
 
@@ -384,7 +400,7 @@ def scale_permute_cols(src, idx, s, scatter=False):
     if idx is not None:
         _chk(idx, torch.int64)
     dst = torch.empty_like(src)
-    _lib.call("slk_scale_permute_cols_f32", _ptr(src), src.shape[0], src.shape[1], _ptr(idx), _ptr(s),
+    _call("slk_scale_permute_cols_f32", _ptr(src), src.shape[0], src.shape[1], _ptr(idx), _ptr(s),
               1 if scatter else 0, _ptr(dst), _stream())
     return dst
 
@@ -408,7 +424,7 @@ def upload_symmetric(h_pinned, h_dev):
     n = h_dev.shape[0]
     assert h_pinned.shape == (n, n) and h_dev.shape == (n, n)
     bs = symmetric_block_rows(n)
-    _lib.call("slk_upload_symmetric_f32", C.c_void_p(h_pinned.data_ptr()), _ptr(h_dev), n, bs, _stream())
+    _call("slk_upload_symmetric_f32", C.c_void_p(h_pinned.data_ptr()), _ptr(h_dev), n, bs, _stream())
     return int(_lib.load().slk_upload_symmetric_bytes(n, bs))
 
 
@@ -426,11 +442,11 @@ def hinv(h, order=None, dampval=None, want64=False, want32=True):
     if h.dtype == torch.float32:
         if order is not None:
             _chk(order, torch.int64)
-        _lib.call("slk_hinv_from_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(u64), _ptr(u32),
+        _call("slk_hinv_from_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(u64), _ptr(u32),
                   _ptr(info), _stream())
     else:
         assert h.dtype == torch.float64 and order is None and dampval is None
-        _lib.call("slk_hinv_from_f64", _ptr(h), n, _ptr(ws), nbytes, _ptr(u64), _ptr(u32), _ptr(info), _stream())
+        _call("slk_hinv_from_f64", _ptr(h), n, _ptr(ws), nbytes, _ptr(u64), _ptr(u32), _ptr(info), _stream())
     return u64, u32, info
 
 
@@ -450,9 +466,159 @@ def chol_factor(h, order=None, dampval=None, want_rt=True):
     info = torch.empty(1, dtype=torch.int32, device=h.device)
     if order is not None:
         _chk(order, torch.int64)
-    _lib.call("slk_chol_factor_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(r32),
+    _call("slk_chol_factor_f32", _ptr(h), n, _ptr(order), _ptr(dampval), _ptr(ws), nbytes, _ptr(r32),
               _ptr(rt[0]) if want_rt else None, _ptr(rt[1]) if want_rt else None, _ptr(ud32), _ptr(info), _stream())
     return r32, rt, ud32, info
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
+
+
+@_timed("chol_factor")
+def chol_factor_batched(hs, orders=None, dampvals=None, want_rt=True):
+    """chol_factor for a list of equal-sized matrices in ONE launch sequence whose tile tasks share a
+    ticket queue (slk_chol_factor_batched_f32).  Returns a list of (r32, rt, ud32, info) per matrix."""
+    B = len(hs)
+    n = hs[0].shape[0]
+    dev = hs[0].device
+    for h in hs:
+        _chk(h, torch.float32)
+        assert h.shape == (n, n)
+    lib = _lib.load()
+    nbytes = int(lib.slk_chol_factor_ws_bytes(n))
+    nbytes = (nbytes + 255) // 256 * 256
+    ws = torch.empty((B, nbytes), dtype=torch.uint8, device=dev)
+    r32 = torch.empty((B, n, n), dtype=torch.float32, device=dev)
+    rt = torch.empty((B, 2, n, n), dtype=torch.float32, device=dev) if want_rt else None
+    ud32 = torch.empty((B, (n + 31) // 32, 32, 32), dtype=torch.float32, device=dev)
+    info = torch.empty((B, 1), dtype=torch.int32, device=dev)
+    if orders is not None:
+        for o in orders:
+            if o is not None:
+                _chk(o, torch.int64)
+    _call("slk_chol_factor_batched_f32", B, _ptr_array(hs), n,
+          _ptr_array(orders) if orders is not None else None,
+          _ptr_array(dampvals) if dampvals is not None else None,
+          _ptr_array([ws[k] for k in range(B)]), _ptr_array([r32[k] for k in range(B)]),
+          _ptr_array([rt[k, 0] for k in range(B)]) if want_rt else None,
+          _ptr_array([rt[k, 1] for k in range(B)]) if want_rt else None,
+          _ptr_array([ud32[k] for k in range(B)]), _ptr_array([info[k] for k in range(B)]), _stream())
+    return [(r32[k], rt[k] if want_rt else None, ud32[k], info[k]) for k in range(B)]
+
+
+class PeerWorkspace:
+    """This rank's workspace of the multi-GPU factorisation in peer-visible device memory
+    (slk_peer_alloc), plus the peers' workspaces mapped into this process (slk_peer_open).  The CUDA
+    IPC handles travel through torch.distributed (all_gather_object)."""
+
+    def __init__(self, nbytes, group=None):
+        import torch.distributed as dist
+
+        require_cuda()
+        self.nbytes = int(nbytes)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.call("slk_peer_alloc", self.nbytes, C.byref(ptr), handle)
+        self.ptr = ptr.value
+        self._opened = []
+        self.peers = [None] * self.world
+        self.peers[self.rank] = self.ptr
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                p = C.c_void_p()
+                _lib.call("slk_peer_open", C.create_string_buffer(handles[q], 64), C.byref(p))
+                self.peers[q] = p.value
+                self._opened.append(p.value)
+            dist.barrier(group=group)
+
+    def peer_array(self):
+        return (C.c_void_p * self.world)(*self.peers)
+
+    def close(self):
+        import torch.distributed as dist
+
+        if self.ptr is None:
+            return
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            _lib.call("slk_peer_close", C.c_void_p(p))
+        self._opened = []
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        _lib.call("slk_peer_free", C.c_void_p(self.ptr))
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            if self.ptr is not None and not self._opened:
+                _lib.call("slk_peer_free", C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def chol_dist_ws_bytes(n):
+    return int(_lib.load().slk_chol_factor_ws_bytes(n))
+
+
+@_timed("chol_factor")
+def chol_factor_dist(h, order, dampval, pws, barrier, want_rt=True):
+    """chol_factor with the tile rows of the factorisation spread over the ranks of pws (PeerWorkspace):
+    finished tiles are pushed to every peer through NVLink (slk_chol_dist_*), so every rank ends with
+    the complete factor.  barrier(): a stream-ordered barrier over the ranks (an all-reduce of one
+    element on the current stream).  Returns (r32, rt, ud32, info) like chol_factor; info is
+    max-reduced over the ranks by the caller if it is going to be read."""
+    _chk(h, torch.float32)
+    n = h.shape[0]
+    assert pws.nbytes >= chol_dist_ws_bytes(n)
+    r32 = torch.empty((n, n), dtype=torch.float32, device=h.device)
+    rt = torch.empty((2, n, n), dtype=torch.float32, device=h.device) if want_rt else None
+    ud32 = torch.empty(((n + 31) // 32, 32, 32), dtype=torch.float32, device=h.device)
+    info = torch.empty(1, dtype=torch.int32, device=h.device)
+    if order is not None:
+        _chk(order, torch.int64)
+    ws = C.c_void_p(pws.ptr)
+    _call("slk_chol_dist_gather_f32", _ptr(h), n, _ptr(order), _ptr(dampval), ws, pws.nbytes, _ptr(info), _stream())
+    barrier()
+    _call("slk_chol_dist_factor", n, ws, pws.world, pws.rank, pws.peer_array(), _ptr(info), _stream())
+    barrier()
+    _call("slk_chol_dist_export_f32", n, ws, _ptr(r32), _ptr(rt[0]) if want_rt else None,
+          _ptr(rt[1]) if want_rt else None, _ptr(ud32), _stream())
+    return r32, rt, ud32, info
+
+
+def sym_pack(h, packed, scale=1.0):
+    """packed[:L] = scale * (block upper triangle of the symmetric h); returns L (floats)."""
+    _chk(h, torch.float32)
+    _chk(packed, torch.float32)
+    n = h.shape[0]
+    bs = symmetric_block_rows(n)
+    L = int(_lib.load().slk_upload_symmetric_bytes(n, bs)) // 4
+    assert packed.numel() >= L
+    _call("slk_sym_pack_f32", _ptr(h), n, bs, float(scale), _ptr(packed), _stream())
+    return L
+
+
+def sym_packed_len(n):
+    return int(_lib.load().slk_upload_symmetric_bytes(n, symmetric_block_rows(n))) // 4
+
+
+def sym_unpack(packed, h, scale=1.0):
+    """h = scale * unpack(packed), mirrored to the full symmetric matrix."""
+    _chk(h, torch.float32)
+    _chk(packed, torch.float32)
+    n = h.shape[0]
+    _call("slk_sym_unpack_f32", _ptr(packed), n, symmetric_block_rows(n), float(scale), _ptr(h), _stream())
+    return h
 
 
 @_timed("gptq_sweep")
@@ -470,7 +636,7 @@ def gptq_sweep_r(q, r32, rt, ud32, cb, d=None, err_sums=None):
         assert err_sums.shape == (q.shape[0], 2)
     nbytes = _lib.load().slk_gptq_sweep_r_ws_bytes(q.shape[0], q.shape[1]) if rt is not None else 0
     ws = _ws(nbytes, q.device) if nbytes else None
-    _lib.call("slk_gptq_sweep_r_err_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32),
+    _call("slk_gptq_sweep_r_err_f32", _ptr(q), _ptr(d), q.shape[0], q.shape[1], _ptr(r32),
               _ptr(rt[0]) if rt is not None else None, _ptr(rt[1]) if rt is not None else None, _ptr(ud32),
               cb.ref, _ptr(ws), nbytes, _ptr(err_sums), _stream())
     return q, d
@@ -485,7 +651,7 @@ def sweep_error(err_sums, row_scale=None, dampval=None, want_rows=False):
     r = err_sums.shape[0]
     out = torch.empty(1, dtype=torch.float32, device=err_sums.device)
     rows = torch.empty(r, dtype=torch.float32, device=err_sums.device) if want_rows else None
-    _lib.call("slk_sweep_error_f32", _ptr(err_sums), _ptr(row_scale), _ptr(dampval), r, _ptr(rows), _ptr(out), _stream())
+    _call("slk_sweep_error_f32", _ptr(err_sums), _ptr(row_scale), _ptr(dampval), r, _ptr(rows), _ptr(out), _stream())
     return out, rows
 
 
@@ -500,7 +666,7 @@ def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None, exact_leaf=False):
         _chk(u64, torch.float64)
     if e is None:
         e = torch.empty_like(q)
-    _lib.call("slk_gptq_sweep_f32", _ptr(q), _ptr(e), q.shape[0], q.shape[1], _ptr(u64) if exact_leaf else None,
+    _call("slk_gptq_sweep_f32", _ptr(q), _ptr(e), q.shape[0], q.shape[1], _ptr(u64) if exact_leaf else None,
               _ptr(u32), cb.ref, int(leaf), int(fanout), 1 if exact_leaf else 0, _stream())
     return q, e
 
@@ -518,7 +684,7 @@ def local_search(w, q, h, cb, moves):
     lib = _lib.load()
     nbytes = lib.slk_local_search_ws_bytes(r, n)
     ws = _ws(nbytes, w.device)
-    _lib.call("slk_local_search_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(ws), nbytes, _stream())
+    _call("slk_local_search_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(ws), nbytes, _stream())
     return q
 
 
@@ -528,5 +694,5 @@ def bias_delta(w, wq, mean_vec):
     _chk(wq, torch.float32)
     _chk(mean_vec, torch.float32)
     out = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
-    _lib.call("slk_bias_delta_f32", _ptr(w), _ptr(wq), _ptr(mean_vec), w.shape[0], w.shape[1], _ptr(out), _stream())
+    _call("slk_bias_delta_f32", _ptr(w), _ptr(wq), _ptr(mean_vec), w.shape[0], w.shape[1], _ptr(out), _stream())
     return out

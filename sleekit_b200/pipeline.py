@@ -9,9 +9,11 @@ layer's serial chain overlaps the others' -- same kernels, same results, no coll
 
 from __future__ import annotations
 
+import os
+
 import torch
 
-from . import _lib, ops
+from . import _lib, obq, ops
 from .scaling import quantize_scaled_device
 from .statistics import _device_scaling
 
@@ -51,8 +53,16 @@ class LayerSetQuantizer:
     """Holds the side streams; call it with lists of device tensors."""
 
     def __init__(self, codebook, scaling_mode="diag", act_order="diag", damp=0.01, nb_ls_moves=0, grid_size=100,
-                 min_factor=0.05, max_factor=1.0, streams=8, big_first=True):
+                 min_factor=0.05, max_factor=1.0, streams=8, big_first=True, batch_k2=None, k2_group=None):
+        """batch_k2: factor the Hessians of equal-sized layers in batched launches whose tile tasks share
+        one ticket queue (ops.chol_factor_batched) instead of one factorisation per layer; default on
+        when there is more than one stream (SLK_BATCH_K2=0/1 overrides).  k2_group: at most this many
+        layers per batched launch (SLK_K2_GROUP)."""
         ops.require_cuda()
+        env = os.environ.get("SLK_BATCH_K2")
+        self.batch_k2 = (int(streams) > 1 if batch_k2 is None else bool(batch_k2)) if env is None else env != "0"
+        self.k2_group = int(os.environ.get("SLK_K2_GROUP") or k2_group or 64)
+        self.k2_streams = [torch.cuda.Stream() for _ in range(4)]
         self.cb = codebook
         self.scaling_mode, self.act_order = scaling_mode, act_order
         self.damp, self.nb_ls_moves = damp, nb_ls_moves
@@ -78,6 +88,8 @@ class LayerSetQuantizer:
         L = len(Ws)
         dev = Ws[0].device
         errs = errs_out if errs_out is not None else torch.empty(L, dtype=torch.float32, device=dev)
+        if self.batch_k2 and L > 1 and obq.USE_CHOL_FORM:
+            return self._staged(Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order)
         main = torch.cuda.current_stream()
         start = torch.cuda.Event()
         start.record(main)
@@ -106,6 +118,83 @@ class LayerSetQuantizer:
             done = torch.cuda.Event()
             done.record(st)
             main.wait_event(done)
+        return outs, scales, errs
+
+    def _staged(self, Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order):
+        """The same pass in three stages so that the fp64 factorisations can be batched:
+        A (per layer, its stream): [copy in] -> scale search -> damp, ordering, scaled + permuted weights;
+        B (per group of equal-sized layers, a factor stream): ONE batched tile-task Cholesky launch;
+        C (per layer, its stream): sweep -> un-permute / de-scale -> layer error -> [copy out].
+        Same kernels and arithmetic as the per-layer path: identical results."""
+        L = len(Ws)
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        outs, scales = [None] * L, [None] * L
+        S = len(self.streams)
+        issue = self._issue_order([tuple(w.shape) for w in Ws], _order)
+        stream_of, stage, done_a = {}, {}, {}
+        for slot, i in enumerate(issue):
+            st = self.streams[slot % S]
+            stream_of[i] = st
+            if slot < S:
+                st.wait_event(start)
+            with torch.cuda.stream(st):
+                if _pre is not None:
+                    _pre(i)
+                sc = _device_scaling(Ws[i], self.cb, Hs[i], self.scaling_mode, self.grid_size, self.min_factor,
+                                     self.max_factor)
+                stage[i] = (sc, obq.gptq_prepare(Ws[i], Hs[i], self.cb, self.act_order, self.damp, self.nb_ls_moves,
+                                                 row_scale=sc, want_err=True))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done_a[i] = ev
+        # groups of equal n in issue order
+        groups, cur = [], []
+        for i in issue:
+            if cur and (Ws[cur[0]].shape[1] != Ws[i].shape[1] or len(cur) >= self.k2_group):
+                groups.append(cur)
+                cur = []
+            cur.append(i)
+        if cur:
+            groups.append(cur)
+        keep = []                                        # factor tensors stay alive until the join below
+        for g, members in enumerate(groups):
+            ks = self.k2_streams[g % len(self.k2_streams)]
+            if g < len(self.k2_streams):
+                ks.wait_event(start)
+            for i in members:
+                ks.wait_event(done_a[i])
+            with torch.cuda.stream(ks):
+                if len(members) == 1:
+                    i = members[0]
+                    facs = [ops.chol_factor(Hs[i], stage[i][1].order, stage[i][1].dampval)]
+                else:
+                    facs = ops.chol_factor_batched([Hs[i] for i in members], [stage[i][1].order for i in members],
+                                                   [stage[i][1].dampval for i in members])
+                ev = torch.cuda.Event()
+                ev.record(ks)
+            keep.append(facs)
+            for i, fac in zip(members, facs):
+                st = stream_of[i]
+                st.wait_event(ev)
+                with torch.cuda.stream(st):
+                    sc, gs = stage[i]
+                    q, (e, _) = obq.gptq_finish(gs, fac)
+                    errs[i:i + 1].copy_(e.reshape(1))
+                    if _post is not None:
+                        _post(i, q)
+                    if keep_outputs:
+                        outs[i], scales[i] = q, sc
+                        if not _in_capture:
+                            q.record_stream(main)
+                            sc.record_stream(main)
+        for st in list(self.streams[: min(S, L)]) + list(self.k2_streams[: min(len(self.k2_streams), len(groups))]):
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+        stage.clear()
+        del keep
         return outs, scales, errs
 
     def capture(self, Ws, Hs):
@@ -200,40 +289,111 @@ class HostPlan:
         return self.Q, self.err
 
 
+class ShardedLayerQuantizer:
+    """One big layer over the ranks of a process group (BASELINE config 5, SURVEY 8e / 8f-3).
+
+    Rank g holds a contiguous slice of the output rows of W (dist.row_partition) and a slice of the
+    calibration samples.  Per call:
+    1. K1 folds the local samples into running statistics; the count-weighted block upper triangle of
+       H and the mean are summed over the ranks by ONE all-reduce (dist.allreduce_statistics), after
+       which H and the mean are identical everywhere (statistics.py:76-87);
+    2. scale search, ordering, sweep, local search and row errors run on the local rows with no
+       communication (rows never interact: obq.py:106-137, :264-346, scaling.py:127-133);
+    3. the fp64 factor of H_opt -- the one step that is not row-parallel (obq.py:38-55) -- is SHARED:
+       tile row i of the tile-task Cholesky belongs to rank i % P, finished tiles are pushed into every
+       peer's workspace through NVLink peer stores (ops.chol_factor_dist), so every rank ends with the
+       complete factor at ~1/P of the fp64 work (dist_factor=False: every rank factors on its own);
+    4. the only other exchanges: the column residual sums of the err / sqerr orderings (n floats) and
+       the scalar layer error.
+    phases_ms (after a call with timing=True): device time per phase on this rank."""
+
+    def __init__(self, n, codebook, scaling_mode="diag", act_order="diag", damp=0.01, nb_ls_moves=0,
+                 bias_correction=False, grid_size=100, min_factor=0.05, max_factor=1.0, group=None, dist_factor=True):
+        import torch.distributed as tdist
+
+        ops.require_cuda()
+        self.n, self.cb, self.group = int(n), codebook, group
+        self.scaling_mode, self.act_order, self.damp, self.nb_ls_moves = scaling_mode, act_order, damp, nb_ls_moves
+        self.bias_correction = bias_correction
+        self.grid_size, self.min_factor, self.max_factor = grid_size, min_factor, max_factor
+        self.world = tdist.get_world_size(group) if (tdist.is_available() and tdist.is_initialized()) else 1
+        self.dist_factor = bool(dist_factor) and self.world > 1
+        self.pws = ops.PeerWorkspace(ops.chol_dist_ws_bytes(self.n), group) if self.dist_factor else None
+        self._token = torch.zeros(1, dtype=torch.float32, device=ops.device())
+        self.phases_ms = {}
+
+    def _barrier(self):
+        import torch.distributed as tdist
+
+        tdist.all_reduce(self._token, group=self.group)        # stream-ordered: no host synchronisation
+
+    def _factor_fn(self, Hd, order, dampval):
+        fac = ops.chol_factor_dist(Hd, order, dampval, self.pws, self._barrier)
+        import torch.distributed as tdist
+
+        tdist.all_reduce(fac[3], op=tdist.ReduceOp.MAX, group=self.group)   # a non-PD pivot seen by any rank
+        return fac
+
+    def close(self):
+        if self.pws is not None:
+            self.pws.close()
+            self.pws = None
+
+    def __call__(self, W_rows, X_rows, timing=False):
+        """W_rows [r_local, n], X_rows [S_local, n] fp32 on the device.  Returns (quantized rows,
+        scales, layer error (0-dim), H, mean)."""
+        import torch.distributed as tdist
+
+        from . import dist as sdist
+
+        dev = W_rows.device
+        n = self.n
+        marks = []
+
+        def mark(name):
+            if timing:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
+        H = torch.zeros((n, n), dtype=torch.float32, device=dev)
+        mean = torch.zeros(n, dtype=torch.float32, device=dev)
+        count = int(X_rows.shape[0])
+        if count:
+            ops.hessian_accum(X_rows.contiguous(), H, mean, 0.0, count)
+        mark("statistics")
+        H, mean, count = sdist.allreduce_statistics(H, mean, count, self.group)
+        mark("allreduce")
+        Hq = ops.remove_input_bias(H, mean) if self.bias_correction else H
+        sc = _device_scaling(W_rows, self.cb, Hq, self.scaling_mode, self.grid_size, self.min_factor, self.max_factor)
+        mark("scale_search")
+        reduce_cols = ((lambda c: sdist.allreduce_column_sums(c, self.group))
+                       if self.act_order in ("err", "sqerr") else None)
+        st = obq.gptq_prepare(W_rows, Hq, self.cb, self.act_order, self.damp, self.nb_ls_moves,
+                              colsum_reduce=reduce_cols, row_scale=sc, want_err=True)
+        mark("order_permute")
+        fac = None
+        if st.chol_form:
+            fac = self._factor_fn(Hq, st.order, st.dampval) if self.dist_factor else ops.chol_factor(Hq, st.order, st.dampval)
+        mark("factor")
+        q, (_, rows_err) = obq.gptq_finish(st, fac)
+        mark("sweep")
+        total_rows = torch.tensor([W_rows.shape[0]], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            tdist.all_reduce(total_rows, group=self.group)
+        err = sdist.allreduce_row_error_mean(rows_err, int(total_rows.item()), self.group)
+        mark("error")
+        if timing:
+            torch.cuda.synchronize()
+            self.phases_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+        return q, sc, err, Hq, mean
+
+
 def quantize_layer_sharded(W_rows, X_rows, codebook, scaling_mode="diag", act_order="diag", damp=0.01, nb_ls_moves=0,
                            bias_correction=False, grid_size=100, min_factor=0.05, max_factor=1.0, group=None):
-    """One big layer over the ranks of a process group (BASELINE config 5, SURVEY 8e).
-
-    W_rows [r_local, n]: this rank's contiguous slice of the output rows of W (dist.row_partition).
-    X_rows [S_local, n]: this rank's slice of the calibration samples.
-    1. every rank folds its samples into running statistics (K1) and ONE all-reduce of
-       [n*n + n + 1] floats makes H and the mean identical everywhere (statistics.py:76-87);
-    2. scale search, ordering, fp64 factor, sweep, local search and the row errors run on the local
-       rows with no communication (rows never interact); the factor is recomputed on every rank
-       (deterministic, hence identical) -- it is the term that does not shard;
-    3. the only other exchanges: the column residual sums of the err / sqerr orderings (n floats)
-       and the scalar layer error.
-    Returns (quantized rows [r_local, n], scales [r_local], layer error (0-dim tensor), H, mean)."""
-    import torch.distributed as tdist
-
-    from . import dist as sdist
-
-    ops.require_cuda()
-    dev = W_rows.device
-    n = W_rows.shape[1]
-    H = torch.zeros((n, n), dtype=torch.float32, device=dev)
-    mean = torch.zeros(n, dtype=torch.float32, device=dev)
-    count = int(X_rows.shape[0])
-    if count:
-        ops.hessian_accum(X_rows.contiguous(), H, mean, 0.0, count)
-    H, mean, count = sdist.allreduce_statistics(H, mean, count, group)
-    Hq = ops.remove_input_bias(H, mean) if bias_correction else H
-    sc = _device_scaling(W_rows, codebook, Hq, scaling_mode, grid_size, min_factor, max_factor)
-    reduce_cols = (lambda c: sdist.allreduce_column_sums(c, group)) if act_order in ("err", "sqerr") else None
-    q, (_, rows_err) = quantize_scaled_device(W_rows, sc, codebook, Hq, act_order, damp, nb_ls_moves,
-                                              colsum_reduce=reduce_cols, want_err=True)
-    total_rows = torch.tensor([W_rows.shape[0]], dtype=torch.int64, device=dev)
-    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
-        tdist.all_reduce(total_rows, group=group)
-    err = sdist.allreduce_row_error_mean(rows_err, int(total_rows.item()), group)
-    return q, sc, err, Hq, mean
+    """One-shot form of ShardedLayerQuantizer with the factor replicated on every rank (no peer
+    workspace to set up); see the class for the distributed factor."""
+    slq = ShardedLayerQuantizer(W_rows.shape[1], codebook, scaling_mode, act_order, damp, nb_ls_moves, bias_correction,
+                                grid_size, min_factor, max_factor, group, dist_factor=False)
+    return slq(W_rows, X_rows)

@@ -85,13 +85,13 @@ def compute_non_saturating_scaling(data, codebook, axis=0):
 
 
 def quantize_scaled_device(Wd, sd, quantizer, Hd=None, act_order="diag", damp=0.01, nb_ls_moves=0, check=False,
-                           colsum_reduce=None, want_err=False):
+                           colsum_reduce=None, want_err=False, factor_fn=None):
     """quantize_with_scaling on device tensors; returns de-scaled quantized weights (with want_err and
     a Hessian: (weights, (mean layer error, row errors)), see gptq_device)."""
     if Hd is not None:
         # scaling.py:73, 75-77, 80: the two row scalings ride on the column permutations
         return gptq_device(Wd, Hd, quantizer, act_order, damp, nb_ls_moves, check=check,
-                           colsum_reduce=colsum_reduce, row_scale=sd, want_err=want_err)
+                           colsum_reduce=colsum_reduce, row_scale=sd, want_err=want_err, factor_fn=factor_fn)
     assert not want_err
     x = ops.scale_rows(Wd, sd, 0)                                          # scaling.py:73
     x = ops.round_to_codebook(x, quantizer)[0]                              # scaling.py:79

@@ -10,6 +10,7 @@ import torch
 
 from oracle import sleekit_oracle as orc
 from sleekit_b200 import workloads as wl
+from tests.conftest import record_parity, scales_equivalent
 
 pytestmark = pytest.mark.gpu
 
@@ -62,17 +63,16 @@ def test_config3_full_h_scaling_bias_corrected_1p5_bit(api):
     np.testing.assert_array_equal(Hh, orc.strip_input_bias(Hd.cpu().numpy(), md.cpu().numpy()))
     sc_ref = orc.search_scale(W[:rows], grid, 0, H=Hh)
     sc_got = sc[:rows].cpu().numpy()
-    same = float((sc_got == sc_ref).mean())
-    e_ref = orc.weighted_sq_error(Hh, orc.quantize_scaled(W[:rows], sc_ref, grid) - W[:rows])
-    e_got = orc.weighted_sq_error(Hh, orc.quantize_scaled(W[:rows], sc_got, grid) - W[:rows])
-    print(f"config 3: full-H scale identical in {same:.3f} of rows; chosen-scale error ratio max "
-          f"{float((e_got / e_ref).max()):.6f}")
-    assert same >= 0.9 and np.all(e_got <= e_ref * (1 + 1e-4))
+    Wr = W[:rows]
+    scales_equivalent(sc_got, sc_ref, lambda s_: orc.weighted_sq_error(Hh, orc.quantize_scaled(Wr, s_, grid) - Wr),
+                      "test_config3", "[1024,4096] c=3 full-H search, first 24 rows")
     q_ref = orc.quantize_scaled(W[:rows], sc_got, grid, H=Hh, rule="diag", damp=0.01)
     q_got = q[:rows].cpu().numpy()
     a = agree(grid.index(orc.divide_rows(q_got, sc_got, 0)), grid.index(orc.divide_rows(q_ref, sc_got, 0)))
     eg, er = orc.mean_error(W[:rows], q_got, Hh), orc.mean_error(W[:rows], q_ref, Hh)
     print(f"config 3: code agreement {a:.6f}, layer error {eg:.6e} vs {er:.6e}; full layer error {err:.6e}")
+    record_parity("test_config3", "GPTQ code agreement (24 rows)", a, 0.999)
+    record_parity("test_config3", "GPTQ layer error rel diff", rel(eg, er), 1e-3)
     assert a >= 0.999 and rel(eg, er) <= 1e-3
     rtn = api.scaling.quantize_with_scaling(Wd, sc, cb)
     assert err < float(api.obq.quantization_error(Wd, rtn, Hc))
@@ -103,6 +103,8 @@ def test_config4_llama7b_mlp_gptq_local_search(api):
     a0 = agree(grid.index(orc.divide_rows(q0[:rows].cpu().numpy(), sch, 0)), grid.index(orc.divide_rows(ref0, sch, 0)))
     eg, er = orc.mean_error(W[:rows], q0[:rows].cpu().numpy(), Hh), orc.mean_error(W[:rows], ref0, Hh)
     print(f"config 4: GPTQ code agreement {a0:.6f}, error {eg:.6e} vs {er:.6e}")
+    record_parity("test_config4", "[11008,4096] c=4 GPTQ code agreement (16 rows)", a0, 0.999)
+    record_parity("test_config4", "GPTQ layer error rel diff", rel(eg, er), 1e-3)
     assert a0 >= 0.999 and rel(eg, er) <= 1e-3
     # local search from identical (W, Q, H): identical moves
     Ws = orc.divide_rows(W[:rows], sch, 0)
@@ -111,6 +113,7 @@ def test_config4_llama7b_mlp_gptq_local_search(api):
     ls_got = api.obq.quantize_local_search(Ws, Qs, Hh, cb, moves)
     a1 = agree(ls_got, ls_ref)
     print(f"config 4: local search ({moves} moves) agreement {a1:.6f}")
+    record_parity("test_config4", "local search 10 moves from identical (W,Q,H): weights equal", a1, 0.9999)
     assert a1 >= 0.9999
 
 
@@ -146,3 +149,61 @@ def test_config5_llama70b_down_proj_rank_share(api):
     assert float((cb.quantize_value(scaled) - scaled).abs().max()) <= 2e-6
     part = api.scaling.quantize_with_scaling(Wd[:32].contiguous(), sc[:32].contiguous(), cb, H=Hd)
     assert torch.equal(part, q[:32])
+
+
+# ---------------------------------------------------------------------------
+# n > 4096: the two-level lazy batching of the sweep (2048-column super blocks + one K = 2048 push per
+# super block, sweep.cu slk_gptq_sweep_r_err_f32) against the oracle's recursion (obq.py:121-137)
+# ---------------------------------------------------------------------------
+
+
+def _wide_layer_vs_oracle(api, r, n, c, lid, test, moves=0):
+    W, Hd, md = device_layer(r, n, lid, 2048)           # S = 2048 < n: rank-deficient H, PD through damping
+    cb, grid = api.codebook.UniformCodebook(c, -1, 1), orc.UniformGrid(c, -1, 1)
+    Wd = torch.from_numpy(W).cuda()
+    Hh = Hd.cpu().numpy()
+    sc = api.scaling.compute_min_mse_scaling(Wd, cb, 0, H=Hd.diagonal().contiguous())
+    sch = orc.search_scale(W, grid, 0, H=Hh.diagonal())
+    hdiag = Hh.diagonal().copy()
+    scales_equivalent(sc.cpu().numpy(), sch, lambda s_: orc.weighted_sq_error(hdiag, orc.quantize_scaled(W, s_, grid) - W),
+                      test, f"[{r},{n}] c={c} diag-H search")
+    sc = torch.from_numpy(sch).cuda()                    # identical scales on both sides from here on
+    q = api.scaling.quantize_with_scaling(Wd, sc, cb, H=Hd)
+    err_dev = float(api.obq.quantization_error(Wd, q, Hd))
+    got = q.cpu().numpy()
+    ref = orc.quantize_scaled(W, sch, grid, H=Hh, rule="diag", damp=0.01)   # fp64 LAPACK factor + reference recursion
+    a = agree(grid.index(orc.divide_rows(got, sch, 0)), grid.index(orc.divide_rows(ref, sch, 0)))
+    eg, er = orc.mean_error(W, got, Hh), orc.mean_error(W, ref, Hh)
+    print(f"{test}: [{r},{n}] c={c}: code agreement {a:.6f}, layer error {eg:.6e} vs oracle {er:.6e}")
+    record_parity(test, f"[{r},{n}] c={c} two-level sweep: code agreement", a, 0.999)
+    record_parity(test, f"[{r},{n}] c={c} two-level sweep: layer error rel diff", rel(eg, er), 1e-3)
+    assert a >= 0.999 and rel(eg, er) <= 1e-3
+    assert rel(err_dev, er) <= 1e-3                      # K6 on the device agrees with the oracle's error too
+    # the fused path's own error (from the sweep residuals) as well
+    from sleekit_b200.scaling import quantize_scaled_device
+
+    q2, (e2, _) = quantize_scaled_device(Wd, sc, cb, Hd, "diag", 0.01, 0, want_err=True)
+    assert torch.equal(q2, q)
+    record_parity(test, f"[{r},{n}] layer error from sweep residuals rel diff vs oracle", rel(float(e2), er), 1e-3)
+    assert rel(float(e2), er) <= 1e-3
+    if moves:
+        Ws = orc.divide_rows(W, sch, 0)
+        Qs = grid(orc.divide_rows(got, sch, 0))
+        ls_ref = orc.local_search(Ws, Qs, Hh, grid, moves)
+        ls_got = api.obq.quantize_local_search(Ws, Qs, Hh, cb, moves)
+        a1 = agree(ls_got, ls_ref)
+        record_parity(test, f"[{r},{n}] local search {moves} moves: weights equal", a1, 0.9999)
+        assert a1 >= 0.9999
+
+
+@pytest.mark.parametrize("r,n,c", [(16, 4352, 8), (16, 6144, 8), (24, 6144, 4)])
+def test_two_level_sweep_vs_oracle(api, r, n, c):
+    """[16,4352]: super blocks 2048 + 2048 + 256 (a ragged last one); [.,6144]: three full super blocks."""
+    _wide_layer_vs_oracle(api, r, n, c, 61, "test_two_level_sweep_vs_oracle")
+
+
+def test_config4_down_proj_vs_oracle(api):
+    """Llama-2-7B down-proj shape: 32 of its 4096 rows over the full n = 11008 (six super blocks, the last
+    one ragged: 11008 = 5 * 2048 + 768), 4-entry codebook, + 10 local-search moves; the oracle runs the
+    reference's whole path once (one fp64 LAPACK factor of an 11008 x 11008 matrix, ~1 min of CPU)."""
+    _wide_layer_vs_oracle(api, 32, 11008, 4, 43, "test_config4_down_proj_vs_oracle", moves=10)
