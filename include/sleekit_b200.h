@@ -251,6 +251,16 @@ int slk_peer_free(void* dptr);
 int slk_sym_pack_f32(const float* h, int64_t n, int64_t bs, float scale, float* packed, void* stream);
 int slk_sym_unpack_f32(const float* packed, int64_t n, int64_t bs, float scale, float* h, void* stream);
 
+/* Streams for the layer-set driver: one real CUDA stream per independent layer, with a priority
+ * (0 default, negative = higher, clamped to the device's range). */
+int slk_stream_create(int priority, void** stream_host);
+int slk_stream_destroy(void* stream);
+/* Process-wide tuning knobs, by name: "sweep_ctas" = CTAs wanted per macro-block sweep launch (0 = the
+ * single-layer default; a layer set that runs many sweeps side by side prefers fewer, taller CTAs). */
+int slk_set_option(const char* name, int64_t value);
+
+/* Development aid: stores %globaltimer (ns, uint64) into *slot when the stream reaches the call. */
+int slk_debug_timestamp(void* slot, void* stream);
 /* Development aid: per-tile-task trace of the Cholesky kernel (8 int64 per task); NULL disables. */
 int slk_debug_chol_trace(void* buf);
 /* Same for the macro-block sweep kernel: 8 int64 phase clocks per 32-column block of CTA 0. */
@@ -299,8 +309,19 @@ size_t slk_local_search_ws_bytes(int64_t r, int64_t n);
 int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n,
                          const slk_codebook* cb_host, int32_t moves, void* ws, size_t ws_bytes,
                          void* stream);
+/* The same moves in instalments (LocalSearchQuantizer.do_move, obq.py:338-346: one move per call): the
+ * workspace keeps P = (Q - W) H between calls.  resume = 0 forms it, resume = 1 continues from the P the
+ * previous call left for the same q, w, h, so a move costs one pass over the gains instead of a GEMM. */
+int slk_local_search_step_f32(const float* w, float* q, const float* h, int64_t r, int64_t n,
+                              const slk_codebook* cb_host, int32_t moves, void* ws, size_t ws_bytes,
+                              int32_t resume, void* stream);
 
 /* bias correction  bias += ((W - Wq) * mean).sum(1)          statistics.py:187-190 */
+/* _compute_mse with H None or 1-D                              scaling.py:84-95
+ * out[row] = sum_j h[j] * e[row, j]^2 (h NULL: sum of squares); the 2-D case is slk_hweighted_error_*. */
+int slk_row_wsq_f32(const float* e, const float* h, int64_t r, int64_t n, float* out, void* stream);
+int slk_row_wsq_f64(const double* e, const double* h, int64_t r, int64_t n, double* out, void* stream);
+
 int slk_bias_delta_f32(const float* w, const float* wq, const float* mean, int64_t r, int64_t n,
                        float* delta, void* stream);
 

@@ -89,6 +89,10 @@ SIGNATURES = {
     "slk_sym_unpack_f32": (_INT, [_P, _I64, _I64, C.c_float, _P, _P]),
     "slk_gptq_sweep_r_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_codebook_breaks_host": (_INT, [_CB, _P]),
+    "slk_stream_create": (_INT, [_INT, _P]),
+    "slk_stream_destroy": (_INT, [_P]),
+    "slk_set_option": (_INT, [C.c_char_p, _I64]),
+    "slk_debug_timestamp": (_INT, [_P, _P]),
     "slk_debug_chol_trace": (_INT, [_P]),
     "slk_debug_sweep_trace": (_INT, [_P]),
     "slk_debug_scale_search_direct": (_INT, [_INT]),
@@ -100,6 +104,9 @@ SIGNATURES = {
     "slk_gptq_sweep_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _CB, _I32, _I32, _I32, _P]),
     "slk_local_search_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_local_search_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _P]),
+    "slk_local_search_step_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _I32, _P]),
+    "slk_row_wsq_f32": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "slk_row_wsq_f64": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "slk_bias_delta_f32": (_INT, [_P, _P, _P, _I64, _I64, _P, _P]),
     "slk_selftest_fastdiv_f32": (_INT, [_P, _I32, _P, _P]),
     "slk_tc_gemm_ws_bytes": (_SZ, [_I64, _I64, _I64]),

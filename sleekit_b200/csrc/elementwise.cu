@@ -560,6 +560,25 @@ __global__ void __launch_bounds__(256) bias_delta_kernel(const float* __restrict
   }
 }
 
+// out[row] = sum_j h[j] * e[row, j]^2  (h NULL: plain sum of squares) -- the None / 1-D branches of
+// _compute_mse (scaling.py:84-95); products and squares rounded as numpy rounds them, sums in fp64.
+template <typename T>
+__global__ void __launch_bounds__(256) row_wsq_kernel(const T* __restrict__ e, const T* __restrict__ h, int64_t r, int64_t n,
+                                                      T* __restrict__ out) {
+  __shared__ double scratch[32];
+  typedef Ieee<T> F;
+  for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+      const T v = e[row * n + j];
+      const T sq = F::mul(v, v);
+      acc += (double)(h ? F::mul(h[j], sq) : sq);
+    }
+    acc = block_sum<double>(acc, scratch);
+    if (threadIdx.x == 0) out[row] = (T)acc;
+  }
+}
+
 // H[i][j] = H[j][i] for the 32x32 tiles (ti > tj) that lie below the block diagonal of the symmetric
 // upload (tiles of one copy block share floor(t / tpb)); one CTA per tile pair, transposed through
 // shared memory so that both the read and the write are coalesced.
@@ -860,6 +879,22 @@ int slk_selftest_fastdiv_f32(const float* divisors, int32_t count, uint64_t* mis
   SLK_CUDA(cudaMemsetAsync(mismatches, 0, (size_t)count * sizeof(uint64_t), (cudaStream_t)stream));
   dim3 grid((unsigned)(sm_count() * 8), (unsigned)count);
   selftest_fastdiv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(divisors, (unsigned long long*)mismatches, 1ull << 32);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+/* _compute_mse, H None or 1-D (scaling.py:84-95): out[row] = sum_j h[j] e[row, j]^2 (h may be NULL) */
+int slk_row_wsq_f32(const float* e, const float* h, int64_t r, int64_t n, float* out, void* stream) {
+  SLK_REQUIRE(e && out && r >= 1 && n >= 1, "bad arguments");
+  int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  row_wsq_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+int slk_row_wsq_f64(const double* e, const double* h, int64_t r, int64_t n, double* out, void* stream) {
+  SLK_REQUIRE(e && out && r >= 1 && n >= 1, "bad arguments");
+  int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  row_wsq_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

@@ -39,9 +39,10 @@ __device__ __forceinline__ Best warp_best(Best x) {
   return x;
 }
 
-__global__ void __launch_bounds__(256) local_search_kernel(float* __restrict__ Q, const float* __restrict__ P,
+__global__ void __launch_bounds__(256) local_search_kernel(float* __restrict__ Q, float* __restrict__ P,
                                                            const float* __restrict__ H, const float* __restrict__ hdiag,
-                                                           int64_t r, int64_t n, DevGrid<float> g, int moves) {
+                                                           int64_t r, int64_t n, DevGrid<float> g, int moves,
+                                                           int keep_p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* p = (float*)smem_raw;                       // [n]
   uint16_t* code = (uint16_t*)(p + n);               // [n]
@@ -99,7 +100,10 @@ __global__ void __launch_bounds__(256) local_search_kernel(float* __restrict__ Q
       if (tid == 0) code[col] = (uint16_t)s_newk;
       __syncthreads();
     }
-    for (int64_t j = tid; j < n; j += blockDim.x) Q[row * n + j] = grid_value_of_index(g, code[j]);
+    for (int64_t j = tid; j < n; j += blockDim.x) {
+      Q[row * n + j] = grid_value_of_index(g, code[j]);
+      if (keep_p) P[row * n + j] = p[j];             // (Q - W) H of the row after its moves, for a later resume
+    }
     __syncthreads();
   }
 }
@@ -118,8 +122,26 @@ size_t slk_local_search_ws_bytes(int64_t r, int64_t n) {
   return bytes;
 }
 
+static int local_search_impl(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
+                             int32_t moves, void* ws, size_t ws_bytes, int resume, int keep_p, void* stream);
+
 int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
                          int32_t moves, void* ws, size_t ws_bytes, void* stream) {
+  return local_search_impl(w, q, h, r, n, cb, moves, ws, ws_bytes, 0, 0, stream);
+}
+
+/* The same moves in instalments (LocalSearchQuantizer.do_move, obq.py:338-346, one move per call): the
+   workspace keeps P = (Q - W) H between calls; resume = 0 forms it (2 r n^2 flop), resume = 1 continues from
+   the P a previous call left for the SAME q, w, h -- a move then costs one pass over the gains, not a GEMM. */
+int slk_local_search_step_f32(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
+                              int32_t moves, void* ws, size_t ws_bytes, int32_t resume, void* stream) {
+  return local_search_impl(w, q, h, r, n, cb, moves, ws, ws_bytes, resume ? 1 : 0, 1, stream);
+}
+
+}  // extern "C"
+
+static int local_search_impl(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
+                             int32_t moves, void* ws, size_t ws_bytes, int resume, int keep_p, void* stream) {
   int rc = check_codebook(cb);
   if (rc) return rc;
   SLK_REQUIRE(r >= 0 && n >= 1 && moves >= 0, "bad arguments");
@@ -136,7 +158,9 @@ int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, in
   SLK_LAUNCH_CHECK();
   // P = (Q - W) @ H                                           obq.py:229-231
   void* gws = (char*)ws + align256((size_t)r * n * sizeof(float)) + align256((size_t)n * sizeof(float));
-  if (n % 4 == 0 && n >= 32 && tc_gemm_usable(q, n, h, n) && (uintptr_t)w % 16 == 0) {
+  if (resume) {
+    rc = SLK_OK;                                               // P of the previous instalment is still valid
+  } else if (n % 4 == 0 && n >= 32 && tc_gemm_usable(q, n, h, n) && (uintptr_t)w % 16 == 0) {
     // tcgen05, fp32-faithful 3xTF32; H is symmetric, hence its own K-major B operand
     TcParams tp;
     tp.C = P; tp.ldc = n; tp.R = nullptr; tp.R2 = nullptr; tp.ldr = 0; tp.M = r; tp.N = n; tp.K = n;
@@ -151,9 +175,7 @@ int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, in
   if (smem > 48 * 1024)
     SLK_CUDA(cudaFuncSetAttribute(local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
-  local_search_kernel<<<grid, 256, smem, st>>>(q, P, h, hdiag, r, n, make_grid<float>(cb), moves);
+  local_search_kernel<<<grid, 256, smem, st>>>(q, P, h, hdiag, r, n, make_grid<float>(cb), moves, keep_p);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
-
-}  // extern "C"

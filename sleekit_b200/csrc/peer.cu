@@ -10,7 +10,46 @@
 
 using namespace slk;
 
+namespace slk {
+__global__ void timestamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}  // namespace slk
+
 extern "C" {
+
+/* A CUDA stream of the given priority on the current device (0 = default, negative = higher; clamped to
+   the device's range).  The layer-set driver needs one real stream per independent layer -- a framework's
+   stream pool may hand out the same few streams again and again -- and high-priority streams for the
+   longest chains.  *stream_host receives the cudaStream_t. */
+int slk_stream_create(int priority, void** stream_host) {
+  SLK_REQUIRE(stream_host, "NULL output");
+  int lo = 0, hi = 0;
+  SLK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (largest number)
+  if (priority < hi) priority = hi;
+  if (priority > lo) priority = lo;
+  cudaStream_t s;
+  SLK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority));
+  *stream_host = (void*)s;
+  return SLK_OK;
+}
+
+int slk_stream_destroy(void* stream) {
+  SLK_REQUIRE(stream, "NULL stream");
+  SLK_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+  return SLK_OK;
+}
+
+/* development aid (tools/timeline.py): a one-thread kernel that stores %globaltimer (ns) into *slot when the
+   stream reaches it -- stream-ordered phase marks inside a multi-stream CUDA graph */
+int slk_debug_timestamp(void* slot, void* stream) {
+  SLK_REQUIRE(slot, "NULL slot");
+  timestamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)slot);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
 
 /* bytes of device memory on the current device; *dptr_host receives the pointer, handle_host (64
    bytes, host) the cudaIpcMemHandle_t to send to the peers */

@@ -18,6 +18,8 @@
 
 #include <stdlib.h>
 
+static int64_t g_opt_sweep_ctas = 0;     // slk_set_option("sweep_ctas", v)
+
 namespace slk {
 
 constexpr int LEAF_ROWS = 64;  // rows (threads) per CTA of the leaf kernel
@@ -636,11 +638,14 @@ struct MacroSmem {
   static constexpr int NLEAF = 4 * R;                       // threads of the leaf
   static constexpr int NSLOT = 8 * R;                       // (row, 4-column) output slots of a block
   static constexpr int HELP = FT - NLEAF;                   // threads free while the leaf runs
-  static constexpr int KGH = HELP >= NSLOT ? HELP / NSLOT : 1;   // their k groups
+  // ONE k group for the look-ahead whatever the tile height: the order in which a row's products are
+  // summed must not depend on R, so that a row gets the same bits however the rows are cut into CTAs
+  // (row slices, row-sharded runs and the layer-set driver's taller tiles all agree with the full run)
+  static constexpr int KGH = 1;
   static constexpr int SPT = HELP >= NSLOT ? 1 : NSLOT / HELP;   // slots per helper thread
   float Dm[R][MB_PITCH];                    // D = W - Q of this macro block
   PanelBufs<COMPACT> pb;
-  float red[KG][R][33];
+  float red[4][R][33];                      // tail product: four chains of 8 k-steps, summed in a fixed order
   float red2[KGH][R][33];                   // look-ahead part of the next block's product
   float XV[16];                             // codebook breakpoints X[0..7] (X[0] unused) and values V[0..7]
   float Qs[R][33];
@@ -737,22 +742,28 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
       if (has_next) prefetch_panel(a + 32, buf ^ 1);
     }
     if (tr) tr[1] = clock64();
-    // ---- (1) tail: D[:, a-32:a] R[a-32:a, J], the 32 k split over the k groups --------------------
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ka > 0) {
-      constexpr int KPG = 32 / KG;
-      const int kb = ka - 32 + kg * KPG;
+    // ---- (1) tail: D[:, a-32:a] R[a-32:a, J]: four chains of 8 k-steps each (chain c = k 8c..8c+7), dealt to
+    // the KG thread groups, summed ((c0 + c1) + c2) + c3 -- the same association for every tile height R
+    constexpr int CPG = 4 / KG;                        // chains per thread group
+    float acc[CPG][4];
 #pragma unroll
-      for (int kk = 0; kk < KPG; ++kk) {
-        const float e = sm.Dm[lrow][kb + kk];
-        const float* rp;
-        if constexpr (COMPACT) rp = &sm.pb.Rt[buf][kg * KPG + kk][seg * 4];
-        else rp = &sm.pb.Rs[buf][kb + kk][seg * 4];
-        const float4 u = *reinterpret_cast<const float4*>(rp);
-        acc[0] = __fmaf_rn(e, u.x, acc[0]);
-        acc[1] = __fmaf_rn(e, u.y, acc[1]);
-        acc[2] = __fmaf_rn(e, u.z, acc[2]);
-        acc[3] = __fmaf_rn(e, u.w, acc[3]);
+    for (int c = 0; c < CPG; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    if (ka > 0) {
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) {
+        const int koff = (kg * CPG + c) * 8;           // within the last 32 columns of D
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const float e = sm.Dm[lrow][ka - 32 + koff + kk];
+          const float* rp;
+          if constexpr (COMPACT) rp = &sm.pb.Rt[buf][koff + kk][seg * 4];
+          else rp = &sm.pb.Rs[buf][ka - 32 + koff + kk][seg * 4];
+          const float4 u = *reinterpret_cast<const float4*>(rp);
+          acc[c][0] = __fmaf_rn(e, u.x, acc[c][0]);
+          acc[c][1] = __fmaf_rn(e, u.y, acc[c][1]);
+          acc[c][2] = __fmaf_rn(e, u.z, acc[c][2]);
+          acc[c][3] = __fmaf_rn(e, u.w, acc[c][3]);
+        }
       }
     }
     {
@@ -761,7 +772,8 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
       for (int j = 0; j < 4; ++j) {
         sm.leaf.U[i][seg * 4 + j] = cur.ud[j];
         sm.leaf.U[i][32 + seg * 4 + j] = 0.0f;
-        sm.red[kg][lrow][seg * 4 + j] = acc[j];
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) sm.red[kg * CPG + c][lrow][seg * 4 + j] = acc[c][j];
       }
       if (tid < 32) sm.leaf.Uy[tid] = cur.rdiag;
     }
@@ -771,7 +783,7 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
       for (int j = 0; j < 4; ++j) {
         float t = sm.red[0][lrow][seg * 4 + j];
 #pragma unroll
-        for (int q = 1; q < KG; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
+        for (int q = 1; q < 4; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
 #pragma unroll
         for (int q = 0; q < SM::KGH; ++q) t = __fadd_rn(t, sm.red2[q][lrow][seg * 4 + j]);
         sm.Qs[lrow][seg * 4 + j] = __fadd_rn(t, cur.pa[j]);
@@ -882,10 +894,93 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
   }
 }
 
+extern "C" int slk_set_option(const char* name, int64_t value) {
+  SLK_REQUIRE(name, "NULL option name");
+  if (strcmp(name, "sweep_ctas") == 0) { g_opt_sweep_ctas = value > 0 ? value : 0; return SLK_OK; }
+  set_error("unknown option %s", name);
+  return SLK_ERR_ARG;
+}
+
 extern "C" int slk_debug_sweep_trace(void* buf) {
   long long* p = (long long*)buf;
   SLK_CUDA(cudaMemcpyToSymbol(g_sweep_trace, &p, sizeof(p)));
   return SLK_OK;
+}
+
+// ---- CUDA-core push for narrow layers -------------------------------------------------------------
+// P[:, 0:N] += D[:, 0:K] Rm[0:K, 0:N]  (the macro-block GEMM of the sweep) as a light fp32 FMA kernel:
+// 64 x 64 tiles, 256 threads, 16 accumulators, ~17 KB of shared memory.  A tensor-core tile of
+// tc_gemm.cu owns a whole SM (192 KB of shared memory, 36 K registers), so inside a layer SET it can
+// not run beside a resident Cholesky CTA of another layer and the sweep stalls at its first push; for
+// narrow layers (n <= 1024: K = 256, N <= 768, a few hundred MFLOP) this kernel costs microseconds,
+// is exact fp32 FMA arithmetic in k order (deterministic) and shares an SM with anything.
+constexpr int PS_BM = 64, PS_BN = 64, PS_BK = 16;
+__global__ void __launch_bounds__(256, 4) push_simt_kernel(const float* __restrict__ D, int64_t ldd,
+                                                           const float* __restrict__ Rm, int64_t ldr,
+                                                           float* __restrict__ P, int64_t ldp, int64_t M, int64_t N,
+                                                           int64_t K) {
+  __shared__ __align__(16) float As[PS_BK][PS_BM + 4];
+  __shared__ __align__(16) float Bs[PS_BK][PS_BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * PS_BM, n0 = (int64_t)blockIdx.x * PS_BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const int ar = tid >> 2, ak = (tid & 3) * 4;          // A: row ar, k quad ak
+  const int bk = tid >> 4, bn = (tid & 15) * 4;         // B: k row bk, column quad bn
+  for (int64_t k0 = 0; k0 < K; k0 += PS_BK) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + ar < M) {
+      const float* src = D + (m0 + ar) * ldd + k0 + ak;
+      if (k0 + ak + 3 < K) a = *reinterpret_cast<const float4*>(src);
+      else {
+        if (k0 + ak < K) a.x = src[0];
+        if (k0 + ak + 1 < K) a.y = src[1];
+        if (k0 + ak + 2 < K) a.z = src[2];
+      }
+    }
+    if (k0 + bk < K) {
+      const float* src = Rm + (k0 + bk) * ldr + n0 + bn;
+      if (n0 + bn + 3 < N) b = *reinterpret_cast<const float4*>(src);
+      else {
+        if (n0 + bn < N) b.x = src[0];
+        if (n0 + bn + 1 < N) b.y = src[1];
+        if (n0 + bn + 2 < N) b.z = src[2];
+      }
+    }
+    __syncthreads();                                    // the previous tile has been consumed
+    As[ak][ar] = a.x; As[ak + 1][ar] = a.y; As[ak + 2][ar] = a.z; As[ak + 3][ar] = a.w;
+    *reinterpret_cast<float4*>(&Bs[bk][bn]) = b;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < PS_BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float ax[4] = {av.x, av.y, av.z, av.w}, bx[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(ax[i], bx[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    float* dst = P + row * ldp + n0 + tx * 4;
+    if (n0 + tx * 4 + 3 < N) {
+      float4 c = *reinterpret_cast<float4*>(dst);
+      c.x = __fadd_rn(c.x, acc[i][0]); c.y = __fadd_rn(c.y, acc[i][1]);
+      c.z = __fadd_rn(c.z, acc[i][2]); c.w = __fadd_rn(c.w, acc[i][3]);
+      *reinterpret_cast<float4*>(dst) = c;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + tx * 4 + j < N) dst[j] = __fadd_rn(dst[j], acc[i][j]);
+    }
+  }
 }
 
 template <int R, bool COMPACT>
@@ -965,7 +1060,8 @@ extern "C" int slk_gptq_sweep_r_err_f32(float* q, float* d, int64_t r, int64_t n
     const char* ev = getenv("SLK_SWEEP_CTAS");
     want_env = ev ? atoll(ev) : 0;
   }
-  const int64_t want = want_env > 0 ? want_env : ((int64_t)sm_count() / 48) * 16;   // 48 on a B200: 768 rows -> 16 per CTA
+  const int64_t want = want_env > 0 ? want_env : (g_opt_sweep_ctas > 0 ? g_opt_sweep_ctas
+                                                  : ((int64_t)sm_count() / 48) * 16);   // 48 on a B200: 768 rows -> 16 per CTA
   const GridBreaks xv = make_breaks(cb);        // codebook breakpoints for the leaf's compare tree
   auto fused = [&](int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo) -> int {
     if (n % 4 == 0 && c1 - c0 <= MB_COLS && (((uintptr_t)r32) & 15) == 0) {
@@ -983,7 +1079,20 @@ extern "C" int slk_gptq_sweep_r_err_f32(float* q, float* d, int64_t r, int64_t n
   float* dhi = pacc + (size_t)r * n;
   float* dlo = dhi + (size_t)r * n;
   SLK_CUDA(cudaMemsetAsync(pacc, 0, (size_t)r * n * sizeof(float), st));
+  // narrow layers push on the CUDA cores (push_simt_kernel); SLK_SWEEP_SIMT_N: widest such layer (0 = never)
+  static int64_t simt_n = -1;
+  if (simt_n < 0) {
+    const char* ev = getenv("SLK_SWEEP_SIMT_N");
+    simt_n = ev ? atoll(ev) : 1024;
+  }
+  const bool simt = n <= simt_n && (((uintptr_t)d) & 15) == 0;
   auto push = [&](int64_t k0, int64_t k1, int64_t c0, int64_t c1) -> int {   // Pacc[:, c0:c1] += D[:, k0:k1] R[k0:k1, c0:c1]
+    if (simt) {
+      dim3 grid((unsigned)ceil_div(c1 - c0, PS_BN), (unsigned)ceil_div(r, PS_BM));
+      push_simt_kernel<<<grid, 256, 0, st>>>(d + k0, n, r32 + k0 * n + c0, n, pacc + c0, n, r, c1 - c0, k1 - k0);
+      SLK_LAUNCH_CHECK();
+      return SLK_OK;
+    }
     TcParams p;
     p.C = pacc + c0; p.ldc = n; p.R = nullptr; p.R2 = nullptr; p.ldr = 0;
     p.M = r; p.N = c1 - c0; p.K = k1 - k0;
@@ -998,7 +1107,7 @@ extern "C" int slk_gptq_sweep_r_err_f32(float* q, float* d, int64_t r, int64_t n
     const int64_t S1 = (S0 + super) < n ? (S0 + super) : n;
     for (int64_t s0 = S0; s0 < S1; s0 += SWEEP_MB) {
       const int64_t e0 = (s0 + SWEEP_MB) < S1 ? (s0 + SWEEP_MB) : S1;
-      rc = fused(s0, e0, pacc, e0 < n ? dhi : nullptr, dlo);
+      rc = fused(s0, e0, pacc, (e0 < n && !simt) ? dhi : nullptr, dlo);
       if (rc) return rc;
       if (e0 < S1 && (rc = push(s0, e0, e0, S1))) return rc;
     }

@@ -40,7 +40,7 @@ def remove_input_bias(H, input_bias):
     assert H.shape[0] == H.shape[1]
     assert H.shape[0] == input_bias.shape[0]
     dt = cv.torch_float(np.result_type(cv.float_dtype_of(H), cv.float_dtype_of(input_bias)))
-    out = ops.remove_input_bias(cv.to_dev(H, dt), cv.to_dev(input_bias, dt))
+    out = ops.remove_input_bias(cv.to_dev_cached(H, dt), cv.to_dev_cached(input_bias, dt))
     return cv.back(out, H)
 
 
@@ -59,6 +59,8 @@ def remove_dead_values(H, W):
     dead = d == 0
     H[dead, dead] = fill
     W[:, dead] = 0
+    cv.invalidate(H)      # device copies of the arrays just patched are stale
+    cv.invalidate(W)
 
 
 def _raise_if_not_pd(info):
@@ -69,7 +71,7 @@ def _raise_if_not_pd(info):
 
 def compute_hessian_chol(H):
     """Upper factor U with inv(H) = U^T U, fp64 (obq.py:38-55)."""
-    h = cv.to_dev(H, torch.float64)
+    h = cv.to_dev_cached(H, torch.float64)
     assert h.ndim == 2 and h.shape[0] == h.shape[1]
     u64, _, info = ops.hinv(h, want64=True, want32=False)
     if not cv.is_tensor(H):
@@ -103,8 +105,8 @@ def compute_hessian_order(W, H, quantizer, act_order):
     """Column ordering heuristics (obq.py:58-86); returns int64 indices."""
     if act_order not in ("err", "sqerr", "combined_diag", "inv_diag", "pivot", "diag", "none"):
         raise RuntimeError(f"Invalid act_order value {act_order}")
-    Wd = cv.to_dev(W, torch.float32)
-    Hd = cv.to_dev(H)
+    Wd = cv.to_dev_cached(W, torch.float32)
+    Hd = cv.to_dev_cached(H)
     order = _device_order(Wd, Hd, quantizer, act_order)
     return cv.back(order, W)
 
@@ -115,10 +117,10 @@ def channelwise_error(W, Q, H):
     dt = cv.torch_float(dt_np)
     # the residual is formed in the dtype of W and Q, then promoted with H (numpy semantics)
     wq = cv.torch_float(np.result_type(cv.float_dtype_of(W), cv.float_dtype_of(Q)))
-    Wd, Qd = cv.to_dev(W, wq), cv.to_dev(Q, wq)
+    Wd, Qd = cv.to_dev_cached(W, wq), cv.to_dev_cached(Q, wq)
     lead = Wd.shape[:-1]
     Wd, Qd = Wd.reshape(-1, Wd.shape[-1]), Qd.reshape(-1, Qd.shape[-1])
-    Hd = cv.to_dev(H, dt)
+    Hd = cv.to_dev_cached(H, dt)
     if wq == dt:
         err = ops.hweighted_error(Wd, Qd, Hd)
     else:
@@ -131,7 +133,7 @@ def quantization_error(W, Q, H):
     if cv.is_tensor(W):
         return ops.mean(channelwise_error(W, Q, H).reshape(-1).contiguous())
     dt_np = np.result_type(cv.float_dtype_of(W), cv.float_dtype_of(Q), cv.float_dtype_of(H))
-    rows = channelwise_error(cv.to_dev(W), cv.to_dev(Q), cv.to_dev(H))
+    rows = channelwise_error(cv.to_dev_cached(W), cv.to_dev_cached(Q), cv.to_dev_cached(H))
     m = ops.mean(rows.reshape(-1).contiguous())
     return np.dtype(dt_np).type(m.item())  # a numpy scalar, so f-strings print as the reference's do
 
@@ -145,16 +147,18 @@ def _quantize_opt_block(Q, E, Hinv, quantizer, min_block_size, num_blocks):
     split further (the result is the same algebra; the reference's own test_blockobq shows the
     blocking does not matter)."""
     if cv.is_tensor(Q):
-        u64 = cv.to_dev(Hinv, torch.float64)
+        u64 = cv.to_dev_cached(Hinv, torch.float64)
         ops.gptq_sweep(Q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks, e=E,
                        exact_leaf=True)
         return
     q = cv.to_dev(Q, torch.float32)
-    u64 = cv.to_dev(Hinv, torch.float64)
+    u64 = cv.to_dev_cached(Hinv, torch.float64)
     q, e = ops.gptq_sweep(q, u64, u64.to(torch.float32), quantizer, _sweep_leaf(min_block_size), num_blocks,
                           exact_leaf=True)
     Q[...] = cv.to_host(q)
     E[...] = cv.to_host(e)
+    cv.invalidate(Q)
+    cv.invalidate(E)
 
 
 def _quantize_opt_core(Q, E, Hinv, quantizer):
@@ -277,8 +281,8 @@ def quantize_opt(W, H, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, mi
     assert H.shape[0] == H.shape[1]
     assert H.shape[0] == W.shape[1]
     assert min_block_size >= 1
-    Wd = cv.to_dev(W, torch.float32)   # obq.py:195-196: both cast to fp32
-    Hd = cv.to_dev(H, torch.float32)
+    Wd = cv.to_dev_cached(W, torch.float32)   # obq.py:195-196: both cast to fp32
+    Hd = cv.to_dev_cached(H, torch.float32)
     Q = gptq_device(Wd, Hd, quantizer, act_order, damp, nb_ls_moves, min_block_size, num_blocks,
                     check=not cv.is_tensor(W))
     return cv.back(Q, W)
@@ -287,7 +291,7 @@ def quantize_opt(W, H, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, mi
 def compute_gain(W, Q, H, candidates):
     """Gain of moving each weight to its candidate (obq.py:220-231)."""
     dt = cv.torch_float(np.result_type(*(cv.float_dtype_of(a) for a in (W, Q, H, candidates))))
-    out = ops.gain(cv.to_dev(W, dt), cv.to_dev(Q, dt), cv.to_dev(H, dt), cv.to_dev(candidates, dt))
+    out = ops.gain(cv.to_dev_cached(W, dt), cv.to_dev_cached(Q, dt), cv.to_dev_cached(H, dt), cv.to_dev_cached(candidates, dt))
     return cv.back(out, W)
 
 
@@ -303,10 +307,11 @@ class LocalSearchQuantizer:
         assert H.shape[0] == W.shape[1]
         assert Q.shape == W.shape
         self._like = W
-        self._W = cv.to_dev(W, torch.float32)
-        self._Q = cv.to_dev(Q, torch.float32).clone()
-        self._H = cv.to_dev(H, torch.float32)
+        self._W = cv.to_dev_cached(W, torch.float32)
+        self._Q = cv.to_dev_cached(Q, torch.float32).clone()
+        self._H = cv.to_dev_cached(H, torch.float32)
         self.quantizer = quantizer
+        self._state = ops.LocalSearchState(self._W)      # keeps (Q - W) H across do_move calls
 
     @property
     def nchannels(self):
@@ -348,15 +353,15 @@ class LocalSearchQuantizer:
         return cv.back(ops.gain(self._W, self._Q, self._H, self._cand(ops.DOWN)), self._like)
 
     def do_move(self):
-        ops.local_search(self._W, self._Q, self._H, self.quantizer, 1)
+        ops.local_search_step(self._W, self._Q, self._H, self.quantizer, 1, self._state)
 
 
 def quantize_local_search(W, Q, H, quantizer, nb_moves):
     """nb_moves best-first flips per row (obq.py:349-358)."""
     if nb_moves == 0:
         return Q
-    Wd = cv.to_dev(W, torch.float32)
-    Qd = cv.to_dev(Q, torch.float32).clone()
-    Hd = cv.to_dev(H, torch.float32)
+    Wd = cv.to_dev_cached(W, torch.float32)
+    Qd = cv.to_dev_cached(Q, torch.float32).clone()
+    Hd = cv.to_dev_cached(H, torch.float32)
     ops.local_search(Wd, Qd, Hd, quantizer, nb_moves)
     return cv.back(Qd, W)

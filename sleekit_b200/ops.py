@@ -81,7 +81,23 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream(_Target.dev).cuda_stream)
 
 
+# development aid (tools/timeline.py --ops): {"buf": int64 CUDA tensor, "names": [], "tag": any}; every C call is then
+# followed by a stream-ordered %globaltimer stamp so that a replayed graph yields a per-call Gantt chart
+TRACE = None
+
+
 def _call(name, *args):
+    if TRACE is not None and name != "slk_debug_timestamp":
+        out = _call_inner(name, *args)
+        k = len(TRACE["names"])
+        if k < TRACE["buf"].numel():
+            TRACE["names"].append((name, TRACE.get("tag"), int(torch.cuda.current_stream(_Target.dev).cuda_stream)))
+            _lib.call("slk_debug_timestamp", C.c_void_p(TRACE["buf"].data_ptr() + 8 * k), _stream())
+        return out
+    return _call_inner(name, *args)
+
+
+def _call_inner(name, *args):
     dev = _Target.dev
     if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
         with torch.cuda.device(dev):
@@ -471,6 +487,29 @@ def chol_factor(h, order=None, dampval=None, want_rt=True):
     return r32, rt, ud32, info
 
 
+def create_streams(count, priority=0):
+    """`count` real CUDA streams of the given priority on the current device (slk_stream_create), as
+    torch ExternalStreams.  torch.cuda.Stream() draws from a pool of 32 streams per priority, which
+    would make 72 "independent" layers share 32 queues."""
+    require_cuda()
+    out = []
+    for _ in range(int(count)):
+        p = C.c_void_p()
+        _lib.call("slk_stream_create", int(priority), C.byref(p))
+        out.append(torch.cuda.ExternalStream(p.value))
+    return out
+
+
+def set_option(name, value):
+    _lib.call("slk_set_option", name.encode(), int(value))
+
+
+def timestamp(trace, row, col):
+    """Development aid: %globaltimer into trace[row, col] (int64 CUDA tensor) when the current stream gets there."""
+    _Target.dev = trace.device
+    _call("slk_debug_timestamp", C.c_void_p(trace.data_ptr() + 8 * (row * trace.shape[1] + col)), _stream())
+
+
 def _ptr_array(tensors):
     return (C.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
 
@@ -669,6 +708,46 @@ def gptq_sweep(q, u64, u32, cb, leaf=32, fanout=8, e=None, exact_leaf=False):
     _call("slk_gptq_sweep_f32", _ptr(q), _ptr(e), q.shape[0], q.shape[1], _ptr(u64) if exact_leaf else None,
               _ptr(u32), cb.ref, int(leaf), int(fanout), 1 if exact_leaf else 0, _stream())
     return q, e
+
+
+def row_wsq(e, h=None):
+    """sum_j h[j] e[row, j]^2 per row (h None: sum of squares): _compute_mse's None / 1-D branches."""
+    _chk(e)
+    assert e.dtype in (torch.float32, torch.float64) and e.ndim == 2
+    if h is not None:
+        _chk(h, e.dtype)
+        assert h.numel() == e.shape[1]
+    out = torch.empty(e.shape[0], dtype=e.dtype, device=e.device)
+    _call("slk_row_wsq_f32" if e.dtype == torch.float32 else "slk_row_wsq_f64", _ptr(e), _ptr(h), e.shape[0],
+          e.shape[1], _ptr(out), _stream())
+    return out
+
+
+class LocalSearchState:
+    """Workspace of an instalment-wise local search (slk_local_search_step_f32): keeps P = (Q - W) H
+    between calls so that LocalSearchQuantizer.do_move does not redo the 2 r n^2 product per move."""
+
+    def __init__(self, w):
+        r, n = w.shape
+        self.nbytes = int(_lib.load().slk_local_search_ws_bytes(r, n))
+        self.ws = _ws(self.nbytes, w.device)
+        self.valid = False
+
+
+@_timed("local_search")
+def local_search_step(w, q, h, cb, moves, state):
+    """In place on q; continues from the state a previous call left (same w, q, h)."""
+    cb = device_codebook(cb)
+    _chk(w, torch.float32)
+    _chk(q, torch.float32)
+    _chk(h, torch.float32)
+    if moves <= 0:
+        return q
+    r, n = w.shape
+    _call("slk_local_search_step_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(state.ws), state.nbytes,
+          1 if state.valid else 0, _stream())
+    state.valid = True
+    return q
 
 
 @_timed("local_search")

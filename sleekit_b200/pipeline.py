@@ -53,22 +53,42 @@ class LayerSetQuantizer:
     """Holds the side streams; call it with lists of device tensors."""
 
     def __init__(self, codebook, scaling_mode="diag", act_order="diag", damp=0.01, nb_ls_moves=0, grid_size=100,
-                 min_factor=0.05, max_factor=1.0, streams=8, big_first=True, batch_k2=None, k2_group=None):
+                 min_factor=0.05, max_factor=1.0, streams=8, big_first=True, batch_k2=None, k2_group=None,
+                 bias_correction=False):
         """batch_k2: factor the Hessians of equal-sized layers in batched launches whose tile tasks share
         one ticket queue (ops.chol_factor_batched) instead of one factorisation per layer; default on
         when there is more than one stream (SLK_BATCH_K2=0/1 overrides).  k2_group: at most this many
         layers per batched launch (SLK_K2_GROUP)."""
         ops.require_cuda()
+        self.bias_correction = bool(bias_correction)      # H - m m^T (obq.py:14-25) before everything else
         env = os.environ.get("SLK_BATCH_K2")
         self.batch_k2 = (int(streams) > 1 if batch_k2 is None else bool(batch_k2)) if env is None else env != "0"
         self.k2_group = int(os.environ.get("SLK_K2_GROUP") or k2_group or 64)
-        self.k2_streams = [torch.cuda.Stream() for _ in range(4)]
+        # the factor launches and the layers with the longest chains run on high-priority streams: their
+        # CTAs are scheduled ahead of the short layers' whenever both are ready (SLK_PRIORITY=0: off)
+        self.use_priority = os.environ.get("SLK_PRIORITY", "1") != "0"
+        hp = -1 if self.use_priority else 0
+        self.k2_streams = mk(4, hp)
+        self.hi_streams = mk(max(1, int(streams)), hp) if self.use_priority else None
+        # CTAs per macro-block sweep launch while a layer SET is in flight (fewer, taller CTAs: less SM-slot
+        # time per layer; measured on the sixty n = 768 layers: 6.2 ms with 24, 6.6 with 48, 7.1 with 96)
+        self.sweep_ctas = int(os.environ.get("SLK_SET_SWEEP_CTAS", "24")) if int(streams) > 1 else 0
+        self.trace = None      # development aid: int64 CUDA tensor [layers, 8] of phase time stamps (tools/timeline.py)
         self.cb = codebook
         self.scaling_mode, self.act_order = scaling_mode, act_order
         self.damp, self.nb_ls_moves = damp, nb_ls_moves
         self.grid_size, self.min_factor, self.max_factor = grid_size, min_factor, max_factor
-        self.streams = [torch.cuda.Stream() for _ in range(max(1, int(streams)))]
+        real = os.environ.get("SLK_REAL_STREAMS", "1") != "0"
+        mk = (lambda cnt, prio: ops.create_streams(cnt, prio)) if real else (
+            lambda cnt, prio: [torch.cuda.Stream(priority=prio) for _ in range(cnt)])
+        self.streams = mk(max(1, int(streams)), 0)
         self.big_first = bool(big_first)
+
+    def _hessian(self, H, mean):
+        if not self.bias_correction:
+            return H
+        assert mean is not None, "bias_correction needs the per-layer input means"
+        return ops.remove_input_bias(H, mean)
 
     def _one(self, W, H):
         sc = _device_scaling(W, self.cb, H, self.scaling_mode, self.grid_size, self.min_factor, self.max_factor)
@@ -80,7 +100,8 @@ class LayerSetQuantizer:
     def _issue_order(self, shapes, order=None):
         return issue_order(shapes, order or ("big" if self.big_first else "model"))
 
-    def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True, _in_capture=False, _pre=None, _post=None, _order=None):
+    def __call__(self, Ws, Hs, errs_out=None, keep_outputs=True, _in_capture=False, _pre=None, _post=None, _order=None,
+                 means=None):
         """Ws[i] [r_i, n_i] fp32, Hs[i] [n_i, n_i] fp32 on the device.  Returns (quantized
         weights, scales, errors) -- errors as one fp32 device vector.  Nothing synchronises.
         _pre(i) / _post(i, q) run on layer i's stream before / after its kernels (HostPlan uses
@@ -88,8 +109,16 @@ class LayerSetQuantizer:
         L = len(Ws)
         dev = Ws[0].device
         errs = errs_out if errs_out is not None else torch.empty(L, dtype=torch.float32, device=dev)
+        ops.set_option("sweep_ctas", self.sweep_ctas)
+        try:
+            return self._run(Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order, means)
+        finally:
+            ops.set_option("sweep_ctas", 0)
+
+    def _run(self, Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order, means):
+        L = len(Ws)
         if self.batch_k2 and L > 1 and obq.USE_CHOL_FORM:
-            return self._staged(Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order)
+            return self._staged(Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order, means)
         main = torch.cuda.current_stream()
         start = torch.cuda.Event()
         start.record(main)
@@ -105,10 +134,10 @@ class LayerSetQuantizer:
             with torch.cuda.stream(st):
                 if _pre is not None:
                     _pre(i)
-                q, sc, e = self._one(Ws[i], Hs[i])
+                q, sc, e = self._one(Ws[i], self._hessian(Hs[i], means[i] if means is not None else None))
                 errs[i:i + 1].copy_(e.reshape(1))
                 if _post is not None:
-                    _post(i, q)
+                    _post(i, q, sc)
                 if keep_outputs:
                     outs[i], scales[i] = q, sc
                     if not _in_capture:
@@ -120,7 +149,7 @@ class LayerSetQuantizer:
             main.wait_event(done)
         return outs, scales, errs
 
-    def _staged(self, Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order):
+    def _staged(self, Ws, Hs, errs, keep_outputs, _in_capture, _pre, _post, _order, means=None):
         """The same pass in three stages so that the fp64 factorisations can be batched:
         A (per layer, its stream): [copy in] -> scale search -> damp, ordering, scaled + permuted weights;
         B (per group of equal-sized layers, a factor stream): ONE batched tile-task Cholesky launch;
@@ -134,18 +163,34 @@ class LayerSetQuantizer:
         S = len(self.streams)
         issue = self._issue_order([tuple(w.shape) for w in Ws], _order)
         stream_of, stage, done_a = {}, {}, {}
+        Hs = list(Hs)
+        nmax = max(int(w.shape[1]) for w in Ws)
+        nmin = min(int(w.shape[1]) for w in Ws)
+        used = []
         for slot, i in enumerate(issue):
-            st = self.streams[slot % S]
+            long_chain = self.hi_streams is not None and nmax >= 2 * nmin and int(Ws[i].shape[1]) * 2 > nmax
+            st = (self.hi_streams if long_chain else self.streams)[slot % S]
             stream_of[i] = st
-            if slot < S:
+            if st not in used:
+                used.append(st)
                 st.wait_event(start)
             with torch.cuda.stream(st):
+                tr = self.trace
+                if tr is not None:
+                    ops.timestamp(tr, i, 0)
                 if _pre is not None:
                     _pre(i)
+                if tr is not None:
+                    ops.timestamp(tr, i, 1)
+                Hs[i] = self._hessian(Hs[i], means[i] if means is not None else None)
                 sc = _device_scaling(Ws[i], self.cb, Hs[i], self.scaling_mode, self.grid_size, self.min_factor,
                                      self.max_factor)
+                if tr is not None:
+                    ops.timestamp(tr, i, 2)
                 stage[i] = (sc, obq.gptq_prepare(Ws[i], Hs[i], self.cb, self.act_order, self.damp, self.nb_ls_moves,
                                                  row_scale=sc, want_err=True))
+                if tr is not None:
+                    ops.timestamp(tr, i, 3)
                 ev = torch.cuda.Event()
                 ev.record(st)
                 done_a[i] = ev
@@ -158,6 +203,7 @@ class LayerSetQuantizer:
             cur.append(i)
         if cur:
             groups.append(cur)
+        self.last_groups = [(int(Ws[m[0]].shape[1]), len(m)) for m in groups]   # (n, matrices) per factor launch
         keep = []                                        # factor tensors stay alive until the join below
         for g, members in enumerate(groups):
             ks = self.k2_streams[g % len(self.k2_streams)]
@@ -166,12 +212,16 @@ class LayerSetQuantizer:
             for i in members:
                 ks.wait_event(done_a[i])
             with torch.cuda.stream(ks):
+                if self.trace is not None:
+                    ops.timestamp(self.trace, members[0], 4)
                 if len(members) == 1:
                     i = members[0]
                     facs = [ops.chol_factor(Hs[i], stage[i][1].order, stage[i][1].dampval)]
                 else:
                     facs = ops.chol_factor_batched([Hs[i] for i in members], [stage[i][1].order for i in members],
                                                    [stage[i][1].dampval for i in members])
+                if self.trace is not None:
+                    ops.timestamp(self.trace, members[0], 5)
                 ev = torch.cuda.Event()
                 ev.record(ks)
             keep.append(facs)
@@ -180,16 +230,20 @@ class LayerSetQuantizer:
                 st.wait_event(ev)
                 with torch.cuda.stream(st):
                     sc, gs = stage[i]
+                    if self.trace is not None:
+                        ops.timestamp(self.trace, i, 6)
                     q, (e, _) = obq.gptq_finish(gs, fac)
                     errs[i:i + 1].copy_(e.reshape(1))
                     if _post is not None:
-                        _post(i, q)
+                        _post(i, q, sc)
+                    if self.trace is not None:
+                        ops.timestamp(self.trace, i, 7)
                     if keep_outputs:
                         outs[i], scales[i] = q, sc
                         if not _in_capture:
                             q.record_stream(main)
                             sc.record_stream(main)
-        for st in list(self.streams[: min(S, L)]) + list(self.k2_streams[: min(len(self.k2_streams), len(groups))]):
+        for st in used + list(self.k2_streams[: min(len(self.k2_streams), len(groups))]):
             done = torch.cuda.Event()
             done.record(st)
             main.wait_event(done)
@@ -197,7 +251,7 @@ class LayerSetQuantizer:
         del keep
         return outs, scales, errs
 
-    def capture(self, Ws, Hs):
+    def capture(self, Ws, Hs, means=None):
         """Record one pass over the layer set into a CUDA graph (the side streams become parallel
         branches) and return (graph, errors, quantized weights).  graph.replay() re-runs the whole
         pass on the current contents of Ws / Hs with no per-kernel CPU launch cost; outputs are
@@ -206,13 +260,13 @@ class LayerSetQuantizer:
         errs = torch.empty(L, dtype=torch.float32, device=Ws[0].device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            outs, _, _ = self(Ws, Hs, errs_out=errs, keep_outputs=True, _in_capture=True)
+            outs, _, _ = self(Ws, Hs, errs_out=errs, keep_outputs=True, _in_capture=True, means=means)
         return graph, errs, outs
 
-    def host_plan(self, shapes, symmetric_h=True):
+    def host_plan(self, shapes, symmetric_h=True, outputs="weights"):
         """Pinned host buffers + device buffers + one CUDA graph for a fixed list of layer shapes
         [(r, n), ...]; see HostPlan."""
-        return HostPlan(self, shapes, symmetric_h)
+        return HostPlan(self, shapes, symmetric_h, outputs)
 
 
 class HostPlan:
@@ -225,10 +279,17 @@ class HostPlan:
     the quantized weights; the copy engines therefore work under the kernels of the other
     layers.  Same kernels and results as the device-tensor path.  H is a Hessian, hence symmetric:
     by default only its block upper triangle is sent over PCIe and mirrored on the device
-    (slk_upload_symmetric_f32; 53-63 % of the bytes); symmetric_h=False sends the whole matrix."""
+    (slk_upload_symmetric_f32; 53-63 % of the bytes); symmetric_h=False sends the whole matrix.
+    outputs="weights": Q[i] are the de-scaled fp32 quantized weights, what the reference's
+    quantize_with_scaling returns (scaling.py:80-81).  outputs="codes": the plan returns instead the
+    codebook indices ``codes[i]`` (uint8 / uint16 [r, n], codebook.py:43-54 of Q / scale) and the row scales
+    ``scales[i]`` [r] -- the packed form a deployment stores; a quarter of the device->host bytes.
+    With the quantizer's bias_correction the plan also owns ``M[i]`` (input means, obq.py:14-25)."""
 
-    def __init__(self, lsq, shapes, symmetric_h=True):
+    def __init__(self, lsq, shapes, symmetric_h=True, outputs="weights"):
         ops.require_cuda()
+        assert outputs in ("weights", "codes")
+        self.outputs = outputs
         self.lsq = lsq
         # H is a Hessian X^T X / n: symmetric.  With symmetric_h only its block upper triangle crosses
         # PCIe (ops.upload_symmetric) and the device mirrors it; pass False for arbitrary matrices.
@@ -242,34 +303,85 @@ class HostPlan:
         f32 = torch.float32
         self._Wp = [torch.empty((r, n), dtype=f32).pin_memory() for r, n in self.shapes]
         self._Hp = [torch.empty((n, n), dtype=f32).pin_memory() for r, n in self.shapes]
-        self._Qp = [torch.empty((r, n), dtype=f32).pin_memory() for r, n in self.shapes]
+        cdt = ops.device_codebook(lsq.cb).index_dtype
+        if outputs == "weights":
+            self._Qp = [torch.empty((r, n), dtype=f32).pin_memory() for r, n in self.shapes]
+            self._Sp = []
+        else:
+            self._Qp = [torch.empty((r, n), dtype=cdt).pin_memory() for r, n in self.shapes]
+            self._Sp = [torch.empty(r, dtype=f32).pin_memory() for r, n in self.shapes]
+        self._Mp = [torch.empty(n, dtype=f32).pin_memory() for r, n in self.shapes] if lsq.bias_correction else []
+        self._Md = [torch.empty(n, dtype=f32, device=dev) for r, n in self.shapes] if lsq.bias_correction else None
+        self.M = [t.numpy() for t in self._Mp]
         self._errp = torch.empty(len(self.shapes), dtype=f32).pin_memory()
         self.W = [t.numpy() for t in self._Wp]
         self.H = [t.numpy() for t in self._Hp]
-        self.Q = [t.numpy() for t in self._Qp]
+        self.Q = [t.numpy() for t in self._Qp] if outputs == "weights" else None
+        self.codes = [t.numpy() for t in self._Qp] if outputs == "codes" else None
+        self.scales = [t.numpy() for t in self._Sp] if outputs == "codes" else None
         self.err = self._errp.numpy()
         self._Wd = [torch.empty((r, n), dtype=f32, device=dev) for r, n in self.shapes]
         self._Hd = [torch.empty((n, n), dtype=f32, device=dev) for r, n in self.shapes]
         self._errd = torch.empty(len(self.shapes), dtype=f32, device=dev)
         self._graph = None
+        # high priority: the mirror kernel of the symmetric upload must not queue behind the layers' kernels
+        self.copy_stream = ops.create_streams(1, -1)[0]
+        self._copy_joined = False
+        # the plan's layers arrive one after the other over PCIe: per-layer factorisations start as soon as
+        # a layer's Hessian has landed, a batched launch only after the last one of its group
+        # (measured: 19.7 ms per OPT-125M pass per layer, 27 ms batched); SLK_PLAN_BATCH_K2=1 batches anyway
+        self.batch_k2 = os.environ.get("SLK_PLAN_BATCH_K2", "0") != "0"
         lib = _lib.load()
         self.h2d_bytes = sum(4 * r * n + (int(lib.slk_upload_symmetric_bytes(n, ops.symmetric_block_rows(n)))
                                           if self.symmetric_h else 4 * n * n) for r, n in self.shapes)
-        self.d2h_bytes = sum(4 * r * n for r, n in self.shapes) + 4 * len(self.shapes)
+        self.h2d_bytes += sum(4 * n for r, n in self.shapes) if lsq.bias_correction else 0
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self._Qp + self._Sp) + 4 * len(self.shapes)
 
     def _pre(self, i):
-        self._Wd[i].copy_(self._Wp[i], non_blocking=True)
-        if self.symmetric_h:
-            ops.upload_symmetric(self._Hp[i], self._Hd[i])
-        else:
-            self._Hd[i].copy_(self._Hp[i], non_blocking=True)
+        # All host->device copies go through ONE copy stream in the issue order of the layers, so the
+        # inputs of the longest chains (issued first) really arrive first; a layer's stream waits for
+        # its own copies only.  (Left to 72 independent streams the DMA engine interleaves the copies
+        # and the big layers' Hessians land last.)
+        cur = torch.cuda.current_stream()
+        cs = self.copy_stream
+        if not self._copy_joined:
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            cs.wait_event(ev0)
+            self._copy_joined = True
+        with torch.cuda.stream(cs):
+            self._Wd[i].copy_(self._Wp[i], non_blocking=True)
+            if self.symmetric_h:
+                ops.upload_symmetric(self._Hp[i], self._Hd[i])
+            else:
+                self._Hd[i].copy_(self._Hp[i], non_blocking=True)
+            if self._Md is not None:
+                self._Md[i].copy_(self._Mp[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        cur.wait_event(ev)
 
-    def _post(self, i, q):
-        self._Qp[i].copy_(q, non_blocking=True)
+    def _post(self, i, q, sc):
+        if self.outputs == "weights":
+            self._Qp[i].copy_(q, non_blocking=True)
+        else:
+            # codebook.py:43-54 on Q / scale: two HBM passes, then a quarter of the bytes over PCIe
+            idx = ops.round_to_codebook(ops.scale_rows(q, sc, 0), self.lsq.cb, want_val=False, want_idx=True)[1]
+            self._Qp[i].copy_(idx, non_blocking=True)
+            self._Sp[i].copy_(sc, non_blocking=True)
 
     def _pass(self, in_capture):
+        self._copy_joined = False
+        saved = self.lsq.batch_k2
+        self.lsq.batch_k2 = self.batch_k2
+        try:
+            self._pass_inner(in_capture)
+        finally:
+            self.lsq.batch_k2 = saved
+
+    def _pass_inner(self, in_capture):
         self.lsq(self._Wd, self._Hd, errs_out=self._errd, keep_outputs=False, _in_capture=in_capture,
-                 _pre=self._pre, _post=self._post, _order=self.order)
+                 _pre=self._pre, _post=self._post, _order=self.order, means=self._Md)
         self._errp.copy_(self._errd, non_blocking=True)
 
     def run(self, sync=True):
@@ -286,7 +398,7 @@ class HostPlan:
         self._graph.replay()
         if sync:
             torch.cuda.current_stream().synchronize()
-        return self.Q, self.err
+        return (self.Q if self.outputs == "weights" else (self.codes, self.scales)), self.err
 
 
 class ShardedLayerQuantizer:

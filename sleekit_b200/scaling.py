@@ -48,7 +48,7 @@ def apply_scaling(data, scale, axis=0):
     """data / scale broadcast along ``axis`` (scaling.py:21-25)."""
     assert scale.ndim == 1
     dt = cv.torch_float(np.result_type(cv.float_dtype_of(data), cv.float_dtype_of(scale)))
-    out = _scale_dev(cv.to_dev(data, dt), cv.to_dev(scale, dt), axis, 0)
+    out = _scale_dev(cv.to_dev_cached(data, dt), cv.to_dev_cached(scale, dt), axis, 0)
     return cv.back(out, data)
 
 
@@ -59,6 +59,7 @@ def apply_scaling_in_place(data, scale, axis=0):
         data.copy_(res)
     else:
         data[...] = res
+        cv.invalidate(data)
 
 
 def _rows_first(x, axis):
@@ -71,7 +72,7 @@ def _rows_first(x, axis):
 
 def compute_norm_scaling(data, axis=0):
     """sqrt(max(mean(x^2) over the other axes, 1e-16)) (scaling.py:35-41)."""
-    x = cv.to_dev(data)
+    x = cv.to_dev_cached(data)
     return cv.back(ops.row_rms_scale(_rows_first(x, axis)), data)
 
 
@@ -79,7 +80,7 @@ def compute_non_saturating_scaling(data, codebook, axis=0):
     """Smallest scale with no clipping (scaling.py:44-55)."""
     if codebook.min() >= 0 or codebook.max() <= 0:
         raise RuntimeError("Codebook should have both negative and positive values.")
-    x = cv.to_dev(data)
+    x = cv.to_dev_cached(data)
     out = ops.row_noclip_scale(_rows_first(x, axis), float(codebook.min()), float(codebook.max()))
     return cv.back(out, data)
 
@@ -104,26 +105,27 @@ def quantize_with_scaling(data, scale, quantizer, H=None, act_order="diag", damp
     assert data.ndim == 2
     assert scale.ndim == 1
     assert data.shape[0] == (scale.numel() if cv.is_tensor(scale) else scale.size)
-    Wd = cv.to_dev(data, torch.float32)
-    sd = cv.to_dev(scale, torch.float32)
-    Hd = cv.to_dev(H, torch.float32) if H is not None else None
+    Wd = cv.to_dev_cached(data, torch.float32)
+    sd = cv.to_dev_cached(scale, torch.float32)
+    Hd = cv.to_dev_cached(H, torch.float32) if H is not None else None
     out = quantize_scaled_device(Wd, sd, quantizer, Hd, act_order, damp, nb_ls_moves, check=not cv.is_tensor(data))
     return cv.back(out, data)
 
 
 def _compute_mse(H, E):
-    """Row errors for no / diagonal / full Hessian (scaling.py:84-95)."""
-    Ed = cv.to_dev(E)
+    """Row errors for no / diagonal / full Hessian (scaling.py:84-95): sum E^2, sum h_j E_j^2 or
+    ((E @ H) * E).sum(-1), in the promoted dtype of E and H."""
     if H is None:
-        out = (Ed * Ed).sum(dim=1)
+        Ed = cv.to_dev_cached(E)
+        out = ops.row_wsq(Ed.reshape(-1, Ed.shape[-1]).contiguous()).reshape(Ed.shape[:-1])
     elif H.ndim == 1:
         assert E.shape[1] == H.shape[0]
-        Hd = cv.to_dev(H)
-        out = (Hd.unsqueeze(0) * (Ed * Ed)).sum(dim=1)
+        dt = cv.torch_float(np.result_type(cv.float_dtype_of(E), cv.float_dtype_of(H)))
+        out = ops.row_wsq(cv.to_dev_cached(E, dt), cv.to_dev_cached(H, dt))
     else:
         assert H.ndim == 2 and E.shape[1] == H.shape[0] and H.shape[1] == H.shape[0]
         dt = cv.torch_float(np.result_type(cv.float_dtype_of(E), cv.float_dtype_of(H)))
-        out = ops.hweighted_error(Ed.to(dt), None, cv.to_dev(H, dt))
+        out = ops.hweighted_error(cv.to_dev_cached(E, dt), None, cv.to_dev_cached(H, dt))
     return cv.back(out, E)
 
 
@@ -153,10 +155,10 @@ def compute_min_mse_scaling(data, codebook, axis=0, H=None, min_factor=0.05, max
     """Grid search of the per-row scale minimising the (H-weighted) squared error (scaling.py:98-134)."""
     if codebook.min() >= 0 or codebook.max() <= 0:
         raise RuntimeError("Codebook should have both negative and positive values.")
-    flat = _rows_first(cv.to_dev(data, torch.float32), axis)
+    flat = _rows_first(cv.to_dev_cached(data, torch.float32), axis)
     Hd = None
     if H is not None:
-        Hd = cv.to_dev(H)
+        Hd = cv.to_dev_cached(H)
         if Hd.dtype not in (torch.float32, torch.float64):
             Hd = Hd.float()
         assert Hd.shape[-1] == flat.shape[1]
@@ -218,8 +220,8 @@ def compute_obq_scaling(data, codebook, axis, H, damp=0.01, act_order="diag", mi
     """Scale search where every grid point is evaluated after a full GPTQ sweep (scaling.py:137-190)."""
     if codebook.min() >= 0 or codebook.max() <= 0:
         raise RuntimeError("Codebook should have both negative and positive values.")
-    Wd = _rows_first(cv.to_dev(data, torch.float32), axis)
-    Hd = cv.to_dev(H, torch.float32)
+    Wd = _rows_first(cv.to_dev_cached(data, torch.float32), axis)
+    Hd = cv.to_dev_cached(H, torch.float32)
     out, info = obq_scale_device(Wd, codebook, Hd, damp, act_order, min_factor, max_factor, grid_size)
     if not cv.is_tensor(data):
         from .obq import _raise_if_not_pd
@@ -254,7 +256,7 @@ def compute_scaling(data, codebook, H, mode="mse", axis=0, min_factor=0.05, max_
 
 def _add_to_diagonal(H, penalty):
     """H + penalty * mean(diag H) * eye, promoted to fp64 as np.eye does (scaling.py:222)."""
-    Hd = cv.to_dev(H)
+    Hd = cv.to_dev_cached(H)
     mean_diag = Hd.diagonal().mean()          # stays in H's dtype
     out = Hd.to(torch.float64).clone()
     out.diagonal().add_((penalty * mean_diag).to(Hd.dtype).to(torch.float64))
@@ -263,7 +265,7 @@ def _add_to_diagonal(H, penalty):
 
 def _diag_with_penalty(H, penalty):
     """H.diagonal() [+ penalty * its mean], in H's dtype (scaling.py:224-227)."""
-    d = cv.to_dev(H).diagonal().contiguous()
+    d = cv.to_dev_cached(H).diagonal().contiguous()
     if penalty is not None:
         d = d + (penalty * d.mean()).to(d.dtype)
     return d

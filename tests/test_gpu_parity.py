@@ -385,6 +385,30 @@ def test_symmetric_pack_roundtrip(slk):
         assert torch.equal(back, Hd)
 
 
+def test_sweep_rows_do_not_depend_on_cta_tiling(slk):
+    """The macro-block sweep sums a row's products in an order that does not depend on how many rows a
+    CTA takes (8 / 16 / 32): the same layer quantized with different tile heights -- what the layer-set
+    driver, a row slice or a row-sharded run use -- gives the same bits."""
+    from sleekit_b200 import ops
+
+    r, n = 768, 1024
+    W, H, _ = wl.synthetic_layer(r, n, 29, samples=1024)
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    Wd, Hd = torch.from_numpy(W).cuda(), torch.from_numpy(H).cuda()
+    sc = slk.scaling.compute_min_mse_scaling(Wd, cb, 0, H=Hd.diagonal().contiguous())
+    outs = []
+    try:
+        for want in (0, 24, 96, 100000):
+            ops.set_option("sweep_ctas", want)
+            outs.append(slk.scaling.quantize_with_scaling(Wd, sc, cb, H=Hd))
+    finally:
+        ops.set_option("sweep_ctas", 0)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    part = slk.scaling.quantize_with_scaling(Wd[:40].contiguous(), sc[:40].contiguous(), cb, H=Hd)
+    assert torch.equal(part, outs[0][:40])
+
+
 def test_cholesky_form_sweep_equals_inverse_form(slk):
     """quantize_opt through (Cholesky factor, R-form sweep) and through (inverse factor, U-form
     sweep): the same algebra in different fp32 rounding -- codes agree to the GPTQ noise floor."""
@@ -853,3 +877,148 @@ def test_fast_exact_division_matches_ieee_exhaustively(slk):
               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert int(bad.sum().item()) == 0, [(divs[i], int(b)) for i, b in enumerate(bad.tolist()) if b]
+
+
+# ---------------------------------------------------------------------------
+# the small public functions (a7, a11, a18, a22, a2/a3 for conv layers) and the upload cache
+# ---------------------------------------------------------------------------
+
+
+def test_compute_mse_all_branches_vs_oracle(slk):
+    """_compute_mse (scaling.py:84-95): H None, 1-D (fp32 and fp64) and 2-D, against the oracle."""
+    rng = np.random.default_rng(12)
+    E = (rng.standard_normal((37, 515)) * 0.1).astype(np.float32)
+    _, H, _ = wl.synthetic_layer(4, 515, 2, samples=256)
+    f = slk.scaling._compute_mse
+    got = f(None, E)
+    assert got.dtype == np.float32 and got.shape == (37,)
+    np.testing.assert_allclose(got, orc.weighted_sq_error(None, E), rtol=2e-6)
+    hd = H.diagonal().copy()
+    got = f(hd, E)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, orc.weighted_sq_error(hd, E), rtol=2e-6)
+    h64 = rng.random(515)
+    got = f(h64, E)
+    assert got.dtype == np.float64
+    np.testing.assert_allclose(got, orc.weighted_sq_error(h64, E), rtol=1e-12)
+    got = f(H, E)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, orc.weighted_sq_error(H, E), rtol=2e-5)
+    # device tensors pass through
+    gd = f(torch.from_numpy(hd).cuda(), torch.from_numpy(E).cuda())
+    assert gd.is_cuda
+    np.testing.assert_allclose(gd.cpu().numpy(), orc.weighted_sq_error(hd, E), rtol=2e-6)
+
+
+def test_apply_scaling_in_place(slk):
+    """apply_scaling_in_place (scaling.py:28-32) writes data / scale into the caller's array."""
+    rng = np.random.default_rng(4)
+    for axis, shape in ((0, (13, 70)), (1, (13, 70)), (1, (5, 6, 7))):
+        data = rng.standard_normal(shape).astype(np.float32)
+        scale = (rng.random(shape[axis]) + 0.5).astype(np.float32)
+        want = orc.divide_rows(data, scale, axis)
+        keep = data
+        slk.scaling.apply_scaling_in_place(data, scale, axis)
+        assert data is keep
+        np.testing.assert_array_equal(data, want)
+
+
+def test_conv_layer_hessian_values(slk):
+    """Sleekit.add_batch on Conv2d / Conv1d layers (statistics.py:44-87): the Hessian and the mean equal
+    numpy's on the unfolded input (the unfold itself stays torch's, as in the reference)."""
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 4, 3, padding=1, stride=2)
+    st = slk.Sleekit(conv)
+    x1, x2 = torch.randn(2, 3, 9, 8), torch.randn(3, 3, 9, 8)
+    st.add_batch(x1)
+    st.add_batch(x2)
+    cols = [F.unfold(x, conv.kernel_size, conv.dilation, conv.padding, conv.stride).permute(1, 0, 2).flatten(1)
+            for x in (x1, x2)]
+    X = torch.cat(cols, dim=1).numpy().astype(np.float64)          # [features, samples]
+    assert st.count == X.shape[1]
+    np.testing.assert_allclose(st.hessian.cpu().numpy(), X @ X.T / X.shape[1], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(st.mean.cpu().numpy(), X.mean(axis=1), rtol=1e-5, atol=1e-6)
+    c1 = torch.nn.Conv1d(3, 4, 3, dilation=2)
+    s1 = slk.Sleekit(c1)
+    y = torch.randn(4, 3, 20)
+    s1.add_batch(y)
+    u = F.unfold(y.unsqueeze(-1), (3, 1), (2, 1), (0, 0), (1, 1)).permute(1, 0, 2).flatten(1).numpy().astype(np.float64)
+    assert s1.count == u.shape[1]
+    np.testing.assert_allclose(s1.hessian.cpu().numpy(), u @ u.T / u.shape[1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("block_size", [3, 4, 7, 8, 63, 64])
+@pytest.mark.parametrize("nb_blocks", [2, 8])
+def test_blocked_sweep_equals_unblocked_for_reference_leaf_widths(slk, block_size, nb_blocks):
+    """The reference's tests/test_obq.py:57-70 (test_blockobq) on the device: _quantize_opt_block with
+    min_block_size in {3,4,7,8,63,64} equals _quantize_opt_core."""
+    rng = np.random.default_rng(7)
+    size = 65
+    A = rng.standard_normal((size, 2 * size)).astype(np.float32)
+    H = (A @ A.T).astype(np.float64) + 0.5 * np.eye(size)
+    W = rng.standard_normal((10, size)).astype(np.float32)
+    cb = slk.codebook.UniformCodebook(9, -4, 4)       # step 1: rounds like the reference test's np.round
+    Hinv = slk.obq.compute_hessian_chol(H)
+    Q1, E1 = W.copy(), np.zeros_like(W)
+    Q2, E2 = W.copy(), np.zeros_like(W)
+    slk.obq._quantize_opt_core(Q1, E1, Hinv, cb)
+    slk.obq._quantize_opt_block(Q2, E2, Hinv, cb, block_size, nb_blocks)
+    np.testing.assert_allclose(Q1, Q2, atol=1e-5)
+    np.testing.assert_allclose(E1, E2, rtol=1e-4, atol=1e-5)
+    Qo, Eo = W.copy(), np.zeros_like(W)
+    orc.sweep_in_place(Qo, Eo, orc.inverse_upper_factor(H), orc.UniformGrid(9, -4, 4), min(block_size, 32), nb_blocks)
+    np.testing.assert_allclose(Q2, Qo, atol=1e-5)
+
+
+def test_local_search_quantizer_moves_one_by_one(slk):
+    """LocalSearchQuantizer.do_move (obq.py:338-346) keeps (Q - W) H between calls
+    (slk_local_search_step_f32): k single moves equal quantize_local_search(k), and the attributes the
+    reference exposes follow the current Q."""
+    g = load_golden("local_search")
+    cb = slk.codebook.UniformCodebook(4, -1, 1)
+    Ws, H, Q0 = g["Ws"], g["H"], g["Q0"]
+    ls = slk.obq.LocalSearchQuantizer(Ws, Q0, H, cb)
+    for k in range(1, 31):
+        ls.do_move()
+        if k in (1, 5, 30):
+            np.testing.assert_array_equal(ls.Q, g[f"ls_{k}"], err_msg=f"{k} single moves")
+    grid = orc.UniformGrid(4, -1, 1)
+    np.testing.assert_array_equal(ls.Q_up, grid.up(g["ls_30"]))
+    np.testing.assert_array_equal(ls.Q_down, grid.down(g["ls_30"]))
+    np.testing.assert_allclose(ls.gain_up, orc.flip_gain(Ws, g["ls_30"], H, grid.up(g["ls_30"])), rtol=1e-4, atol=1e-6)
+    assert ls.nchannels == Ws.shape[0]
+
+
+def test_upload_cache_reuses_and_invalidates(slk):
+    """_convert: a large read-only host operand is uploaded once and found again by identity; sleekit's own
+    in-place functions and invalidate() drop the stale copy; a changed array is detected by its fingerprint."""
+    from sleekit_b200 import _convert as cv
+
+    cv.cache_clear()
+    W, H, m = wl.synthetic_layer(96, 768, 8, samples=512)
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    h0, miss0 = cv.CACHE_HITS, cv.CACHE_MISSES
+    sc = slk.scaling.compute_min_mse_scaling(W, cb, 0, H=H.diagonal().copy())
+    q = slk.scaling.quantize_with_scaling(W, sc, cb, H=H)
+    e1 = slk.obq.quantization_error(W, q, H)
+    assert cv.CACHE_MISSES - miss0 == 2                      # W and H, once each
+    assert cv.CACHE_HITS - h0 >= 3                           # W twice more, H once more, q from its own download
+    before = cv.H2D_BYTES
+    e2 = slk.obq.quantization_error(W, q, H)
+    assert cv.H2D_BYTES == before and e1 == e2               # nothing crosses PCIe the second time
+    # in-place mutation through sleekit's own function: the copy is dropped and the new content is used
+    H2, W2 = H.copy(), W.copy()
+    H2[5, :] = 0
+    H2[:, 5] = 0
+    slk.obq.quantization_error(W2, q, H2)                    # caches H2 (with its dead column)
+    slk.obq.remove_dead_values(H2, W2)
+    assert H2[5, 5] != 0 and np.all(W2[:, 5] == 0)
+    e3 = slk.obq.quantization_error(W2, q, H2)
+    np.testing.assert_allclose(e3, orc.mean_error(W2, q, H2), rtol=1e-4)
+    # a diagonal overwrite (dampening in place) changes the fingerprint
+    H2[np.arange(768), np.arange(768)] += np.float32(1.0)
+    e4 = slk.obq.quantization_error(W2, q, H2)
+    np.testing.assert_allclose(e4, orc.mean_error(W2, q, H2), rtol=1e-4)
+    cv.cache_clear()
