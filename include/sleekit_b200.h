@@ -321,6 +321,7 @@ int slk_local_search_step_f32(const float* w, float* q, const float* h, int64_t 
  * out[row] = sum_j h[j] * e[row, j]^2 (h NULL: sum of squares); the 2-D case is slk_hweighted_error_*. */
 int slk_row_wsq_f32(const float* e, const float* h, int64_t r, int64_t n, float* out, void* stream);
 int slk_row_wsq_f64(const double* e, const double* h, int64_t r, int64_t n, double* out, void* stream);
+int slk_row_wsq_f32_h64(const float* e, const double* h, int64_t r, int64_t n, double* out, void* stream);
 
 int slk_bias_delta_f32(const float* w, const float* wq, const float* mean, int64_t r, int64_t n,
                        float* delta, void* stream);

@@ -107,6 +107,7 @@ SIGNATURES = {
     "slk_local_search_step_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _I32, _P]),
     "slk_row_wsq_f32": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "slk_row_wsq_f64": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "slk_row_wsq_f32_h64": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "slk_bias_delta_f32": (_INT, [_P, _P, _P, _I64, _I64, _P, _P]),
     "slk_selftest_fastdiv_f32": (_INT, [_P, _I32, _P, _P]),
     "slk_tc_gemm_ws_bytes": (_SZ, [_I64, _I64, _I64]),

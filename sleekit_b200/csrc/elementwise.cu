@@ -562,20 +562,20 @@ __global__ void __launch_bounds__(256) bias_delta_kernel(const float* __restrict
 
 // out[row] = sum_j h[j] * e[row, j]^2  (h NULL: plain sum of squares) -- the None / 1-D branches of
 // _compute_mse (scaling.py:84-95); products and squares rounded as numpy rounds them, sums in fp64.
-template <typename T>
-__global__ void __launch_bounds__(256) row_wsq_kernel(const T* __restrict__ e, const T* __restrict__ h, int64_t r, int64_t n,
-                                                      T* __restrict__ out) {
+// TE: dtype of e (the square is rounded in it, as np.square(E) is); TH: promoted dtype of h and of the result.
+template <typename TE, typename TH>
+__global__ void __launch_bounds__(256) row_wsq_kernel(const TE* __restrict__ e, const TH* __restrict__ h, int64_t r, int64_t n,
+                                                      TH* __restrict__ out) {
   __shared__ double scratch[32];
-  typedef Ieee<T> F;
   for (int64_t row = blockIdx.x; row < r; row += gridDim.x) {
     double acc = 0.0;
     for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-      const T v = e[row * n + j];
-      const T sq = F::mul(v, v);
-      acc += (double)(h ? F::mul(h[j], sq) : sq);
+      const TE v = e[row * n + j];
+      const TE sq = Ieee<TE>::mul(v, v);
+      acc += (double)(h ? Ieee<TH>::mul(h[j], (TH)sq) : (TH)sq);
     }
     acc = block_sum<double>(acc, scratch);
-    if (threadIdx.x == 0) out[row] = (T)acc;
+    if (threadIdx.x == 0) out[row] = (TH)acc;
   }
 }
 
@@ -887,14 +887,23 @@ int slk_selftest_fastdiv_f32(const float* divisors, int32_t count, uint64_t* mis
 int slk_row_wsq_f32(const float* e, const float* h, int64_t r, int64_t n, float* out, void* stream) {
   SLK_REQUIRE(e && out && r >= 1 && n >= 1, "bad arguments");
   int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
-  row_wsq_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
+  row_wsq_kernel<float, float><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
 int slk_row_wsq_f64(const double* e, const double* h, int64_t r, int64_t n, double* out, void* stream) {
   SLK_REQUIRE(e && out && r >= 1 && n >= 1, "bad arguments");
   int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
-  row_wsq_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
+  row_wsq_kernel<double, double><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+/* fp32 residuals under an fp64 diagonal (the "diagN" / hessianN penalties promote H, scaling.py:222): the square
+   is rounded in fp32 as np.square(E) is, the product and the sum are fp64 */
+int slk_row_wsq_f32_h64(const float* e, const double* h, int64_t r, int64_t n, double* out, void* stream) {
+  SLK_REQUIRE(e && h && out && r >= 1 && n >= 1, "bad arguments");
+  int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
+  row_wsq_kernel<float, double><<<grid, 256, 0, (cudaStream_t)stream>>>(e, h, r, n, out);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

@@ -411,10 +411,9 @@ bool tc_gemm_usable(const void* a, int64_t lda, const void* b, int64_t ldb) {
   return ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && encode_fn() != nullptr;
 }
 
-template <int BN, int EPI>
-static int tc_launch(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
-                     int64_t ldb, const TcParams& p, cudaStream_t st, int splits = 1) {
-  constexpr int STAGES = BN == 128 ? 3 : 4;
+template <int BN, int STAGES, int EPI>
+static int tc_launch_s(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
+                       int64_t ldb, const TcParams& p, cudaStream_t st, int splits = 1) {
   typedef TcSmem<BN, STAGES> SM;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
@@ -428,6 +427,12 @@ static int tc_launch(const float* a_hi, const float* a_lo, int64_t lda, const fl
   kern<<<grid, TC_THREADS, SM::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
+}
+
+template <int BN, int EPI>
+static int tc_launch(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
+                     int64_t ldb, const TcParams& p, cudaStream_t st, int splits = 1) {
+  return tc_launch_s<BN, (BN == 128 ? 3 : 4), EPI>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st, splits);
 }
 
 static inline int split_grid(int64_t total) {
@@ -465,7 +470,18 @@ int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t 
                          const float* b_lo, int64_t ldb, TcParams p, cudaStream_t st) {
   switch (epi) {
     case TC_STORE: return tc_launch<128, TC_STORE>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
-    case TC_ACCUM: return tc_launch<128, TC_ACCUM>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case TC_ACCUM: {
+      // The sweep's macro-block pushes have K = 256: eight k-blocks.  Two pipeline stages (129 KB of shared
+      // memory instead of 193 KB) then cost nothing and let the tile share an SM with one sweep CTA of
+      // another layer instead of waiting for an empty SM (SLK_TC_STAGES2=0: always three stages).
+      static int two = -1;
+      if (two < 0) {
+        const char* e = getenv("SLK_TC_STAGES2");
+        two = (e && e[0] == '0') ? 0 : 1;
+      }
+      if (two && p.K <= 512) return tc_launch_s<128, 2, TC_ACCUM>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+      return tc_launch<128, TC_ACCUM>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    }
     case TC_ROWDOT: return tc_launch<128, TC_ROWDOT>(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
   }
   SLK_REQUIRE(false, "tc_gemm_presplit: unsupported epilogue %d", epi);

@@ -173,7 +173,7 @@ class GptqStage:
     their Hessians in batched launches (ops.chol_factor_batched) and then finishes each layer."""
 
     __slots__ = ("W_in", "Wd", "Hd", "quantizer", "act_order", "dampval", "order", "Q", "fuse", "row_scale",
-                 "nb_ls_moves", "leaf", "num_blocks", "want_err", "chol_form")
+                 "nb_ls_moves", "leaf", "num_blocks", "want_err", "chol_form", "info")
 
 
 def gptq_prepare(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, min_block_size=32, num_blocks=8,
@@ -220,6 +220,7 @@ def gptq_finish(st, factor=None, check=False):
     if st.chol_form:
         # factor only (no triangular inverse): H_opt = R R^T, sweep from R
         r32, rt32, ud32, info = factor if factor is not None else ops.chol_factor(Hd, order, st.dampval)  # obq.py:204
+        st.info = info                                   # first non-PD pivot (0 = fine): obq.py:49-50 raises there
         if want_err and not nb_ls_moves and USE_SWEEP_ERROR:
             sums = torch.empty((Q.shape[0], 2), dtype=torch.float32, device=Q.device)
         ops.gptq_sweep_r(Q, r32, rt32, ud32, quantizer, err_sums=sums)    # obq.py:208-209
@@ -228,6 +229,7 @@ def gptq_finish(st, factor=None, check=False):
     else:
         assert factor is None
         u64, u32, info = ops.hinv(Hd, order, st.dampval)                  # obq.py:204-205
+        st.info = info
         ops.gptq_sweep(Q, u64, u32, quantizer, st.leaf, st.num_blocks)    # obq.py:208-209
     if st.fuse:
         Q = ops.scale_permute_cols(Q, order, row_scale, scatter=True)     # obq.py:212-213 + scaling.py:80

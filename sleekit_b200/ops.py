@@ -714,12 +714,18 @@ def row_wsq(e, h=None):
     """sum_j h[j] e[row, j]^2 per row (h None: sum of squares): _compute_mse's None / 1-D branches."""
     _chk(e)
     assert e.dtype in (torch.float32, torch.float64) and e.ndim == 2
+    odt = e.dtype
+    fn = "slk_row_wsq_f32" if e.dtype == torch.float32 else "slk_row_wsq_f64"
     if h is not None:
-        _chk(h, e.dtype)
-        assert h.numel() == e.shape[1]
-    out = torch.empty(e.shape[0], dtype=e.dtype, device=e.device)
-    _call("slk_row_wsq_f32" if e.dtype == torch.float32 else "slk_row_wsq_f64", _ptr(e), _ptr(h), e.shape[0],
-          e.shape[1], _ptr(out), _stream())
+        _chk(h)
+        assert h.numel() == e.shape[1] and h.dtype in (torch.float32, torch.float64)
+        if h.dtype != e.dtype:
+            if e.dtype == torch.float64:
+                h = h.to(torch.float64)
+            else:                                    # fp32 residuals, fp64 diagonal: result fp64
+                fn, odt = "slk_row_wsq_f32_h64", torch.float64
+    out = torch.empty(e.shape[0], dtype=odt, device=e.device)
+    _call(fn, _ptr(e), _ptr(h), e.shape[0], e.shape[1], _ptr(out), _stream())
     return out
 
 

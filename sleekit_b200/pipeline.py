@@ -66,6 +66,10 @@ class LayerSetQuantizer:
         self.k2_group = int(os.environ.get("SLK_K2_GROUP") or k2_group or 64)
         # the factor launches and the layers with the longest chains run on high-priority streams: their
         # CTAs are scheduled ahead of the short layers' whenever both are ready (SLK_PRIORITY=0: off)
+        real = os.environ.get("SLK_REAL_STREAMS", "1") != "0"
+        mk = (lambda cnt, prio: ops.create_streams(cnt, prio)) if real else (
+            lambda cnt, prio: [torch.cuda.Stream(priority=prio) for _ in range(cnt)])
+        self.streams = mk(max(1, int(streams)), 0)
         self.use_priority = os.environ.get("SLK_PRIORITY", "1") != "0"
         hp = -1 if self.use_priority else 0
         self.k2_streams = mk(4, hp)
@@ -73,15 +77,12 @@ class LayerSetQuantizer:
         # CTAs per macro-block sweep launch while a layer SET is in flight (fewer, taller CTAs: less SM-slot
         # time per layer; measured on the sixty n = 768 layers: 6.2 ms with 24, 6.6 with 48, 7.1 with 96)
         self.sweep_ctas = int(os.environ.get("SLK_SET_SWEEP_CTAS", "24")) if int(streams) > 1 else 0
+        self.infos = None      # optional int32 CUDA tensor [layers]: receives every layer's factorisation status
         self.trace = None      # development aid: int64 CUDA tensor [layers, 8] of phase time stamps (tools/timeline.py)
         self.cb = codebook
         self.scaling_mode, self.act_order = scaling_mode, act_order
         self.damp, self.nb_ls_moves = damp, nb_ls_moves
         self.grid_size, self.min_factor, self.max_factor = grid_size, min_factor, max_factor
-        real = os.environ.get("SLK_REAL_STREAMS", "1") != "0"
-        mk = (lambda cnt, prio: ops.create_streams(cnt, prio)) if real else (
-            lambda cnt, prio: [torch.cuda.Stream(priority=prio) for _ in range(cnt)])
-        self.streams = mk(max(1, int(streams)), 0)
         self.big_first = bool(big_first)
 
     def _hessian(self, H, mean):
@@ -93,9 +94,9 @@ class LayerSetQuantizer:
     def _one(self, W, H):
         sc = _device_scaling(W, self.cb, H, self.scaling_mode, self.grid_size, self.min_factor, self.max_factor)
         # layer error (obq.py:89-103): from the sweep's own residuals when possible (gptq_device)
-        q, (err, _) = quantize_scaled_device(W, sc, self.cb, H, self.act_order, self.damp, self.nb_ls_moves,
-                                             want_err=True)
-        return q, sc, err
+        gs = obq.gptq_prepare(W, H, self.cb, self.act_order, self.damp, self.nb_ls_moves, row_scale=sc, want_err=True)
+        q, (err, _) = obq.gptq_finish(gs)
+        return q, sc, err, gs.info
 
     def _issue_order(self, shapes, order=None):
         return issue_order(shapes, order or ("big" if self.big_first else "model"))
@@ -134,8 +135,10 @@ class LayerSetQuantizer:
             with torch.cuda.stream(st):
                 if _pre is not None:
                     _pre(i)
-                q, sc, e = self._one(Ws[i], self._hessian(Hs[i], means[i] if means is not None else None))
+                q, sc, e, info = self._one(Ws[i], self._hessian(Hs[i], means[i] if means is not None else None))
                 errs[i:i + 1].copy_(e.reshape(1))
+                if self.infos is not None:
+                    self.infos[i:i + 1].copy_(info.reshape(1))
                 if _post is not None:
                     _post(i, q, sc)
                 if keep_outputs:
@@ -168,7 +171,8 @@ class LayerSetQuantizer:
         nmin = min(int(w.shape[1]) for w in Ws)
         used = []
         for slot, i in enumerate(issue):
-            long_chain = self.hi_streams is not None and nmax >= 2 * nmin and int(Ws[i].shape[1]) * 2 > nmax
+            long_chain = (self.hi_streams is not None and S > 1 and nmax >= 2 * nmin
+                          and int(Ws[i].shape[1]) * 2 > nmax)
             st = (self.hi_streams if long_chain else self.streams)[slot % S]
             stream_of[i] = st
             if st not in used:
@@ -234,6 +238,8 @@ class LayerSetQuantizer:
                         ops.timestamp(self.trace, i, 6)
                     q, (e, _) = obq.gptq_finish(gs, fac)
                     errs[i:i + 1].copy_(e.reshape(1))
+                    if self.infos is not None:
+                        self.infos[i:i + 1].copy_(gs.info.reshape(1))
                     if _post is not None:
                         _post(i, q, sc)
                     if self.trace is not None:
@@ -323,6 +329,9 @@ class HostPlan:
         self._Wd = [torch.empty((r, n), dtype=f32, device=dev) for r, n in self.shapes]
         self._Hd = [torch.empty((n, n), dtype=f32, device=dev) for r, n in self.shapes]
         self._errd = torch.empty(len(self.shapes), dtype=f32, device=dev)
+        self._infod = torch.zeros(len(self.shapes), dtype=torch.int32, device=dev)
+        self._infop = torch.zeros(len(self.shapes), dtype=torch.int32).pin_memory()
+        self.info = self._infop.numpy()       # per layer: 0, or the first non-positive pivot of its factorisation
         self._graph = None
         # high priority: the mirror kernel of the symmetric upload must not queue behind the layers' kernels
         self.copy_stream = ops.create_streams(1, -1)[0]
@@ -380,9 +389,14 @@ class HostPlan:
             self.lsq.batch_k2 = saved
 
     def _pass_inner(self, in_capture):
-        self.lsq(self._Wd, self._Hd, errs_out=self._errd, keep_outputs=False, _in_capture=in_capture,
-                 _pre=self._pre, _post=self._post, _order=self.order, means=self._Md)
+        self.lsq.infos = self._infod
+        try:
+            self.lsq(self._Wd, self._Hd, errs_out=self._errd, keep_outputs=False, _in_capture=in_capture,
+                     _pre=self._pre, _post=self._post, _order=self.order, means=self._Md)
+        finally:
+            self.lsq.infos = None
         self._errp.copy_(self._errd, non_blocking=True)
+        self._infop.copy_(self._infod, non_blocking=True)
 
     def run(self, sync=True):
         """One pass over the layer set from the current contents of W / H; fills Q and err."""
@@ -398,6 +412,12 @@ class HostPlan:
         self._graph.replay()
         if sync:
             torch.cuda.current_stream().synchronize()
+            bad = [i for i, v in enumerate(self.info) if v != 0]
+            if bad:
+                # the reference raises from np.linalg.cholesky (obq.py:49-50); the plan reports which layers
+                import numpy as np
+
+                raise np.linalg.LinAlgError(f"Matrix is not positive definite (layers {bad[:8]}{'...' if len(bad) > 8 else ''})")
         return (self.Q if self.outputs == "weights" else (self.codes, self.scales)), self.err
 
 

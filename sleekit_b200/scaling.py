@@ -120,8 +120,7 @@ def _compute_mse(H, E):
         out = ops.row_wsq(Ed.reshape(-1, Ed.shape[-1]).contiguous()).reshape(Ed.shape[:-1])
     elif H.ndim == 1:
         assert E.shape[1] == H.shape[0]
-        dt = cv.torch_float(np.result_type(cv.float_dtype_of(E), cv.float_dtype_of(H)))
-        out = ops.row_wsq(cv.to_dev_cached(E, dt), cv.to_dev_cached(H, dt))
+        out = ops.row_wsq(cv.to_dev_cached(E), cv.to_dev_cached(H))     # dtype promotion inside (np.square(E) in E's dtype)
     else:
         assert H.ndim == 2 and E.shape[1] == H.shape[0] and H.shape[1] == H.shape[0]
         dt = cv.torch_float(np.result_type(cv.float_dtype_of(E), cv.float_dtype_of(H)))

@@ -44,7 +44,11 @@ class Sleekit:
         return w if w.type == "cuda" else ops.device()
 
     def _prepare_input(self, inp):
-        """2-D [features, samples] view of a batch (statistics.py:37-74)."""
+        """2-D [features, samples] view of a batch (statistics.py:37-74).  This is the GPTQ-compatible
+        interface's own reshape / unfold sequence (Linear: flatten + transpose; Conv: F.unfold with the layer's
+        kernel / dilation / padding / stride, then [features, batch * positions]); it is layer plumbing that
+        stays torch's and necessarily mirrors the reference step by step -- the arithmetic that follows it
+        (K1, ops.hessian_accum) is what this package replaces."""
         if isinstance(self.layer, nn.Linear):
             inp = inp.reshape((-1, inp.shape[-1]))
             inp = inp.t()

@@ -794,6 +794,41 @@ def test_host_plan_equals_per_layer_api(slk):
             assert rel(err[i], slk.obq.quantization_error(W, want, H)) < 1e-4
 
 
+@pytest.mark.parametrize("batched", [False, True])
+def test_host_plan_variants(slk, batched):
+    """The plan with batched factorisations equals the per-layer plan bit for bit; outputs="codes" returns the
+    codebook indices and row scales of the same result; a non-positive-definite Hessian raises LinAlgError
+    (obq.py:49-50) naming the layer."""
+    from sleekit_b200.pipeline import LayerSetQuantizer
+
+    shapes = [(64, 256), (96, 256), (32, 320), (64, 256), (48, 320)]
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    grid = orc.UniformGrid(8, -1, 1)
+    lsq = LayerSetQuantizer(cb, scaling_mode="diag", act_order="diag", damp=0.01, streams=3)
+    layers = [wl.synthetic_layer(r, n, 40 + i, samples=512) for i, (r, n) in enumerate(shapes)]
+    ref_plan = lsq.host_plan(shapes)
+    ref_plan.batch_k2 = False
+    plan = lsq.host_plan(shapes, outputs="codes")
+    plan.batch_k2 = batched
+    for p in (ref_plan, plan):
+        for i, (W, H, m) in enumerate(layers):
+            p.W[i][...] = W
+            p.H[i][...] = H
+    Q, err = ref_plan.run()
+    (codes, scales), err2 = plan.run()
+    np.testing.assert_array_equal(err, err2)
+    for i, (W, H, m) in enumerate(layers):
+        assert codes[i].dtype == np.uint8 and scales[i].shape == (shapes[i][0],)
+        np.testing.assert_array_equal(codes[i], grid.index(orc.divide_rows(Q[i], scales[i], 0)))
+        np.testing.assert_array_equal(orc.divide_rows(grid._to_value(codes[i].astype(np.float32)), 1 / scales[i], 0), Q[i])
+    plan.H[2][...] = -np.eye(320, dtype=np.float32)
+    with pytest.raises(np.linalg.LinAlgError, match="layers \\[2\\]"):
+        plan.run()
+    plan.H[2][...] = layers[2][1]
+    (codes, scales), err3 = plan.run()
+    np.testing.assert_array_equal(err3, err)
+
+
 @pytest.mark.parametrize("n", [32, 100, 768, 1000, 1100, 3072])
 def test_symmetric_upload_equals_full_copy(slk, n):
     """slk_upload_symmetric_f32: only the block upper triangle of a symmetric pinned host matrix crosses

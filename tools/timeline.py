@@ -57,6 +57,12 @@ def main():
             lsq(Wd, Hd, keep_outputs=False)
         torch.cuda.synchronize()
         lsq.trace = trace
+        strace = None
+        if "--sweeptrace" in sys.argv:
+            import ctypes
+            from sleekit_b200 import _lib
+            strace = torch.zeros((128, 8), dtype=torch.int64, device=dev)
+            _lib.call("slk_debug_sweep_trace", ctypes.c_void_p(strace.data_ptr()))
         if per_op:
             ops.TRACE = {"buf": torch.zeros(8192, dtype=torch.int64, device=dev), "names": [], "tag": None}
         g, errs, _ = lsq.capture(Wd, Hd)
@@ -90,6 +96,15 @@ def main():
             s, e = t[:, c0], t[:, c1]
             return float(np.nansum(np.clip(np.minimum(e, b) - np.maximum(s, a), 0, None)) / 0.5)
         print(f"{a:5.1f}  {overlap(1, 2):6.1f}  {overlap(2, 3):6.1f}  {overlap(3, 6):6.1f}  {overlap(6, 7):6.1f}")
+    if not e2e and strace is not None:
+        st_ = strace.cpu().numpy()
+        st_ = st_[st_[:, 0] > 0]
+        print("sweep macro kernel, CTA 0 of the last launch that wrote the trace, cycles per 32-column block:")
+        print("  block  wait-barrier  tail+reduce  U_JJ-multiply  leaf||look-ahead  total")
+        for b in range(len(st_)):
+            r_ = st_[b]
+            nxt = st_[b + 1][0] if b + 1 < len(st_) else r_[5]
+            print(f"  {b:4d}  {r_[1]-r_[0]:10d}  {r_[2]-r_[1]:10d}  {r_[3]-r_[2]:10d}  {r_[4]-r_[3]:10d}  {nxt-r_[0]:8d}")
     if per_op and not e2e:
         ot = optrace["buf"].cpu().numpy().astype(np.float64)
         names = optrace["names"]
