@@ -279,27 +279,77 @@ def run_reference(args):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled WHILE the timed region runs: an NVML polling thread (5 ms period;
+    nvidia_ml_py), with `nvidia-smi -lms` as fallback.  stop(window) prefers the samples inside the timed window."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
+        self.samples = []            # (time.perf_counter(), sm MHz, max MHz, reasons bitmask)
+        self.thread = None
+        self.stop_flag = False
         self.proc = None
         self.path = None
 
+    def _poll(self, handle, nv):
+        mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((time.perf_counter(), float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.thread = threading.Thread(target=self._poll, args=(handle, nv), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    def stop(self, window=None):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            rows = self.samples
+            inside = [r for r in rows if window and window[0] <= r[0] <= window[1]]
+            use = inside or rows
+            if use:
+                bits = 0
+                for r in use:
+                    bits |= r[3]
+                out.update(sm_mhz=statistics.median(r[1] for r in use), sm_max_mhz=max(r[2] for r in use),
+                           reasons=sorted(n for n, b in self.REASONS if bits & b), samples=len(use),
+                           samples_inside_timed_region=len(inside), source="NVML, 5 ms period")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -311,21 +361,22 @@ class ClockSampler:
         try:
             for ln in open(self.path):
                 f = [x.strip() for x in ln.split(",")]
-                if len(f) < 9:
+                if len(f) < 7:
                     continue
                 try:
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                     if val.lower() == "active":
                         reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi -lms 50 (started before the warm-up; whole loaded window)")
         return out
 
 
@@ -369,6 +420,7 @@ class Dist:
             fn()
         e1.record()
         self.barrier()
+        self.last_window = (t0, time.perf_counter())
         wall = 1e3 * (time.perf_counter() - t0)
         ms = e0.elapsed_time(e1)
         if self.world > 1:
@@ -556,7 +608,7 @@ def sharded_layer(args, D, steps, warmup, peaks):
     sampler = ClockSampler(D.local)
     sampler.start()
     ms, wall = D.timed(step, steps)
-    clocks = sampler.stop()
+    clocks = sampler.stop(D.last_window)
     slq(W, X, timing=True)
     phases = dict(slq.phases_ms)
     if D.world > 1:
@@ -704,7 +756,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     # one stream: an event pair then brackets exactly one operation's kernels (on overlapping streams
     # they would include each other); the factorisations are batched exactly as in the timed pass
-    serial = make(1, False)
+    serial = make(1, not args.model_order)
     serial(Wd, Hd, errs_out=errs, keep_outputs=False, means=means)
     torch.cuda.synchronize()
     ops.PROFILE = {}
@@ -735,7 +787,7 @@ def run_ours(args):
     sampler = ClockSampler(D.local)
     sampler.start()
     ms, wall = D.timed(step_device, args.steps)
-    clocks = sampler.stop()
+    clocks = sampler.stop(D.last_window)
     # a replay launches the kernels recorded at capture time; count them with one eager pass
     launches0 = ops.launch_count()
     serial(Wd, Hd, errs_out=torch.zeros_like(errs), keep_outputs=False, means=means)
@@ -744,6 +796,40 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * weights / (ms_per_step * 1e-3)
     layer_err = float(errs.mean().item())
+
+    # ---- where the step's time goes, measured INSIDE the timed configuration --------------------------
+    # The timed step is a multi-stream graph: kernels of different layers overlap, so no event pair brackets
+    # one kernel.  A second capture of the same pass carries stream-ordered %globaltimer stamps
+    # (slk_debug_timestamp) around every layer's phases and around every factor launch; one untimed replay of
+    # it gives each factor launch's duration as it runs beside the other layers' work.
+    in_step = None
+    if graph is not None and lsq.batch_k2 and L > 1:
+        trace = torch.zeros((L, 8), dtype=torch.int64, device=dev)
+        lsq.trace = trace
+        g2, _, _ = lsq.capture(Wd, Hd, means=means)
+        lsq.trace = None
+        g2.replay()
+        torch.cuda.synchronize()
+        trace.zero_()
+        g2.replay()
+        torch.cuda.synchronize()
+        tt = trace.cpu().numpy().astype(np.float64)
+        t0 = tt[tt > 0].min()
+        tt = np.where(tt > 0, (tt - t0) / 1e6, np.nan)                      # ms since the first stamp
+        pass_ms = float(np.nanmax(tt))
+        launches_k2 = []
+        for (n_, b_), head in zip(lsq.last_groups, lsq.last_group_heads):
+            b0, b1 = float(tt[head, 4]), float(tt[head, 5])
+            launches_k2.append({"n": n_, "matrices": b_, "begin_ms": round(b0, 3), "end_ms": round(b1, 3), "ms": round(b1 - b0, 4),
+                                "achieved": round(b_ * n_ ** 3 / 3.0 / ((b1 - b0) * 1e-3) / 1e12, 3),
+                                "share_of_step": round((b1 - b0) / pass_ms, 3)})
+        in_step = {"pass_ms_with_stamps": round(pass_ms, 3),
+                   "scale_search_window_ms": [round(float(np.nanmin(tt[:, 1])), 3), round(float(np.nanmax(tt[:, 2])), 3)],
+                   "sweep_window_ms": [round(float(np.nanmin(tt[:, 6])), 3), round(float(np.nanmax(tt[:, 7])), 3)],
+                   "factor_launches": launches_k2,
+                   "note": "device %globaltimer stamps on the launching streams, one untimed replay of the same graph with the "
+                           "stamps captured in; the factor launches run beside the other layers' scale searches and sweeps"}
+        del g2
     err_check = None
     if not cfg["moves"]:
         # the timed pass takes each layer's error from the sweep's residuals (sum E^2 - damp * sum D^2,
@@ -853,6 +939,22 @@ def run_ours(args):
         del outs, scs
 
     roofline = rooflines.get(top) if top else None
+    if in_step and in_step["factor_launches"]:
+        # the kernel with the largest share of the TIMED step: the batched factor launch of the widest layers
+        big = max(in_step["factor_launches"], key=lambda e: e["ms"])
+        tr_ = ncu_traffic().get(f"chol_factor_batched:n={big['n']}x{big['matrices']}")
+        roofline = {"kernel": "chol_dag_kernel (slk_chol_factor_batched_f32, %d matrices of n = %d in one launch)" % (big["matrices"], big["n"]),
+                    "bound": "tensor", "unit": "TFLOP/s", "achieved": big["achieved"], "peak": peaks["fp64_tflops"],
+                    "frac": big["achieved"] / peaks["fp64_tflops"], "peak_source": peaks["fp64_source"],
+                    "avg_launch_ms": big["ms"], "launches_timed": 1, "share_of_step": big["share_of_step"],
+                    "traffic": tr_["dram_bytes_per_launch"] if tr_ else None,
+                    "by_launch": in_step["factor_launches"],
+                    "note": ("dominant kernel of the timed step by duration.  Algorithmic work n^3/3 fp64 flop per matrix (factor "
+                             "only: the sweep's R form needs no inverse) / the launch's duration INSIDE the step (device "
+                             "%globaltimer stamps on its stream; it runs with one CTA per SM while the other layers' scale "
+                             "searches and sweeps share the SMs).  FP64 tensor path (DMMA); peak = cuBLAS fp64 GEMM measured in "
+                             "this run.  Alone on the GPU the same launch reaches the figure in profiles/ (ncu: DMMA pipe 56 % "
+                             "active).  rooflines_all_phases has every operation of the serial profile pass.")}
     issued3 = {"gptq_sweep", "hweighted_error", "scale_search_fullh", "local_search"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -864,7 +966,7 @@ def run_ours(args):
                    "l2": f"inputs (W+H ~{sum(4 * r * n + 4 * n * n for r, n in shapes) / 1e9:.2f} GB per rank) are larger than "
                          "the 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "e2e_codes": e2e_codes, "e2e_numpy_api": e2e_numpy, "gpu_launches": launches,
-        "roofline": roofline,
+        "roofline": roofline, "in_step": in_step,
         "rooflines_all_phases": {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "share_of_serial_device_time")}
                                  for k, v in rooflines.items()},
         "tensor_issue_note": f"3xTF32: kernels {sorted(issued3 & set(rooflines))} issue 3 TF32 MMA flop per algorithmic flop",

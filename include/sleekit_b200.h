@@ -113,6 +113,10 @@ int slk_codebook_breaks_host(const slk_codebook* cb_host, float* out16_host);
  * row, a multiple of 32 (bs >= n: plain full copy).  Strided async copies + one mirror kernel on
  * `stream`; slk_upload_symmetric_bytes returns the bytes that cross the bus. */
 int slk_upload_symmetric_f32(const float* h_host, float* h_dev, int64_t n, int64_t bs, void* stream);
+/* The two halves of slk_upload_symmetric_f32 for callers with a dedicated copy stream (copy on it, mirror on
+ * the consumer's stream after an event): the DMA queue then never waits for a kernel. */
+int slk_upload_symmetric_copy_f32(const float* h_host, float* h_dev, int64_t n, int64_t bs, void* stream);
+int slk_mirror_symmetric_f32(float* h_dev, int64_t n, int64_t bs, void* stream);
 size_t slk_upload_symmetric_bytes(int64_t n, int64_t bs);
 
 /* ---- K6: H-weighted error ---------------------------------------------------
@@ -244,6 +248,13 @@ int slk_peer_alloc(size_t bytes, void** dptr_host, void* handle_host);
 int slk_peer_open(const void* handle_host, void** dptr_host);
 int slk_peer_close(void* dptr);
 int slk_peer_free(void* dptr);
+
+/* In-place sum all-reduce of count floats (count % 4 == 0) over nranks peer-visible buffers (peers_host: HOST
+ * array of device pointers from slk_peer_alloc / slk_peer_open, entry `rank` = this rank's own): rank r sums
+ * the r-th slice over all ranks with NVLink peer loads and stores the result into every copy.  The caller puts
+ * a barrier over the ranks on the same stream before and after.  Exchange step of the sample-sharded statistics
+ * (Sleekit.add_batch summed over ranks, statistics.py:76-87). */
+int slk_peer_allreduce_f32(void* const* peers_host, int32_t nranks, int32_t rank, int64_t count, void* stream);
 
 /* Block-upper-triangle packing of a symmetric matrix (layout / size of slk_upload_symmetric_bytes):
  * the exchange format of the sample-sharded statistics (statistics.py:76-87 summed over ranks): pack

@@ -85,6 +85,7 @@ SIGNATURES = {
     "slk_peer_open": (_INT, [_P, _P]),
     "slk_peer_close": (_INT, [_P]),
     "slk_peer_free": (_INT, [_P]),
+    "slk_peer_allreduce_f32": (_INT, [_P, _I32, _I32, _I64, _P]),
     "slk_sym_pack_f32": (_INT, [_P, _I64, _I64, C.c_float, _P, _P]),
     "slk_sym_unpack_f32": (_INT, [_P, _I64, _I64, C.c_float, _P, _P]),
     "slk_gptq_sweep_r_ws_bytes": (_SZ, [_I64, _I64]),
@@ -101,6 +102,8 @@ SIGNATURES = {
     "slk_sweep_error_f32": (_INT, [_P, _P, _P, _I64, _P, _P, _P]),
     "slk_upload_symmetric_f32": (_INT, [_P, _P, _I64, _I64, _P]),
     "slk_upload_symmetric_bytes": (_SZ, [_I64, _I64]),
+    "slk_upload_symmetric_copy_f32": (_INT, [_P, _P, _I64, _I64, _P]),
+    "slk_mirror_symmetric_f32": (_INT, [_P, _I64, _I64, _P]),
     "slk_gptq_sweep_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _CB, _I32, _I32, _I32, _P]),
     "slk_local_search_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_local_search_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _P]),

@@ -25,7 +25,7 @@
 //    -> (matrix t % B, task t / B).  A CTA whose next tile is not ready is then almost always handed a
 //    tile of another matrix instead of spinning: the 72 layers of an OPT-125M pass are bound by the
 //    FP64 pipe instead of by 72 separate chains of diagonal tiles that each hold SM slots while they wait.
-//  * MULTI-GPU (slk_chol_factor_dist_f32): tile row i belongs to rank i % P; a rank runs the tile
+//  * MULTI-GPU (slk_chol_dist_*): tile rows are dealt to the ranks block-cyclically; a rank runs the tile
 //    tasks of its own rows in the same column-major order and PUSHES every finished tile (and the
 //    inverse of a diagonal tile) into the same place of every peer's workspace through NVLink peer
 //    stores, followed by a system-scope release of the tile's flag on that peer.  Consumers only ever
@@ -87,6 +87,7 @@ constexpr int CHOL_MAXP = 8;      // ranks of a distributed factorisation
 struct CholDagParams {
   int njobs, T;
   int nranks, rank;
+  int rowblock;          // multi-GPU: tile rows are dealt to the ranks in blocks of `rowblock` consecutive rows
   int64_t ld;
   int* ticket;
   double* A[CHOL_MAXJ];
@@ -354,12 +355,24 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
     const int tk = sm.ticket;
     const int job = MULTI ? 0 : tk % P.njobs;
     int rem = MULTI ? tk : tk / P.njobs;
+    // Rows are dealt block-cyclically: row i belongs to rank (i / RB) % NR (RB = 1, NR = 1 on one GPU).  The chain
+    // diag(j) -> solve(j+1, j) -> diag(j+1) then stays on one GPU for RB columns before it crosses NVLink.
+    // below(x) = owned rows < x; the m-th owned row is (m / RB) * RB * NR + RK * RB + m % RB.
+    const int RB = MULTI ? P.rowblock : 1;
+    auto below = [&](int x) {
+      const int per = RB * NR, r_ = x % per - RK * RB;
+      return (x / per) * RB + (r_ < 0 ? 0 : (r_ > RB ? RB : r_));
+    };
+    const int owned = below(T);
     int j = 0, i = 0;
     for (;; ++j) {
       if (j >= T) return;                                   // past this rank's last task
-      int first = j + (RK - j % NR + NR) % NR;              // first owned row at or below the diagonal
-      const int cnt = first < T ? (T - 1 - first) / NR + 1 : 0;
-      if (rem < cnt) { i = first + rem * NR; break; }
+      const int b = below(j), cnt = owned - b;              // owned rows at or below the diagonal of column j
+      if (rem < cnt) {
+        const int m = b + rem;
+        i = (m / RB) * RB * NR + RK * RB + m % RB;
+        break;
+      }
       rem -= cnt;
     }
     const bool diag = (i == j);
@@ -454,14 +467,24 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
       // by the export kernel after this launch
       const int64_t xoff = (int64_t)j * CT * CT;
       if (MULTI) {
+        // Local copy and local flag first (gpu-scope release: the solves of this GPU's own rows go on at once),
+        // then the peers' copies and their flags.  The CTA barrier orders every thread's stores before the
+        // flag writers' release stores, and a release is cumulative (the pattern of a grid barrier: one
+        // thread fences for the CTA), so no per-thread system fence sits on the chain of diagonal tiles.
+        for (int e = tid; e < CT * CT / 2; e += CTH) {
+          const int r = e >> 5, c2 = (e & 31) * 2;
+          *reinterpret_cast<double2*>(Dinv + xoff + r * CT + c2) = *reinterpret_cast<const double2*>(&sm.f.X[r * CP + c2]);
+        }
+        __syncthreads();
+        if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
         for (int e = tid; e < CT * CT / 2; e += CTH) {
           const int r = e >> 5, c2 = (e & 31) * 2;
           const double2 v = *reinterpret_cast<const double2*>(&sm.f.X[r * CP + c2]);
-          for (int q = 0; q < NR; ++q) *reinterpret_cast<double2*>(P.peerDinv[q] + xoff + r * CT + c2) = v;
+          for (int q = 0; q < NR; ++q)
+            if (q != RK) *reinterpret_cast<double2*>(P.peerDinv[q] + xoff + r * CT + c2) = v;
         }
-        __threadfence_system();     // every writer orders its peer stores before the flags below
         __syncthreads();
-        if (tid < NR) st_release_sys(P.peerReady[tid] + (int64_t)i * T + j, 1);
+        if (tid < NR && tid != RK) st_release_sys(P.peerReady[tid] + (int64_t)i * T + j, 1);
         for (int e = tid; e < CT * CT; e += CTH) {
           const int r = e >> 6, c = e & 63;
           const double v = (r >= c) ? sm.f.M[c * CP + r] : 0.0;
@@ -533,13 +556,18 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
             *reinterpret_cast<double2*>(&sm.f.M[row * CP + col]) = make_double2(out[ii][jj][0], out[ii][jj][1]);
           }
         __syncthreads();
+        for (int e = tid; e < CT * CT / 2; e += CTH) {           // local copy + local flag first
+          const int r = e >> 5, c2 = (e & 31) * 2;
+          *reinterpret_cast<double2*>(Cij + (int64_t)r * ld + c2) = *reinterpret_cast<const double2*>(&sm.f.M[r * CP + c2]);
+        }
+        __syncthreads();
+        if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
         for (int e = tid; e < CT * CT / 2; e += CTH) {
           const int r = e >> 5, c2 = (e & 31) * 2;
           const double2 v = *reinterpret_cast<const double2*>(&sm.f.M[r * CP + c2]);
           for (int q = 0; q < NR; ++q)
-            *reinterpret_cast<double2*>(P.peerA[q] + tile_off + (int64_t)r * ld + c2) = v;
+            if (q != RK) *reinterpret_cast<double2*>(P.peerA[q] + tile_off + (int64_t)r * ld + c2) = v;
         }
-        __threadfence_system();
       } else {
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii)
@@ -553,7 +581,7 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
     if (tr) tr[6] = clock64();
     __syncthreads();
     if (MULTI) {
-      if (tid < NR) st_release_sys(P.peerReady[tid] + (int64_t)i * T + j, 1);
+      if (tid < NR && tid != RK) st_release_sys(P.peerReady[tid] + (int64_t)i * T + j, 1);
     } else {
       if (tid == 0) st_release_gpu(ready + (int64_t)i * T + j, 1);
     }
@@ -564,7 +592,7 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
 // R32[a, b] = L[npad-1-a, npad-1-b] for b >= a (0 below); rt_hi + rt_lo = R32^T on and below its
 // diagonal, split into TF32 parts (the part above is never read and left untouched); Ud[blk][p][q] = inverse of the 32x32 diagonal
 // block R[32blk.., 32blk..] = flip of the matching diagonal block of the tile inverses.
-// One CTA per 32x32 tile pair (ta <= tb) and matrix (blockIdx.y); the transpose goes through shared
+// One CTA per 32x32 tile pair (ta <= tb) and matrix (blockIdx.z); the transpose goes through shared
 // memory so that all global accesses are coalesced.
 struct CholExportParams {
   const double* A[CHOL_MAXJ];
@@ -578,7 +606,7 @@ struct CholExportParams {
 __global__ void __launch_bounds__(256) chol_export_kernel(const __grid_constant__ CholExportParams P, int64_t n,
                                                           int64_t npad) {
   __shared__ float tile[32][33];
-  const int job = blockIdx.y;
+  const int job = blockIdx.z;
   const double* __restrict__ A = P.A[job];
   const double* __restrict__ Dinv = P.Dinv[job];
   float* __restrict__ r32 = P.r32[job];
@@ -587,10 +615,10 @@ __global__ void __launch_bounds__(256) chol_export_kernel(const __grid_constant_
   float* __restrict__ ud32 = P.ud32[job];
   const int64_t nt = (n + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  // linear block id -> (ta, tb), tb >= ta
-  int64_t ta = 0, rem = blockIdx.x;
-  while (rem >= nt - ta) { rem -= nt - ta; ++ta; }
-  const int64_t tb = ta + rem;
+  // grid (nt, nt, jobs): CTA (tb, ta) with tb >= ta (a linear tile id decoded by a loop cost O(nt) per CTA:
+  // milliseconds at n = 28672)
+  const int64_t tb = blockIdx.x, ta = blockIdx.y;
+  if (tb < ta || tb >= nt) return;
   const int64_t a0 = ta * 32, b0 = tb * 32;
   for (int i = ty; i < 32; i += 8) {
     const int64_t a = a0 + i, b = b0 + tx;
@@ -668,6 +696,10 @@ static int chol_dag(int njobs, int64_t n, void* const* ws, int32_t* const* info,
   const int T = (int)(npad / CT);
   CholDagParams P;
   P.njobs = njobs; P.T = T; P.nranks = nranks; P.rank = rank; P.ld = npad;
+  // rows per ownership block of the distributed factorisation (SLK_CHOL_DIST_BLOCK; 1 = plain cyclic rows)
+  static int rowblock = -2;
+  if (rowblock == -2) rowblock = env_int("SLK_CHOL_DIST_BLOCK", 1);
+  P.rowblock = rowblock < 1 ? 1 : rowblock;
   for (int k = 0; k < njobs; ++k) {
     const ChWs w = chol_ws_layout(ws[k], n);
     P.A[k] = w.A; P.Dinv[k] = w.Dinv; P.ready[k] = w.ready; P.info[k] = info[k];
@@ -683,7 +715,11 @@ static int chol_dag(int njobs, int64_t n, void* const* ws, int32_t* const* info,
   size_t smem = sizeof(CholSmem);
   if (nranks > 1) {
     // every rank owns ~1/P of the tasks of every column; the FP64 pipe is the bound
-    grid = 2 * sms;
+    // (SLK_CHOL_DIST_CTAS: CTAs per SM x 100, experiments)
+    static int dist_pct = -2;
+    if (dist_pct == -2) dist_pct = env_int("SLK_CHOL_DIST_CTAS", 200);
+    grid = sms * dist_pct / 100;
+    if (grid < 1) grid = 1;
   } else if (njobs == 1) {
     // CTAs: a small factorisation is bound by the chain of diagonal tiles, not by the number of CTAs
     // (n = 768: the same 0.28 ms with 11 to 26 CTAs), and every CTA beyond the useful ones only holds
@@ -734,7 +770,7 @@ static int chol_export(int njobs, int64_t n, void* const* ws, float* const* r32,
     E.rt_lo[k] = split ? rt_lo[k] : nullptr;
   }
   const int64_t nt32 = (n + 31) / 32;
-  dim3 grid((unsigned)(nt32 * (nt32 + 1) / 2), (unsigned)njobs);
+  dim3 grid((unsigned)nt32, (unsigned)nt32, (unsigned)njobs);
   chol_export_kernel<<<grid, 256, 0, st>>>(E, n, npad);
   SLK_LAUNCH_CHECK();
   return SLK_OK;

@@ -526,7 +526,7 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
                                            float* __restrict__ qrow, float* __restrict__ drow,
                                            float* __restrict__ dhi, float* __restrict__ dlo,
                                            const float (&w0)[8], float* __restrict__ dsm, float* __restrict__ esm,
-                                           const float* __restrict__ XV = nullptr) {
+                                           const float* __restrict__ XV = nullptr, long long* tr = nullptr) {
   float X[8], V[8];
   float se = 0.0f;
   if (MODE == 2) {
@@ -538,7 +538,9 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
   for (int p = 0; p < 4; ++p) {
     if (p * 8 >= width) break;
     float resv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long tA = tr ? clock64() : 0;
     if (part == p) {
+      float qv[8], dv8[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int i = p * 8 + t;
@@ -564,7 +566,8 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
           qq = grid_value(g, w);
         }
         const float res = __fmul_rn(__fsub_rn(w, qq), sh.Uy[i]);
-        resv[t] = (i < width) ? res : 0.0f;              // padding columns carry nothing (and add nothing to se)
+        const bool in = i < width;
+        resv[t] = in ? res : 0.0f;                       // padding columns carry nothing (and add nothing to se)
         if (t < 7) {
           const float4 ua = *reinterpret_cast<const float4*>(&sh.U[i][p * 8]);
           const float4 ub = *reinterpret_cast<const float4*>(&sh.U[i][p * 8 + 4]);
@@ -572,22 +575,36 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
 #pragma unroll
           for (int c = t + 1; c < 8; ++c) q[c] = __fmaf_rn(-res, u[c], q[c]);
         }
-        const float dv = __fsub_rn(w0[t], qq);
-        const bool in = i < width;
-        dsm[i] = in ? dv : 0.0f;
-        if (rowok && in) {
-          qrow[i] = qq;
-          drow[i] = dv;
-          if (dhi) {                                   // TF32 parts for the macro-block GEMM
-            float h, l;
-            split_tf32(dv, h, l);
-            dhi[i] = h;
-            dlo[i] = l;
+        qv[t] = qq;
+        dv8[t] = in ? __fsub_rn(w0[t], qq) : 0.0f;
+      }
+      // Everything the 8 columns produce is stored AFTER their dependent chain, as 128-bit accesses with one
+      // predicate per quad (the macro path runs with n % 4 == 0 and 256-column macro blocks, so a quad of
+      // columns is inside the block or outside it as a whole) -- no store, predicate or branch sits between
+      // two links of the chain.
+      float4* dsm4 = reinterpret_cast<float4*>(dsm + p * 8);
+      dsm4[0] = make_float4(dv8[0], dv8[1], dv8[2], dv8[3]);
+      dsm4[1] = make_float4(dv8[4], dv8[5], dv8[6], dv8[7]);
+      if (rowok) {
+#pragma unroll
+        for (int h4 = 0; h4 < 2; ++h4) {
+          if (p * 8 + h4 * 4 < width) {
+            const int o = p * 8 + h4 * 4;
+            *reinterpret_cast<float4*>(qrow + o) = make_float4(qv[h4 * 4], qv[h4 * 4 + 1], qv[h4 * 4 + 2], qv[h4 * 4 + 3]);
+            *reinterpret_cast<float4*>(drow + o) = make_float4(dv8[h4 * 4], dv8[h4 * 4 + 1], dv8[h4 * 4 + 2], dv8[h4 * 4 + 3]);
+            if (dhi) {                                   // TF32 parts for the macro-block GEMM
+              float hh[4], ll[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split_tf32(dv8[h4 * 4 + j], hh[j], ll[j]);
+              *reinterpret_cast<float4*>(dhi + o) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<float4*>(dlo + o) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+            }
           }
         }
       }
     }
     __syncwarp();
+    const long long tB = tr ? clock64() : 0;
     const int owner_lane = (lane & ~3) | p;
 #pragma unroll
     for (int t = 0; t < 8; ++t) resv[t] = __shfl_sync(0xffffffffu, resv[t], owner_lane);
@@ -605,6 +622,7 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
         for (int c = 0; c < 8; ++c) q[c] = __fmaf_rn(-resv[t], u[c], q[c]);
       }
     }
+    if (tr) { tr[6] += tB - tA; tr[7] += clock64() - tB; }   // development trace: owner walk / shuffle + update
   }
   esm[0] = __fadd_rn(esm[0], se);                        // this lane's own shared-memory slot
 }
@@ -615,11 +633,11 @@ __device__ long long* g_sweep_trace = nullptr;   // development aid: per-block p
 
 // R panels of the macro kernel.  Default: two full buffers (the look-ahead of block a reads the
 // panel of block a+32 while the tail product of block a reads the last 32 rows of its own panel).
-// COMPACT (SLK_SWEEP_COMPACT=1, prepared at the end of round 1, NOT yet measured on a GPU and off by
-// default): only the last 32 rows of the current panel are ever read again, so one full buffer plus
-// two 32-row tail buffers do -- 20 KB less per CTA (R = 8/16: three CTAs per SM instead of two,
-// R = 32: two instead of one); the prefetch then has to be issued after the barrier that ends the
-// previous look-ahead.
+// COMPACT (default since round 2; SLK_SWEEP_COMPACT=0 selects the double buffer): only the last 32 rows of
+// the current panel are ever read again, so one full buffer plus two 32-row tail buffers do -- 20 KB less
+// per CTA (R = 8/16: three CTAs per SM instead of two, R = 32: two instead of one); the prefetch then has
+// to be issued after the barrier that ends the previous look-ahead.  Measured on B200: a single layer's
+// sweep is ~10 % slower (the prefetch starts later), a layer set's pass 1-2 % faster, [8192, 28672] 58 -> 55 ms.
 template <bool COMPACT>
 struct PanelBufs;
 template <>
@@ -828,7 +846,8 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
       float* dsm = &sm.Dm[lr][ka];
       float* dhi = Dhi ? Dhi + (row0 + lr) * n + a : nullptr;
       float* dlo = Dhi ? Dlo + (row0 + lr) * n + a : nullptr;
-      if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid], sm.XV);
+      if (tr) { tr[6] = 0; tr[7] = 0; }
+      if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid], sm.XV, tr);
       else if (fastq) leaf_rows4<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
       else leaf_rows4<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
     } else if (has_next) {
@@ -1002,7 +1021,7 @@ static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r
   static int compact = -1;   // SLK_SWEEP_COMPACT=0/1: double-buffered / single R-panel buffer (PanelBufs)
   if (compact < 0) {
     const char* ev = getenv("SLK_SWEEP_COMPACT");
-    compact = (ev && ev[0] == '1') ? 1 : 0;
+    compact = (ev && ev[0] == '0') ? 0 : 1;   // default on: one more CTA per SM (measured)
   }
   if (compact) return launch_macro_v<R, true>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
   return launch_macro_v<R, false>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);

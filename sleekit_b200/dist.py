@@ -46,7 +46,7 @@ def layers_of_rank(num_layers, rank, world):
     return list(range(rank, num_layers, world))
 
 
-def allreduce_statistics(hessian, mean, count, group=None):
+def allreduce_statistics(hessian, mean, count, group=None, peer_buffer=None, barrier=None):
     """Combine per-rank running means (statistics.py:76-87 semantics) into the global ones, IN PLACE.
 
     hessian [n, n], mean [n] fp32 are this rank's running means over `count` samples; on return they
@@ -55,7 +55,10 @@ def allreduce_statistics(hessian, mean, count, group=None):
     then weights its statistics by count / total so that ONE sum all-reduce yields the global means
     with no temporaries of the size of H.  On CUDA the Hessian -- symmetric -- is exchanged as its block
     upper triangle (ops.sym_pack / sym_unpack: ~53 % of the bytes, all-reduced in place in the packed
-    buffer); on CPU tensors (gloo tests) the full matrix is reduced in place."""
+    buffer); on CPU tensors (gloo tests) the full matrix is reduced in place.  peer_buffer (ops.PeerBuffer of
+    at least sym_packed_len(n) + n floats) + barrier: the packed statistics are summed by our own NVLink
+    kernel (slk_peer_allreduce_f32: every rank reduces one slice with peer loads and stores the sum into all
+    copies) instead of NCCL."""
     rank, world = _world(group)
     if world == 1:
         return hessian, mean, count
@@ -70,12 +73,21 @@ def allreduce_statistics(hessian, mean, count, group=None):
         from . import ops
 
         L = ops.sym_packed_len(n)
-        buf = torch.empty(L + n, dtype=torch.float32, device=hessian.device)
+        if peer_buffer is not None:
+            assert peer_buffer.count >= L + n and barrier is not None
+            buf = peer_buffer.tensor()
+            if peer_buffer.count > L + n:
+                buf[L + n:].zero_()
+        else:
+            buf = torch.empty(L + n, dtype=torch.float32, device=hessian.device)
         ops.sym_pack(hessian, buf, w)
-        torch.mul(mean, w, out=buf[L:])
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        torch.mul(mean, w, out=buf[L:L + n])
+        if peer_buffer is not None:
+            peer_buffer.allreduce(barrier)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         ops.sym_unpack(buf, hessian, 1.0)
-        mean.copy_(buf[L:])
+        mean.copy_(buf[L:L + n])
     else:
         hessian.mul_(w)
         mean.mul_(w)

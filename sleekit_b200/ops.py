@@ -444,6 +444,21 @@ def upload_symmetric(h_pinned, h_dev):
     return int(_lib.load().slk_upload_symmetric_bytes(n, bs))
 
 
+def upload_symmetric_copy(h_pinned, h_dev):
+    """DMA half of upload_symmetric (current stream)."""
+    assert h_pinned.is_pinned() and h_pinned.dtype == torch.float32 and h_pinned.is_contiguous()
+    _chk(h_dev, torch.float32)
+    n = h_dev.shape[0]
+    _call("slk_upload_symmetric_copy_f32", C.c_void_p(h_pinned.data_ptr()), _ptr(h_dev), n, symmetric_block_rows(n), _stream())
+
+
+def mirror_symmetric(h_dev):
+    """Device half of upload_symmetric (current stream): mirrors the block upper triangle."""
+    _chk(h_dev, torch.float32)
+    n = h_dev.shape[0]
+    _call("slk_mirror_symmetric_f32", _ptr(h_dev), n, symmetric_block_rows(n), _stream())
+
+
 @_timed("hinv")
 def hinv(h, order=None, dampval=None, want64=False, want32=True):
     """Upper factor U of the inverse of (h + dampval*I)[order][:, order]; returns (u64, u32, info)."""
@@ -603,6 +618,31 @@ class PeerWorkspace:
                 self.ptr = None
         except Exception:
             pass
+
+
+class PeerBuffer(PeerWorkspace):
+    """A peer-visible fp32 buffer (one per rank, mapped everywhere) + the in-place NVLink all-reduce over it
+    (slk_peer_allreduce_f32)."""
+
+    def __init__(self, count, group=None):
+        self.count = (int(count) + 3) // 4 * 4
+        super().__init__(4 * self.count, group)
+
+    def tensor(self):
+        """This rank's buffer as a float32 CUDA tensor view (no copy)."""
+        iface = {"shape": (self.count,), "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
+
+        class _Holder:
+            __cuda_array_interface__ = iface
+
+        return torch.as_tensor(_Holder(), device=device())
+
+    def allreduce(self, barrier):
+        """Sum over the ranks, in place, every copy bit-identical afterwards.  barrier(): stream-ordered."""
+        barrier()
+        _Target.dev = device()
+        _call("slk_peer_allreduce_f32", self.peer_array(), self.world, self.rank, self.count, _stream())
+        barrier()
 
 
 def chol_dist_ws_bytes(n):

@@ -208,6 +208,7 @@ class LayerSetQuantizer:
         if cur:
             groups.append(cur)
         self.last_groups = [(int(Ws[m[0]].shape[1]), len(m)) for m in groups]   # (n, matrices) per factor launch
+        self.last_group_heads = [m[0] for m in groups]                          # layer whose trace row holds the launch's stamps
         keep = []                                        # factor tensors stay alive until the join below
         for g, members in enumerate(groups):
             ks = self.k2_streams[g % len(self.k2_streams)]
@@ -361,7 +362,7 @@ class HostPlan:
         with torch.cuda.stream(cs):
             self._Wd[i].copy_(self._Wp[i], non_blocking=True)
             if self.symmetric_h:
-                ops.upload_symmetric(self._Hp[i], self._Hd[i])
+                ops.upload_symmetric_copy(self._Hp[i], self._Hd[i])   # DMA only: the copy queue never waits for a kernel
             else:
                 self._Hd[i].copy_(self._Hp[i], non_blocking=True)
             if self._Md is not None:
@@ -369,6 +370,8 @@ class HostPlan:
             ev = torch.cuda.Event()
             ev.record(cs)
         cur.wait_event(ev)
+        if self.symmetric_h:
+            ops.mirror_symmetric(self._Hd[i])                         # on the layer's own stream
 
     def _post(self, i, q, sc):
         if self.outputs == "weights":
@@ -451,6 +454,10 @@ class ShardedLayerQuantizer:
         self.world = tdist.get_world_size(group) if (tdist.is_available() and tdist.is_initialized()) else 1
         self.dist_factor = bool(dist_factor) and self.world > 1
         self.pws = ops.PeerWorkspace(ops.chol_dist_ws_bytes(self.n), group) if self.dist_factor else None
+        # the packed statistics are summed by our own NVLink kernel over a peer-visible buffer
+        # (SLK_PEER_ALLREDUCE=0: NCCL all-reduce instead)
+        self.pbuf = (ops.PeerBuffer(ops.sym_packed_len(self.n) + self.n, group)
+                     if (self.world > 1 and os.environ.get("SLK_PEER_ALLREDUCE", "1") != "0") else None)
         self._token = torch.zeros(1, dtype=torch.float32, device=ops.device())
         self.phases_ms = {}
 
@@ -470,6 +477,9 @@ class ShardedLayerQuantizer:
         if self.pws is not None:
             self.pws.close()
             self.pws = None
+        if self.pbuf is not None:
+            self.pbuf.close()
+            self.pbuf = None
 
     def __call__(self, W_rows, X_rows, timing=False):
         """W_rows [r_local, n], X_rows [S_local, n] fp32 on the device.  Returns (quantized rows,
@@ -495,7 +505,7 @@ class ShardedLayerQuantizer:
         if count:
             ops.hessian_accum(X_rows.contiguous(), H, mean, 0.0, count)
         mark("statistics")
-        H, mean, count = sdist.allreduce_statistics(H, mean, count, self.group)
+        H, mean, count = sdist.allreduce_statistics(H, mean, count, self.group, self.pbuf, self._barrier)
         mark("allreduce")
         Hq = ops.remove_input_bias(H, mean) if self.bias_correction else H
         sc = _device_scaling(W_rows, self.cb, Hq, self.scaling_mode, self.grid_size, self.min_factor, self.max_factor)

@@ -21,6 +21,13 @@ WANT = {
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active": "alu_pipe_pct",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "fma_pipe_pct",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
+    "sm__cycles_elapsed.max": "sm_cycles",
+    "launch__shared_mem_per_block_dynamic": "dyn_smem_bytes",
+    "launch__occupancy_limit_shared_mem": "occ_limit_smem",
+    "launch__occupancy_limit_registers": "occ_limit_regs",
+    "sm__inst_executed_pipe_fp64.sum": "fp64_inst",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
+    "smsp__inst_executed.sum": "warp_inst",
 }
 
 
@@ -32,8 +39,14 @@ def num(x):
 
 
 def main(path, case):
-    rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
     hdr, units = rows[0], rows[1]
+    # newer ncu versions prefix some metrics with their section ("FBSP.TriageCompute.dram__..."): index by suffix too
+    alias = {}
+    for h in hdr:
+        for k in WANT:
+            if h == k or h.endswith("." + k):
+                alias.setdefault(k, h)
     out = []
     for r in rows[2:]:
         rec = {"case": case}
@@ -41,7 +54,8 @@ def main(path, case):
         u = dict(zip(hdr, units))
         name = re.sub(r"\(.*", "", d.get("Kernel Name", ""))
         rec["kernel"] = re.sub(r"void |slk::", "", name)
-        for k, short in WANT.items():
+        for k0, short in WANT.items():
+            k = alias.get(k0, k0)
             if k in d and num(d[k]) is not None:
                 v = num(d[k])
                 if short == "duration_us":

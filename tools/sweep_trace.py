@@ -25,4 +25,5 @@ t = buf.cpu().numpy().reshape(8, 8)
 print("last macro block, CTA 0: per 32-column block clocks  wait | product+reduce | Ud multiply | leaf | copy")
 for b in range(8):
     x = t[b]
-    print(b, x[1] - x[0], x[2] - x[1], x[3] - x[2], x[4] - x[3], x[5] - x[4], " total", (t[b + 1][0] - x[0]) if b < 7 else "")
+    print(b, x[1] - x[0], x[2] - x[1], x[3] - x[2], x[4] - x[3], x[5] - x[4], " total", (t[b + 1][0] - x[0]) if b < 7 else "",
+          " leaf: owner walks", x[6], "shuffle+update", x[7])
