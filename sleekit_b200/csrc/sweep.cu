@@ -534,13 +534,15 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
     for (int k = 0; k < 8; ++k) { X[k] = XV[k]; V[k] = XV[8 + k]; }
   }
   const float top = (float)(g.size - 1);
+  float qv[8], dv8[8];                                   // this lane's eight columns: stored after all four phases
+#pragma unroll
+  for (int t = 0; t < 8; ++t) qv[t] = dv8[t] = 0.0f;
 #pragma unroll 1
   for (int p = 0; p < 4; ++p) {
     if (p * 8 >= width) break;
     float resv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const long long tA = tr ? clock64() : 0;
     if (part == p) {
-      float qv[8], dv8[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int i = p * 8 + t;
@@ -578,36 +580,15 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
         qv[t] = qq;
         dv8[t] = in ? __fsub_rn(w0[t], qq) : 0.0f;
       }
-      // Everything the 8 columns produce is stored AFTER their dependent chain, as 128-bit accesses with one
-      // predicate per quad (the macro path runs with n % 4 == 0 and 256-column macro blocks, so a quad of
-      // columns is inside the block or outside it as a whole) -- no store, predicate or branch sits between
-      // two links of the chain.
-      float4* dsm4 = reinterpret_cast<float4*>(dsm + p * 8);
-      dsm4[0] = make_float4(dv8[0], dv8[1], dv8[2], dv8[3]);
-      dsm4[1] = make_float4(dv8[4], dv8[5], dv8[6], dv8[7]);
-      if (rowok) {
-#pragma unroll
-        for (int h4 = 0; h4 < 2; ++h4) {
-          if (p * 8 + h4 * 4 < width) {
-            const int o = p * 8 + h4 * 4;
-            *reinterpret_cast<float4*>(qrow + o) = make_float4(qv[h4 * 4], qv[h4 * 4 + 1], qv[h4 * 4 + 2], qv[h4 * 4 + 3]);
-            *reinterpret_cast<float4*>(drow + o) = make_float4(dv8[h4 * 4], dv8[h4 * 4 + 1], dv8[h4 * 4 + 2], dv8[h4 * 4 + 3]);
-            if (dhi) {                                   // TF32 parts for the macro-block GEMM
-              float hh[4], ll[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) split_tf32(dv8[h4 * 4 + j], hh[j], ll[j]);
-              *reinterpret_cast<float4*>(dhi + o) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<float4*>(dlo + o) = make_float4(ll[0], ll[1], ll[2], ll[3]);
-            }
-          }
-        }
-      }
+      if (tr && p == 0) tr[8] = clock64() - tA;          // development trace: the bare 8-column chain of phase 0
     }
+    if (tr && p == 0) tr[9] = clock64() - tA;            // ... + its stores
     __syncwarp();
     const long long tB = tr ? clock64() : 0;
     const int owner_lane = (lane & ~3) | p;
 #pragma unroll
     for (int t = 0; t < 8; ++t) resv[t] = __shfl_sync(0xffffffffu, resv[t], owner_lane);
+    if (tr && p == 0) tr[10] = clock64() - tB;           // the eight shuffles
     // error identity (slk_gptq_sweep_r_err_f32): sum of res^2, off the owner's chain -- every lane of
     // the row holds the 8 residuals now and keeps the same running sum
 #pragma unroll
@@ -624,7 +605,152 @@ __device__ __forceinline__ void leaf_rows4(float (&q)[8], const LeafShared32& sh
     }
     if (tr) { tr[6] += tB - tA; tr[7] += clock64() - tB; }   // development trace: owner walk / shuffle + update
   }
+  // Everything a lane produced is stored AFTER the row's dependent chain, by all four lanes at once, as
+  // 128-bit accesses with one predicate per quad (the macro path runs with n % 4 == 0 and 256-column macro
+  // blocks, so a quad of columns is inside the block or outside it as a whole): no store, predicate or
+  // branch sits between two links of the chain, and the stores of the four lanes overlap.
+  if (part * 8 < width) {
+    float4* dsm4 = reinterpret_cast<float4*>(dsm + part * 8);
+    dsm4[0] = make_float4(dv8[0], dv8[1], dv8[2], dv8[3]);
+    dsm4[1] = make_float4(dv8[4], dv8[5], dv8[6], dv8[7]);
+    if (rowok) {
+#pragma unroll
+      for (int h4 = 0; h4 < 2; ++h4) {
+        if (part * 8 + h4 * 4 < width) {
+          const int o = part * 8 + h4 * 4;
+          *reinterpret_cast<float4*>(qrow + o) = make_float4(qv[h4 * 4], qv[h4 * 4 + 1], qv[h4 * 4 + 2], qv[h4 * 4 + 3]);
+          *reinterpret_cast<float4*>(drow + o) = make_float4(dv8[h4 * 4], dv8[h4 * 4 + 1], dv8[h4 * 4 + 2], dv8[h4 * 4 + 3]);
+          if (dhi) {                                     // TF32 parts for the macro-block GEMM
+            float hh[4], ll[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32(dv8[h4 * 4 + j], hh[j], ll[j]);
+            *reinterpret_cast<float4*>(dhi + o) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(dlo + o) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+          }
+        }
+      }
+    }
+  }
   esm[0] = __fadd_rn(esm[0], se);                        // this lane's own shared-memory slot
+}
+
+// The same leaf as ONE branch-free instruction stream (round 2).  leaf_rows4 above alternates two divergent
+// regions per phase -- the owner lane's 8-column walk, then 8 shuffles and the other lanes' 64 FMAs -- and a warp
+// issues in order, so the owner's chain stalls (50 cycles per column, tools/lat_chain.cu) hide nothing and the
+// update sits between two phases: 1.3-1.5 k cycles per phase measured, 400 of them the chain.  Here every lane
+// executes every column step: it rounds ITS column t (only the owner's result is used: the others are masked to
+// zero, and a multiply-add with a zero factor leaves a value unchanged bit for bit), the residual is broadcast
+// with one shuffle, and the lanes that own later columns apply the residual of the PREVIOUS step -- independent
+// FMAs the compiler schedules into the chain's stall slots.  Same operations on the same operands in the same
+// order for every weight as leaf_rows4: identical results.
+template <int MODE>
+__device__ __forceinline__ void leaf_rows4_pipelined(float (&q)[8], const LeafShared32& sh, const DevGrid<float>& g,
+                                                     const FastDivF& fstep, int width, int part, int lane, bool rowok,
+                                                     float* __restrict__ qrow, float* __restrict__ drow,
+                                                     float* __restrict__ dhi, float* __restrict__ dlo,
+                                                     const float (&w0)[8], float* __restrict__ dsm,
+                                                     float* __restrict__ esm, const float* __restrict__ XV = nullptr,
+                                                     long long* tr = nullptr) {
+  float X[8], V[8];
+  float se = 0.0f;
+  if (MODE == 2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { X[k] = XV[k]; V[k] = XV[8 + k]; }
+  }
+  const float top = (float)(g.size - 1);
+  float qv[8], dv8[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) qv[t] = dv8[t] = 0.0f;
+  const long long tA = tr ? clock64() : 0;
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    if (p * 8 >= width) break;
+    const bool own = part == p;
+    const bool later = part > p;
+    const int owner_lane = (lane & ~3) | p;
+    const float* urow_own = &sh.U[p * 8][p * 8];          // + t * 64: row p*8+t, the phase's own 8 columns
+    const float* urow_lat = &sh.U[p * 8][part * 8];       // + t * 64: row p*8+t, this lane's 8 columns
+    float rq = 0.0f;                                     // the previous step's residual, applied one step late
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int i = p * 8 + t;
+      const float w = q[t];
+      float qq;
+      if (MODE == 2) {
+        const bool b2 = w >= X[4];
+        const float t1 = b2 ? X[6] : X[2];
+        const float xa = b2 ? X[7] : X[3], xb = b2 ? X[5] : X[1];
+        const float va = b2 ? V[7] : V[3], vb = b2 ? V[5] : V[1], vc = b2 ? V[6] : V[2], vd = b2 ? V[4] : V[0];
+        const bool b1 = w >= t1;
+        const float t0 = b1 ? xa : xb;
+        const float c1 = b1 ? va : vb, c0 = b1 ? vc : vd;
+        qq = (w >= t0) ? c1 : c0;
+      } else if (MODE == 1) {
+        const float tt = fastdiv_core(__fsub_rn(w, g.zero), fstep.d, fstep.y);
+        float k = __fsub_rn(__fadd_rn(tt, 12582912.0f), 12582912.0f);
+        k = fminf(fmaxf(k, 0.0f), top);
+        qq = __fadd_rn(__fmul_rn(k, g.step), g.zero);
+      } else {
+        qq = grid_value(g, w);
+      }
+      const float res = __fmul_rn(__fsub_rn(w, qq), sh.Uy[i]);
+      const bool live = own && i < width;                // padding columns and the other lanes carry nothing
+      const float res_m = live ? res : 0.0f;
+      if (t < 7) {
+        const float4 ua = *reinterpret_cast<const float4*>(urow_own + t * 64);
+        const float4 ub = *reinterpret_cast<const float4*>(urow_own + t * 64 + 4);
+        const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+        for (int c = t + 1; c < 8; ++c) q[c] = __fmaf_rn(-res_m, u[c], q[c]);
+      }
+      qv[t] = own ? qq : qv[t];
+      dv8[t] = own ? (i < width ? __fsub_rn(w0[t], qq) : 0.0f) : dv8[t];
+      // the later lanes apply the PREVIOUS step's residual (already broadcast) ...
+      if (t > 0) {
+        const float rm = later ? rq : 0.0f;
+        const float4 ua = *reinterpret_cast<const float4*>(urow_lat + (t - 1) * 64);
+        const float4 ub = *reinterpret_cast<const float4*>(urow_lat + (t - 1) * 64 + 4);
+        const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = __fmaf_rn(-rm, u[c], q[c]);
+      }
+      // ... while this step's residual travels
+      rq = __shfl_sync(0xffffffffu, res_m, owner_lane);
+      se = __fmaf_rn(rq, rq, se);
+    }
+    {                                                    // the phase's last residual
+      const float rm = later ? rq : 0.0f;
+      const float4 ua = *reinterpret_cast<const float4*>(urow_lat + 7 * 64);
+      const float4 ub = *reinterpret_cast<const float4*>(urow_lat + 7 * 64 + 4);
+      const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) q[c] = __fmaf_rn(-rm, u[c], q[c]);
+    }
+  }
+  if (tr) { tr[6] = clock64() - tA; tr[7] = 0; }
+  if (part * 8 < width) {
+    float4* dsm4 = reinterpret_cast<float4*>(dsm + part * 8);
+    dsm4[0] = make_float4(dv8[0], dv8[1], dv8[2], dv8[3]);
+    dsm4[1] = make_float4(dv8[4], dv8[5], dv8[6], dv8[7]);
+    if (rowok) {
+#pragma unroll
+      for (int h4 = 0; h4 < 2; ++h4) {
+        if (part * 8 + h4 * 4 < width) {
+          const int o = part * 8 + h4 * 4;
+          *reinterpret_cast<float4*>(qrow + o) = make_float4(qv[h4 * 4], qv[h4 * 4 + 1], qv[h4 * 4 + 2], qv[h4 * 4 + 3]);
+          *reinterpret_cast<float4*>(drow + o) = make_float4(dv8[h4 * 4], dv8[h4 * 4 + 1], dv8[h4 * 4 + 2], dv8[h4 * 4 + 3]);
+          if (dhi) {
+            float hh[4], ll[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32(dv8[h4 * 4 + j], hh[j], ll[j]);
+            *reinterpret_cast<float4*>(dhi + o) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(dlo + o) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+          }
+        }
+      }
+    }
+  }
+  esm[0] = __fadd_rn(esm[0], se);
 }
 
 constexpr int MB_COLS = 256;
@@ -672,8 +798,8 @@ struct MacroSmem {
   LeafShared32 leaf;
 };
 
-template <int R, bool COMPACT>
-__global__ void __launch_bounds__(FT, COMPACT ? (R == 32 ? 2 : 3) : 2)
+template <int R, bool COMPACT, bool PIPE>
+__global__ void __launch_bounds__(FT, (COMPACT && !PIPE) ? (R == 32 ? 2 : 3) : 2)
 sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int64_t n,
                                                          const float* __restrict__ Rf, const float* __restrict__ Ud,
                                                          DevGrid<float> g, int64_t c0, int64_t c1,
@@ -709,9 +835,13 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
   };
   // R panel of block a: rows c0 .. a-1, columns a .. a+31 (zero beyond c1)
   auto prefetch_panel = [&](int64_t a, int buf) {
+    // issued by the helper threads only (the ones that read it first, in the look-ahead): the leaf threads
+    // then never wait for the panel -- in the compact layout it is requested one barrier later and used to
+    // cost the chain several hundred cycles per block at the CTA-wide wait
+    if (tid < SM::NLEAF) return;
     const int rows = (int)(a - c0);
     const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
-    for (int t = tid; t < rows * 8; t += FT) {
+    for (int t = tid - SM::NLEAF; t < rows * 8; t += SM::HELP) {
       const int k = t >> 3, piece = t & 7;
       float* dst;
       if constexpr (COMPACT) dst = (k < rows - 32) ? &sm.pb.Rs[0][k][piece * 4] : &sm.pb.Rt[buf][k - (rows - 32)][piece * 4];
@@ -748,17 +878,10 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
     const int width = (int)((c1 - a) < 32 ? (c1 - a) : 32);
     const int ka = (int)(a - c0);                      // columns of D that exist when this block starts
     const bool has_next = a + 32 < c1;
-    if (has_next) {
-      if constexpr (!COMPACT) prefetch_panel(a + 32, buf ^ 1);   // read by the look-ahead below and by the next tail
-      fetch(a + 32, nxt);
-    }
-    long long* tr = (g_sweep_trace && blockIdx.x == 0 && tid == 0) ? g_sweep_trace + ((a - c0) / 32) * 8 : nullptr;
+    if (has_next) fetch(a + 32, nxt);
+    long long* tr = (g_sweep_trace && blockIdx.x == 0 && tid == 0) ? g_sweep_trace + ((a - c0) / 32) * 16 : nullptr;
     if (tr) tr[0] = clock64();
-    __syncthreads();                                   // previous leaf's D and the look-ahead sums are visible
-    if constexpr (COMPACT) {
-      // the single full buffer was read by the look-ahead that the barrier above has just ended
-      if (has_next) prefetch_panel(a + 32, buf ^ 1);
-    }
+    __syncthreads();                                   // previous leaf's D, the look-ahead sums and the panel are visible
     if (tr) tr[1] = clock64();
     // ---- (1) tail: D[:, a-32:a] R[a-32:a, J]: four chains of 8 k-steps each (chain c = k 8c..8c+7), dealt to
     // the KG thread groups, summed ((c0 + c1) + c2) + c3 -- the same association for every tile height R
@@ -790,22 +913,39 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
       for (int j = 0; j < 4; ++j) {
         sm.leaf.U[i][seg * 4 + j] = cur.ud[j];
         sm.leaf.U[i][32 + seg * 4 + j] = 0.0f;
-#pragma unroll
-        for (int c = 0; c < CPG; ++c) sm.red[kg * CPG + c][lrow][seg * 4 + j] = acc[c][j];
       }
       if (tid < 32) sm.leaf.Uy[tid] = cur.rdiag;
     }
-    __syncthreads();
-    if (kg == 0) {
+    if constexpr (KG == 1) {
+      // one thread group holds all four chains: same association ((c0 + c1) + c2) + c3, in registers,
+      // and one CTA barrier less per block
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float t = sm.red[0][lrow][seg * 4 + j];
+        float t = acc[0][j];
 #pragma unroll
-        for (int q = 1; q < 4; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
+        for (int q = 1; q < 4; ++q) t = __fadd_rn(t, acc[q][j]);
 #pragma unroll
         for (int q = 0; q < SM::KGH; ++q) t = __fadd_rn(t, sm.red2[q][lrow][seg * 4 + j]);
         sm.Qs[lrow][seg * 4 + j] = __fadd_rn(t, cur.pa[j]);
         sm.W0[lrow][seg * 4 + j] = cur.wq[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) sm.red[kg * CPG + c][lrow][seg * 4 + j] = acc[c][j];
+      __syncthreads();
+      if (kg == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = sm.red[0][lrow][seg * 4 + j];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) t = __fadd_rn(t, sm.red[q][lrow][seg * 4 + j]);
+#pragma unroll
+          for (int q = 0; q < SM::KGH; ++q) t = __fadd_rn(t, sm.red2[q][lrow][seg * 4 + j]);
+          sm.Qs[lrow][seg * 4 + j] = __fadd_rn(t, cur.pa[j]);
+          sm.W0[lrow][seg * 4 + j] = cur.wq[j];
+        }
       }
     }
     __syncthreads();
@@ -828,7 +968,6 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
 #pragma unroll
       for (int j = 0; j < 4; ++j) sm.Qs[lrow][seg * 4 + j] = __fadd_rn(cur.wq[j], s4[j]);
     }
-    cp_async_wait<0>();                                // the next block's panel (own pieces) has landed
     __syncthreads();
     if (tr) tr[3] = clock64();
     if (tid < SM::NLEAF) {
@@ -846,12 +985,23 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
       float* dsm = &sm.Dm[lr][ka];
       float* dhi = Dhi ? Dhi + (row0 + lr) * n + a : nullptr;
       float* dlo = Dhi ? Dlo + (row0 + lr) * n + a : nullptr;
-      if (tr) { tr[6] = 0; tr[7] = 0; }
-      if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid], sm.XV, tr);
-      else if (fastq) leaf_rows4<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
-      else leaf_rows4<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
+      if (tr) { tr[6] = 0; tr[7] = 0; tr[11] = clock64(); }
+      if constexpr (PIPE) {
+        if (tree) leaf_rows4_pipelined<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid], sm.XV, tr);
+        else if (fastq) leaf_rows4_pipelined<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
+        else leaf_rows4_pipelined<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
+      } else {
+        if (tree) leaf_rows4<2>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid], sm.XV, tr);
+        else if (fastq) leaf_rows4<1>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
+        else leaf_rows4<0>(q, sm.leaf, g, fstep, width, part, lane, rowok, qrow, drow, dhi, dlo, w0, dsm, &sm.esd[tid]);
+      }
     } else if (has_next) {
       // ---- (3b) look-ahead: D[:, c0:a] R[c0:a, J+1] on the threads the leaf does not use -----------
+      // The R panels are requested TWO blocks ahead, by the helper threads, at the end of this phase (below):
+      // neither the request loop nor the wait sits on the chain.  Here: the panel of block a + 32, requested
+      // one iteration ago, must have landed (this thread's pieces, then every helper's).
+      cp_async_wait<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(SM::HELP) : "memory");   // a barrier of the helper threads only
       const int h = tid - SM::NLEAF;
       const int gh = SM::SPT == 1 ? h / SM::NSLOT : 0;
       if (gh < SM::KGH) {
@@ -875,8 +1025,17 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
           for (int j = 0; j < 4; ++j) sm.red2[gh][hr][hs * 4 + j] = la[j];
         }
       }
+      // panel requests for later blocks.  Block a + 64's panel goes where block a's was: its rows k < a + 32 - c0
+      // into the look-ahead buffer this phase has just finished reading (hence the helpers' barrier), its last
+      // 32 rows into the tail buffer the tail product of this iteration read long ago.  The first iteration also
+      // requests block c0 + 32's panel (32 rows, tail buffer only) and waits for it, because the next iteration's
+      // tail product -- all threads, before any helper wait -- reads it.
+      asm volatile("bar.sync 1, %0;" ::"n"(SM::HELP) : "memory");
+      if (a == c0) prefetch_panel(a + 32, buf ^ 1);
+      if (a + 64 < c1) prefetch_panel(a + 64, buf);
+      if (a == c0) { if (a + 64 < c1) cp_async_wait<1>(); else cp_async_wait<0>(); }
     }
-    if (tr) tr[4] = clock64();
+    if (tr) { tr[4] = clock64(); tr[11] = tr[4] - tr[11]; }   // tr[11]: the leaf call alone (thread 0)
     cur = nxt;
     if (tr) tr[5] = clock64();
     // the barrier at the top of the next iteration orders Dm / Qs / leaf / red2 reuse
@@ -1002,11 +1161,11 @@ __global__ void __launch_bounds__(256, 4) push_simt_kernel(const float* __restri
   }
 }
 
-template <int R, bool COMPACT>
+template <int R, bool COMPACT, bool PIPE>
 static int launch_macro_v(float* q, float* d, int64_t r, int64_t n, const float* r32, const float* ud, const DevGrid<float>& g,
                           cudaStream_t st, int64_t c0, int64_t c1, const float* pacc, float* dhi, float* dlo,
                           const GridBreaks& xv, float* esum) {
-  auto kern = sweep_macro_kernel<R, COMPACT>;
+  auto kern = sweep_macro_kernel<R, COMPACT, PIPE>;
   SLK_SMEM_ATTR_ONCE(kern, (int)sizeof(MacroSmem<R, COMPACT>));
   kern<<<(unsigned)ceil_div(r, R), FT, sizeof(MacroSmem<R, COMPACT>), st>>>(q, d, r, n, r32, ud, g, c0, c1, pacc, dhi, dlo,
                                                                            xv, esum);
@@ -1023,8 +1182,17 @@ static int launch_macro(float* q, float* d, int64_t r, int64_t n, const float* r
     const char* ev = getenv("SLK_SWEEP_COMPACT");
     compact = (ev && ev[0] == '0') ? 0 : 1;   // default on: one more CTA per SM (measured)
   }
-  if (compact) return launch_macro_v<R, true>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
-  return launch_macro_v<R, false>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
+  static int pipe = -1;      // SLK_LEAF_PIPE=0: the phase-by-phase leaf (leaf_rows4) instead of the branch-free pipelined one
+  if (pipe < 0) {
+    const char* ev = getenv("SLK_LEAF_PIPE");
+    pipe = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  if (pipe) {
+    if (compact) return launch_macro_v<R, true, true>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
+    return launch_macro_v<R, false, true>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
+  }
+  if (compact) return launch_macro_v<R, true, false>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
+  return launch_macro_v<R, false, false>(q, d, r, n, r32, ud, g, st, c0, c1, pacc, dhi, dlo, xv, esum);
 }
 
 // R form of the sweep: r32 = Cholesky factor R (upper, H_opt = R R^T), rt32 = its transpose, ud32 =

@@ -16,14 +16,15 @@ sc = ops.scale_search(Wd, cb, torch.linspace(0.05, 1, 100, device="cuda"), Hd.di
 Ws = ops.scale_rows(Wd, sc, 0)
 for _ in range(2):
     ops.gptq_sweep_r(Ws.clone(), r32, rt32, ud32, cb)
-buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+buf = torch.zeros(128, dtype=torch.int64, device="cuda")
 _lib.call("slk_debug_sweep_trace", ctypes.c_void_p(buf.data_ptr()))
 ops.gptq_sweep_r(Ws.clone(), r32, rt32, ud32, cb)
 torch.cuda.synchronize()
 _lib.call("slk_debug_sweep_trace", None)
-t = buf.cpu().numpy().reshape(8, 8)
+t = buf.cpu().numpy().reshape(8, 16)
 print("last macro block, CTA 0: per 32-column block clocks  wait | product+reduce | Ud multiply | leaf | copy")
 for b in range(8):
     x = t[b]
     print(b, x[1] - x[0], x[2] - x[1], x[3] - x[2], x[4] - x[3], x[5] - x[4], " total", (t[b + 1][0] - x[0]) if b < 7 else "",
-          " leaf: owner walks", x[6], "shuffle+update", x[7])
+          " leaf: owner walks", x[6], "shuffle+update", x[7], "| phase 0: chain", x[8], "+stores", x[9], "shuffles", x[10],
+          "leaf call", x[11])

@@ -61,7 +61,7 @@ def main():
         if "--sweeptrace" in sys.argv:
             import ctypes
             from sleekit_b200 import _lib
-            strace = torch.zeros((128, 8), dtype=torch.int64, device=dev)
+            strace = torch.zeros((128, 16), dtype=torch.int64, device=dev)
             _lib.call("slk_debug_sweep_trace", ctypes.c_void_p(strace.data_ptr()))
         if per_op:
             ops.TRACE = {"buf": torch.zeros(8192, dtype=torch.int64, device=dev), "names": [], "tag": None}
