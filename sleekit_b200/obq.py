@@ -263,7 +263,10 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
     want_err: also return (mean layer error [1], row errors [r]) = quantization_error / channelwise_error
     (obq.py:89-103) of the returned weights against Wd under Hd, taken from the sweep's residuals
     (sum E^2 - damp * sum (W-Q)^2, ops.sweep_error) when the factor-form sweep ran and no local-search
-    move follows, from the K6 product otherwise.  factor_fn(Hd, order, dampval) -> (r32, rt32, ud32,
+    move follows, from the K6 product otherwise.  (The residual form subtracts two fp32 row sums: when
+    delta H delta is smaller than ~1e-6 of damp * |delta|^2 -- a Hessian of much lower rank than n under a large
+    damp -- it cancels; call channelwise_error for such inputs.  Measured agreement with the product on the
+    rank-deficient bench layers: 1.4e-5.)  factor_fn(Hd, order, dampval) -> (r32, rt32, ud32,
     info): an alternative producer of the Cholesky factor (the multi-GPU factorisation)."""
     st = gptq_prepare(Wd, Hd, quantizer, act_order, damp, nb_ls_moves, min_block_size, num_blocks,
                       colsum_reduce, row_scale, want_err)
@@ -300,7 +303,11 @@ def compute_gain(W, Q, H, candidates):
 class LocalSearchQuantizer:
     """Best-first single-weight flips (obq.py:234-346).  State lives on the device; the
     attributes the reference exposes (err, Q_up, Q_down, gain_up, gain_down) are derived from
-    the current Q on access.  ``quantize_local_search`` runs all moves in one kernel launch."""
+    the current Q on access.  ``quantize_local_search`` runs all moves in one kernel launch.
+
+    Contract of the device path (narrower than the reference outside the tested inputs): Q must lie on the
+    codebook (the kernel keeps codes, so an off-grid entry is snapped to its nearest codeword), and H is
+    used as its own transpose (a Hessian: symmetric) when (Q - W) H is formed."""
 
     def __init__(self, W, Q, H, quantizer):
         assert W.ndim == 2
