@@ -460,6 +460,7 @@ class ShardedLayerQuantizer:
                      if (self.world > 1 and os.environ.get("SLK_PEER_ALLREDUCE", "1") != "0") else None)
         self._token = torch.zeros(1, dtype=torch.float32, device=ops.device())
         self.phases_ms = {}
+        self.info = None
 
     def _barrier(self):
         import torch.distributed as tdist
@@ -518,6 +519,7 @@ class ShardedLayerQuantizer:
         fac = None
         if st.chol_form:
             fac = self._factor_fn(Hq, st.order, st.dampval) if self.dist_factor else ops.chol_factor(Hq, st.order, st.dampval)
+            self.info = fac[3]        # device int32 [1]: 0, or the first non-positive pivot (max over the ranks); obq.py:49-50
         mark("factor")
         q, (_, rows_err) = obq.gptq_finish(st, fac)
         mark("sweep")

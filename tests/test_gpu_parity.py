@@ -1057,3 +1057,25 @@ def test_upload_cache_reuses_and_invalidates(slk):
     e4 = slk.obq.quantization_error(W2, q, H2)
     np.testing.assert_allclose(e4, orc.mean_error(W2, q, H2), rtol=1e-4)
     cv.cache_clear()
+
+
+def test_layer_on_a_second_device(slk):
+    """kernel attributes and SM counts are per device, and ops launch on the device (and stream)
+    of their tensors -- a layer that lives on cuda:1 while cuda:0 is the current device gives the same bits."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r, n = 768, 1024                                       # macro sweep (> 48 KB of shared memory), batched-size factor
+    W, H, _ = wl.synthetic_layer(r, n, 33, samples=1024)
+    cb = slk.codebook.UniformCodebook(8, -1, 1)
+    outs = []
+    torch.cuda.set_device(0)
+    for dev in ("cuda:0", "cuda:1"):
+        Wd, Hd = torch.from_numpy(W).to(dev), torch.from_numpy(H).to(dev)
+        sc = slk.scaling.compute_min_mse_scaling(Wd, cb, 0, H=Hd.diagonal().contiguous())
+        q = slk.scaling.quantize_with_scaling(Wd, sc, cb, H=Hd, nb_ls_moves=3)
+        e = slk.obq.quantization_error(Wd, q, Hd)
+        assert q.device == Wd.device and sc.device == Wd.device
+        outs.append((sc.cpu(), q.cpu(), float(e)))
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
