@@ -25,6 +25,7 @@ def issue_order(shapes, order="big"):
     pinned host buffers too (OPT-125M set: 19.4 ms against 19.8 / 20.2 ms for the other two);
     "interleaved": the same sorted list dealt out as one long-chain layer followed by its share of the
     short ones, so that host->device copies deliver work for all SMs from the start;
+    "small": shortest chains first (their inputs are small: work reaches the GPU at once);
     "model": as given."""
     L = len(shapes)
     if order == "model":
@@ -32,6 +33,8 @@ def issue_order(shapes, order="big"):
     by_size = sorted(range(L), key=lambda k: (-shapes[k][1], -shapes[k][0], k))
     if order == "big":
         return by_size
+    if order == "small":
+        return by_size[::-1]
     if order != "interleaved":
         raise ValueError(f"unknown issue order {order!r}")
     nmin = min(sh[1] for sh in shapes)
@@ -64,6 +67,7 @@ class LayerSetQuantizer:
         env = os.environ.get("SLK_BATCH_K2")
         self.batch_k2 = (int(streams) > 1 if batch_k2 is None else bool(batch_k2)) if env is None else env != "0"
         self.k2_group = int(os.environ.get("SLK_K2_GROUP") or k2_group or 64)
+        self.k2_single_from = 1 << 30      # layers at least this wide are factored one launch each (HostPlan "small" mode)
         # the factor launches and the layers with the longest chains run on high-priority streams: their
         # CTAs are scheduled ahead of the short layers' whenever both are ready (SLK_PRIORITY=0: off)
         real = os.environ.get("SLK_REAL_STREAMS", "1") != "0"
@@ -201,7 +205,8 @@ class LayerSetQuantizer:
         # groups of equal n in issue order
         groups, cur = [], []
         for i in issue:
-            if cur and (Ws[cur[0]].shape[1] != Ws[i].shape[1] or len(cur) >= self.k2_group):
+            limit = 1 if int(Ws[i].shape[1]) >= self.k2_single_from else self.k2_group
+            if cur and (Ws[cur[0]].shape[1] != Ws[i].shape[1] or len(cur) >= limit):
                 groups.append(cur)
                 cur = []
             cur.append(i)
@@ -340,7 +345,9 @@ class HostPlan:
         # the plan's layers arrive one after the other over PCIe: per-layer factorisations start as soon as
         # a layer's Hessian has landed, a batched launch only after the last one of its group
         # (measured: 19.7 ms per OPT-125M pass per layer, 27 ms batched); SLK_PLAN_BATCH_K2=1 batches anyway
-        self.batch_k2 = os.environ.get("SLK_PLAN_BATCH_K2", "0") != "0"
+        mode = os.environ.get("SLK_PLAN_BATCH_K2", "0")
+        self.batch_k2 = mode != "0"
+        self.batch_small_only = mode == "small"   # batch the narrow layers in groups of 12, factor the wide ones per layer
         lib = _lib.load()
         self.h2d_bytes = sum(4 * r * n + (int(lib.slk_upload_symmetric_bytes(n, ops.symmetric_block_rows(n)))
                                           if self.symmetric_h else 4 * n * n) for r, n in self.shapes)
@@ -384,12 +391,14 @@ class HostPlan:
 
     def _pass(self, in_capture):
         self._copy_joined = False
-        saved = self.lsq.batch_k2
+        saved = (self.lsq.batch_k2, self.lsq.k2_single_from, self.lsq.k2_group)
         self.lsq.batch_k2 = self.batch_k2
+        if self.batch_small_only:
+            self.lsq.k2_single_from, self.lsq.k2_group = 2048, 12
         try:
             self._pass_inner(in_capture)
         finally:
-            self.lsq.batch_k2 = saved
+            self.lsq.batch_k2, self.lsq.k2_single_from, self.lsq.k2_group = saved
 
     def _pass_inner(self, in_capture):
         self.lsq.infos = self._infod
