@@ -386,15 +386,6 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
     const int64_t tile_off = (int64_t)i * CT * ld + (int64_t)j * CT;
     double* Cij = A + tile_off;
 
-    // the tile itself, in accumulator-fragment layout (rows wm+8ii+fr, columns wn+8jj+2fk, +1)
-    double2 cij[4][2];
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
-        cij[ii][jj] = *reinterpret_cast<const double2*>(Cij + (int64_t)row * ld + col);
-      }
     double acc[4][2][2];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
@@ -448,6 +439,17 @@ __global__ void __launch_bounds__(CTH, 2) chol_dag_kernel(const __grid_constant_
           for (int jj = 0; jj < 2; ++jj) cd_dmma(acc[ii][jj], a[ii], b[jj]);
       }
     }
+    // the tile itself, in accumulator-fragment layout (rows wm+8ii+fr, columns wn+8jj+2fk, +1): loaded AFTER the
+    // k loop (nobody else writes A(i,j) before this task publishes it), so that its 32 registers are free for
+    // the loop's operand prefetch; the load latency overlaps the ring's last wait and the barrier
+    double2 cij[4][2];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int row = wm + 8 * ii + fr, col = wn + 8 * jj + 2 * fk;
+        cij[ii][jj] = *reinterpret_cast<const double2*>(Cij + (int64_t)row * ld + col);
+      }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();   // the ring is dead: its storage becomes M / X / T
     if (tr) tr[5] = clock64();
