@@ -904,6 +904,49 @@ def run_ours(args):
             sharded = {"error": repr(ex)[:300]}
 
     xtx_big = xtx_measure(dev, [(8192, 4096)], reps=3) if args.config == "c2" else None
+    # K1 over the whole layer set at once: the calibration products of independent layers as parallel branches of
+    # one CUDA graph (what a calibration pass over a model does), instead of one launch after the other
+    xtx_set = None
+    if args.config == "c2" and not args.layers and not args.only:
+        try:
+            xs = [torch.from_numpy(wl.synthetic_calibration(n, i + 1000 * rank, SAMPLES)).to(dev) for i, (r, n) in enumerate(shapes)]
+            hs = [torch.zeros((n, n), dtype=torch.float32, device=dev) for r, n in shapes]
+            ms_ = [torch.zeros(n, dtype=torch.float32, device=dev) for r, n in shapes]
+            sts = lsq.streams
+
+            def xtx_pass():
+                main = torch.cuda.current_stream()
+                ev0 = torch.cuda.Event()
+                ev0.record(main)
+                for i in range(L):
+                    st_ = sts[i % len(sts)]
+                    st_.wait_event(ev0)
+                    with torch.cuda.stream(st_):
+                        ops.hessian_accum(xs[i], hs[i], ms_[i], 0.0, SAMPLES)
+                for st_ in sts[: min(L, len(sts))]:
+                    ev1 = torch.cuda.Event()
+                    ev1.record(st_)
+                    main.wait_event(ev1)
+
+            xtx_pass()
+            torch.cuda.synchronize()
+            gx = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gx):
+                xtx_pass()
+            gx.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                gx.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            set_ms = e0.elapsed_time(e1) / 3
+            xtx_set = {"ms": set_ms, "tflops": xtx_flop / (set_ms * 1e-3) / 1e12,
+                       "note": f"the {L} products as parallel branches of one CUDA graph (one replay = the whole set)"}
+            del xs, hs, ms_, gx
+        except Exception as ex:
+            xtx_set = {"error": repr(ex)[:200]}
 
     if rank != 0:
         return
@@ -976,7 +1019,7 @@ def run_ours(args):
         "xtx": {"tflops": xtx_flop / (xtx_ms * 1e-3) / 1e12 if xtx_ms else None, "ms_total": xtx_ms,
                 "note": (f"K1 X^T X over the {L} calibration matrices (S={SAMPLES}), one launch each, algorithmic 2*S*n^2 flop; "
                          "tcgen05 3xTF32, upper tiles only, incl. the hi/lo split+transpose pass"),
-                "s8192_n4096": xtx_big[0] if xtx_big else None},
+                "s8192_n4096": xtx_big[0] if xtx_big else None, "layer_set_concurrent": xtx_set},
         "sharded_c5": sharded, "peaks": peaks,
         "wall_ms_per_step": wall / args.steps,
     }
