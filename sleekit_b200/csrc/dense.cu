@@ -6,6 +6,15 @@
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 
+#include <cuda_bf16.h>
+
+// slk_set_option("fullh_topk", 0 | 4 | 8 | 16): candidates per row of the screened full-H search (0: every grid
+// point is evaluated exactly); ("fullh_bn", 128 | 256): tile width of the screening product
+// ("fullh_bf16", 0 | 1): screening product on TF32 (one kind::tf32 pass) or BF16 (kind::f16) operands
+int64_t g_opt_fullh_topk = 8;
+int64_t g_opt_fullh_bn = 256;
+int64_t g_opt_fullh_bf16 = 1;
+
 namespace slk {
 
 // out[m] = sum over column tiles of part[m, t], fixed order -> deterministic
@@ -70,30 +79,86 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 
 // ---- full-H scale search pieces --------------------------------------------
 // resid[(g - g0) * r + row, j] = descale(quant(w / (f_g * init))) - w   (scaling.py:128-130 -> 73-80)
-template <typename TE>
-__global__ void __launch_bounds__(256) grid_resid_kernel(const float* __restrict__ w, int64_t r, int64_t n,
+// cand != nullptr: slot gi of a row evaluates grid point cand[gi * r + row] instead of g0 + gi (< 0: empty slot,
+// zeros).  SCREEN: resid receives the residual rounded to the nearest TF32 value (operand of the one-pass product).
+// One CTA per (grid point, row) pair at a time: scale and reciprocal once per pair, float4 traffic when the row
+// pitch allows it (the pass is then bound by its stores, not by index arithmetic).
+// SCREEN: 0 exact residuals (+ TF32 parts), 1 residuals rounded to TF32, 2 residuals rounded to bf16 (resid then
+// points to a bf16 matrix of the same shape)
+template <int SCREEN>
+__device__ __forceinline__ float grid_resid_value(const DevGrid<float>& g, float x, float scale, float rs, bool live) {
+  float e = 0.0f;
+  if (live) {
+    const float v = grid_value(g, __fdiv_rn(x, scale));
+    e = __fsub_rn(__fdiv_rn(v, rs), x);
+  }
+  return SCREEN == 1 ? __uint_as_float((__float_as_uint(e) + 0x1000u) & 0xffffe000u) : e;
+}
+
+template <typename TE, int SCREEN = 0>
+__global__ void __launch_bounds__(128) grid_resid_kernel(const float* __restrict__ w, int64_t r, int64_t n,
                                                          DevGrid<float> g, const float* __restrict__ factors,
                                                          int g0, int gcount, const float* __restrict__ init,
                                                          TE* __restrict__ resid, float* __restrict__ rhi = nullptr,
-                                                         float* __restrict__ rlo = nullptr) {
-  const int64_t total = (int64_t)gcount * r * n;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int64_t j = i % n;
-    int64_t row = (i / n) % r;
-    int gi = (int)(i / (n * r));
-    float scale = __fmul_rn(__ldg(factors + g0 + gi), __ldg(init + row));
-    float rs = __fdiv_rn(1.0f, scale);
-    float x = __ldg(w + row * n + j);
-    float v = grid_value(g, __fdiv_rn(x, scale));
-    float dq = __fdiv_rn(v, rs);
-    const float e = __fsub_rn(dq, x);
-    resid[i] = (TE)e;
-    if (rhi) {                                   // TF32 parts for the tensor-core product
-      float hh, ll;
-      split_tf32(e, hh, ll);
-      rhi[i] = hh;
-      rlo[i] = ll;
+                                                         float* __restrict__ rlo = nullptr,
+                                                         const int* __restrict__ cand = nullptr) {
+  const int64_t pairs = (int64_t)gcount * r;
+  const bool vec = sizeof(TE) == 4 && (n & 3) == 0 && (((uintptr_t)w | (uintptr_t)resid | (uintptr_t)rhi | (uintptr_t)rlo) & 15) == 0;
+  for (int64_t pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+    const int gi = (int)(pr / r);
+    const int64_t row = pr - (int64_t)gi * r;
+    const int gp = cand ? __ldg(cand + pr) : g0 + gi;
+    const bool live = gp >= 0;
+    float scale = 1.0f, rs = 1.0f;
+    if (live) {
+      scale = __fmul_rn(__ldg(factors + gp), __ldg(init + row));
+      rs = __fdiv_rn(1.0f, scale);
+    }
+    const float* wr = w + row * n;
+    TE* out = resid + pr * n;
+    if (vec) {
+      const float4* w4 = reinterpret_cast<const float4*>(wr);
+      for (int64_t j = threadIdx.x; j < (n >> 2); j += blockDim.x) {
+        const float4 x = __ldg(w4 + j);
+        float4 e;
+        e.x = grid_resid_value<SCREEN>(g, x.x, scale, rs, live);
+        e.y = grid_resid_value<SCREEN>(g, x.y, scale, rs, live);
+        e.z = grid_resid_value<SCREEN>(g, x.z, scale, rs, live);
+        e.w = grid_resid_value<SCREEN>(g, x.w, scale, rs, live);
+        if (SCREEN == 2) {
+          __nv_bfloat162 lo2 = __floats2bfloat162_rn(e.x, e.y), hi2 = __floats2bfloat162_rn(e.z, e.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+          reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(resid) + pr * n)[j] = pk;
+          continue;
+        }
+        reinterpret_cast<float4*>(out)[j] = e;
+        if (!SCREEN && rhi) {                    // TF32 parts for the tensor-core product
+          float4 hh, ll;
+          split_tf32(e.x, hh.x, ll.x);
+          split_tf32(e.y, hh.y, ll.y);
+          split_tf32(e.z, hh.z, ll.z);
+          split_tf32(e.w, hh.w, ll.w);
+          reinterpret_cast<float4*>(rhi + pr * n)[j] = hh;
+          reinterpret_cast<float4*>(rlo + pr * n)[j] = ll;
+        }
+      }
+    } else {
+      for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const float e = grid_resid_value<SCREEN>(g, __ldg(wr + j), scale, rs, live);
+        if (SCREEN == 2) {
+          reinterpret_cast<__nv_bfloat16*>(resid)[pr * n + j] = __float2bfloat16_rn(e);
+          continue;
+        }
+        out[j] = (TE)e;
+        if (!SCREEN && rhi) {
+          float hh, ll;
+          split_tf32(e, hh, ll);
+          rhi[pr * n + j] = hh;
+          rlo[pr * n + j] = ll;
+        }
+      }
     }
   }
 }
@@ -119,6 +184,72 @@ __global__ void __launch_bounds__(256) fill_inf_kernel(float* a, float* b, int64
   if (i < n) { a[i] = __int_as_float(0x7f800000); b[i] = __int_as_float(0x7f800000); }
 }
 
+// ---- screened full-H search ---------------------------------------------------------------------------------
+// The reference evaluates e_g H e_g^T for every grid point g and keeps the first minimum (scaling.py:125-134).
+// Only the arg-min matters, so all G points are first ranked by a single kind::tf32 pass (~1e-3 relative, the
+// error largely common to the grid points of a row: same H, same weights), and only the TOPK best-ranked points
+// of each row are evaluated by the fp32-faithful 3xTF32 product -- the same kernel and the same per-row
+// arithmetic as the unscreened path, so the chosen scale and its error are bit-identical whenever the true
+// minimum is among the TOPK candidates (neighbouring grid points differ by 1e-3..1e-2 relative around the
+// minimum; TOPK = 8 of 100 leaves a wide margin, test_fullh_screening_*).
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ x, int64_t total, __nv_bfloat16* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) y[i] = __float2bfloat16_rn(x[i]);
+}
+
+template <int TOPK>
+__global__ void __launch_bounds__(128) screen_topk_kernel(const float* __restrict__ err, int64_t r, int G,
+                                                          int* __restrict__ cand) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  float be[TOPK];
+  int bg[TOPK];
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) { be[j] = __int_as_float(0x7f800000); bg[j] = -1; }
+  for (int gi = 0; gi < G; ++gi) {
+    const float e = err[(int64_t)gi * r + row];
+    if (e < be[TOPK - 1]) {   // strict: on ties the lower grid index stays; inf / NaN never enter (as in grid_argmin_kernel)
+      be[TOPK - 1] = e; bg[TOPK - 1] = gi;
+#pragma unroll
+      for (int j = TOPK - 1; j > 0; --j) {
+        const bool sw = be[j] < be[j - 1];
+        const float te = sw ? be[j - 1] : be[j];
+        const int tg = sw ? bg[j - 1] : bg[j];
+        be[j - 1] = sw ? be[j] : be[j - 1];
+        bg[j - 1] = sw ? bg[j] : bg[j - 1];
+        be[j] = te; bg[j] = tg;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) cand[(int64_t)j * r + row] = bg[j];
+}
+
+// first minimum in grid order over the evaluated candidates (strict '<'; equal errors: the lower grid index)
+__global__ void __launch_bounds__(256) cand_argmin_kernel(const float* __restrict__ err, const int* __restrict__ cand,
+                                                          int64_t r, int slots, const float* __restrict__ factors,
+                                                          float* __restrict__ best_err, float* __restrict__ best_f,
+                                                          int* __restrict__ best_g) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  float be = best_err[row];
+  int bg = best_g[row];
+  for (int s = 0; s < slots; ++s) {
+    const int gp = cand[(int64_t)s * r + row];
+    if (gp < 0) continue;
+    const float e = err[(int64_t)s * r + row];
+    if (e < be || (e == be && bg >= 0 && gp < bg)) { be = e; bg = gp; }
+  }
+  best_err[row] = be;
+  best_g[row] = bg;
+  if (bg >= 0) best_f[row] = __ldg(factors + bg);
+}
+
+__global__ void __launch_bounds__(256) fill_int_kernel(int* a, int v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
 __global__ void __launch_bounds__(256) finish_scale_kernel(const float* __restrict__ init, const float* __restrict__ best_f,
                                                            const float* __restrict__ best_err, int64_t r,
                                                            float* __restrict__ out_scale, float* __restrict__ out_err) {
@@ -129,6 +260,8 @@ __global__ void __launch_bounds__(256) finish_scale_kernel(const float* __restri
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+constexpr int FULLH_TOPK_MAX = 16;
 
 // how many grid points are evaluated per GEMM launch
 static inline int fullh_chunk(int64_t r, int64_t n, int G, size_t elem) {
@@ -218,8 +351,12 @@ size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t 
   bytes += align256((size_t)chunk * r * tiles * elem);   // row-dot partials
   bytes += align256((size_t)chunk * r * elem);           // errors
   bytes += 3 * align256((size_t)r * sizeof(float));      // init, best_err, best_f
-  if (h_dtype == 1 && n % 4 == 0)                        // tensor-core path: TF32 parts of the residuals and of H
+  if (h_dtype == 1 && n % 4 == 0) {                      // tensor-core path: TF32 parts of the residuals and of H
     bytes += 2 * align256((size_t)chunk * r * n * 4) + 2 * align256((size_t)n * n * 4);
+    // screening: errors of all grid points, candidate lists, best index, row-dot partials of 2 * chunk points
+    bytes += align256((size_t)G * r * 4) + align256((size_t)FULLH_TOPK_MAX * r * 4) + align256((size_t)r * 4) +
+             align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4) + align256((size_t)n * n * 2);
+  }
   return bytes;
 }
 
@@ -249,9 +386,21 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
     rhi = (float*)base; base += align256((size_t)chunk * r * n * 4);
     rlo = (float*)base; base += align256((size_t)chunk * r * n * 4);
     hhi = (float*)base; base += align256((size_t)n * n * 4);
-    hlo = (float*)base;
+    hlo = (float*)base; base += align256((size_t)n * n * 4);
     rc = tc_split_f32((const float*)h, n, n, n, n, hhi, hlo, st);
     if (rc) return rc;
+  }
+  const int topk = tc ? (int)g_opt_fullh_topk : 0;
+  const bool screen = tc && (topk == 4 || topk == 8 || topk == 16) && G >= 4 * topk;
+  float *errs_all = nullptr, *part_s = nullptr;
+  int *cand = nullptr, *best_g = nullptr;
+  __nv_bfloat16* hbf = nullptr;
+  if (screen) {
+    errs_all = (float*)base; base += align256((size_t)G * r * 4);
+    cand = (int*)base; base += align256((size_t)FULLH_TOPK_MAX * r * 4);
+    best_g = (int*)base; base += align256((size_t)r * 4);
+    part_s = (float*)base; base += align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4);
+    hbf = (__nv_bfloat16*)base;
   }
 
   rc = slk_row_noclip_scale_f32(w, r, n, cb->lo, cb->hi, init, stream);
@@ -259,12 +408,68 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
   fill_inf_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(best_err, best_f, r);
   SLK_LAUNCH_CHECK();
   DevGrid<float> g = make_grid<float>(cb);
-  for (int g0 = 0; g0 < G; g0 += chunk) {
+  auto resid_blocks = [](int64_t pairs) {           // one CTA per (grid point, row) pair, grid-stride beyond 64 per SM
+    const int64_t cap = (int64_t)sm_count() * 64;
+    return (int)(pairs < cap ? pairs : cap);
+  };
+  if (screen) {
+    // 1. rank all grid points with one TF32 pass: TF32-rounded residuals (one array over the rhi | rlo region,
+    //    2 * chunk grid points at a time) against the truncated H
+    const int bn = g_opt_fullh_bn == 128 ? 128 : 256;
+    const bool bf16 = g_opt_fullh_bf16 != 0 && n % 8 == 0;
+    const int64_t tiles_s = ceil_div(n, bn);
+    const int chunk_s = 2 * chunk < G ? 2 * chunk : G;
+    if (bf16) {
+      to_bf16_kernel<<<resid_blocks(ceil_div(n * n, 256)), 256, 0, st>>>((const float*)h, n * n, hbf);
+      SLK_LAUNCH_CHECK();
+    }
+    for (int g0 = 0; g0 < G; g0 += chunk_s) {
+      const int gc = (G - g0) < chunk_s ? (G - g0) : chunk_s;
+      const int64_t rows = (int64_t)gc * r;
+      if (bf16) grid_resid_kernel<float, 2><<<resid_blocks(rows), 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, rhi);
+      else grid_resid_kernel<float, 1><<<resid_blocks(rows), 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, rhi);
+      SLK_LAUNCH_CHECK();
+      TcParams tp;
+      tp.C = part_s; tp.ldc = tiles_s; tp.R = rhi; tp.R2 = nullptr; tp.ldr = n;
+      tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+      rc = bf16 ? tc_gemm_screen_bf16(rhi, n, hbf, n, tp, bn, st) : tc_gemm_screen_f32(rhi, n, hhi, n, tp, bn, st);
+      if (rc) return rc;
+      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>(part_s, rows, tiles_s, errs_all + (int64_t)g0 * r);
+      SLK_LAUNCH_CHECK();
+    }
+    if (topk == 4) screen_topk_kernel<4><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
+    else if (topk == 8) screen_topk_kernel<8><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
+    else screen_topk_kernel<16><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
+    SLK_LAUNCH_CHECK();
+    fill_int_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(best_g, -1, r);
+    SLK_LAUNCH_CHECK();
+    // 2. the candidates, exactly as the unscreened path evaluates a grid point
+    for (int s0 = 0; s0 < topk; s0 += chunk) {
+      const int sc = (topk - s0) < chunk ? (topk - s0) : chunk;
+      const int64_t rows = (int64_t)sc * r;
+      const int* cs = cand + (int64_t)s0 * r;
+      grid_resid_kernel<float><<<resid_blocks(rows), 128, 0, st>>>(w, r, n, g, factors, 0, sc, init, (float*)resid,
+                                                                      rhi, rlo, cs);
+      SLK_LAUNCH_CHECK();
+      TcParams tp;
+      tp.C = (float*)part; tp.ldc = ceil_div(n, TC_TILE_N); tp.R = (const float*)resid; tp.R2 = nullptr; tp.ldr = n;
+      tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+      rc = tc_gemm_presplit_f32(TC_ROWDOT, rhi, rlo, n, hhi, hlo, n, tp, st);
+      if (rc) return rc;
+      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const float*)part, rows, ceil_div(n, TC_TILE_N),
+                                                                           (float*)errs);
+      SLK_LAUNCH_CHECK();
+      cand_argmin_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, cs, r, sc, factors, best_err, best_f,
+                                                                best_g);
+      SLK_LAUNCH_CHECK();
+    }
+  }
+  for (int g0 = 0; g0 < G && !screen; g0 += chunk) {
     const int gc = (G - g0) < chunk ? (G - g0) : chunk;
     const int64_t rows = (int64_t)gc * r;
-    int blocks = (int)(ceil_div(rows * n, 256) < (int64_t)sm_count() * 16 ? ceil_div(rows * n, 256) : (int64_t)sm_count() * 16);
+    const int blocks = resid_blocks(rows);
     if (h_dtype == 1) {
-      grid_resid_kernel<float><<<blocks, 256, 0, st>>>(w, r, n, g, factors, g0, gc, init, (float*)resid, rhi, rlo);
+      grid_resid_kernel<float><<<blocks, 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, (float*)resid, rhi, rlo);
       SLK_LAUNCH_CHECK();
       if (tc) {
         // (E H) . E per row on tcgen05: H symmetric, hence its own K-major B operand; row dot in the epilogue
@@ -282,7 +487,7 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
       SLK_LAUNCH_CHECK();
       grid_argmin_kernel<float><<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, r, g0, gc, factors, best_err, best_f);
     } else {
-      grid_resid_kernel<double><<<blocks, 256, 0, st>>>(w, r, n, g, factors, g0, gc, init, (double*)resid);
+      grid_resid_kernel<double><<<blocks, 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, (double*)resid);
       SLK_LAUNCH_CHECK();
       GemmParams<double> p = gemm_params<double>((const double*)resid, n, (const double*)h, n, (double*)part, 0, rows, n, n);
       rc = gemm_launch<double, false, false, EPI_ROWDOT>(p, 1, st);

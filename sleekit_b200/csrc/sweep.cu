@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 static int64_t g_opt_sweep_ctas = 0;     // slk_set_option("sweep_ctas", v)
+extern int64_t g_opt_fullh_topk, g_opt_fullh_bn, g_opt_fullh_bf16;   // dense.cu
 
 namespace slk {
 
@@ -1075,6 +1076,17 @@ sweep_macro_kernel(float* __restrict__ Q, float* __restrict__ D, int64_t r, int6
 extern "C" int slk_set_option(const char* name, int64_t value) {
   SLK_REQUIRE(name, "NULL option name");
   if (strcmp(name, "sweep_ctas") == 0) { g_opt_sweep_ctas = value > 0 ? value : 0; return SLK_OK; }
+  if (strcmp(name, "fullh_topk") == 0) {
+    SLK_REQUIRE(value == 0 || value == 4 || value == 8 || value == 16, "fullh_topk must be 0, 4, 8 or 16");
+    g_opt_fullh_topk = value;
+    return SLK_OK;
+  }
+  if (strcmp(name, "fullh_bf16") == 0) { g_opt_fullh_bf16 = value != 0; return SLK_OK; }
+  if (strcmp(name, "fullh_bn") == 0) {
+    SLK_REQUIRE(value == 128 || value == 256, "fullh_bn must be 128 or 256");
+    g_opt_fullh_bn = value;
+    return SLK_OK;
+  }
   set_error("unknown option %s", name);
   return SLK_ERR_ARG;
 }

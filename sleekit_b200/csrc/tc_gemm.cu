@@ -21,6 +21,7 @@
 #include "tc_gemm.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace slk {
@@ -79,6 +80,15 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -110,11 +120,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int STAGES>
+// kind::f16 with BF16 operands, fp32 accumulation: a 128-byte swizzle row holds 64 elements, one instruction 16
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES, int PASSES = 3>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  // PASSES == 3: {A_hi, A_lo, B_hi, B_lo} per stage; PASSES == 1 (screening pass): {A, B}
+  static constexpr int B_OFF = PASSES == 3 ? 2 * A_BYTES : A_BYTES;
+  static constexpr int STAGE_BYTES = PASSES == 3 ? 2 * A_BYTES + 2 * B_BYTES : A_BYTES + B_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -131,12 +148,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int STAGES, int EPI>
+// PASSES == 1: a single kind::tf32 product of the operands as given (the caller rounds them to TF32), accumulated
+// over the whole K range in one TMEM tile -- ~1e-3 relative, a third of the tensor time and half of the operand
+// traffic: the screening pass of the full-H scale search (dense.cu), never a result on its own.
+// BF16 (with PASSES == 1): the operands are bf16 matrices (TMA boxes of 64 elements = the same 128-byte rows),
+// the product is kind::f16 -- half the operand bytes and twice the tensor rate of the TF32 pass, ~4e-3 relative.
+template <int BN, int STAGES, int EPI, int PASSES = 3, bool BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcParams p) {
-  typedef TcSmem<BN, STAGES> SM;
-  static_assert(3 * BN <= 512, "two hi buffers and one lo tile must fit the 512 TMEM columns");
+  typedef TcSmem<BN, STAGES, PASSES> SM;
+  static_assert(PASSES == 1 || PASSES == 3, "one TF32 pass or the 3xTF32 split");
+  static_assert((PASSES == 3 ? 3 : 1) * BN <= 512, "two hi buffers and one lo tile must fit the 512 TMEM columns");
+  static_assert(PASSES == 3 || EPI == TC_ROWDOT, "the single-pass product only feeds the row-dot screening");
+  static_assert(!BF16 || PASSES == 1, "bf16 operands: screening pass only");
+  constexpr int BK = BF16 ? 2 * TC_BK : TC_BK;   // elements per 128-byte k-block
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024 B alignment
   uint64_t* bars = (uint64_t*)(tiles + STAGES * SM::STAGE_BYTES);
@@ -149,11 +175,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   if ((EPI == TC_HESS_SYM || EPI == TC_SYM_PART) && n0 + BN <= m0) return;   // strictly-lower tile of a symmetric product
-  const int num_kb_all = (int)((p.K + TC_BK - 1) / TC_BK);
+  const int num_kb_all = (int)((p.K + BK - 1) / BK);
   // split-K (TC_SYM_PART): this CTA covers k-blocks [kb0, kb0 + num_kb) and writes plane blockIdx.z
   const int kb0 = EPI == TC_SYM_PART ? (int)blockIdx.z * p.kb_per_split : 0;
   const int num_kb = EPI == TC_SYM_PART ? max(0, min(p.kb_per_split, num_kb_all - kb0)) : num_kb_all;
-  const int num_chunks = (num_kb + TC_KC - 1) / TC_KC;
+  const int num_chunks = PASSES == 1 ? (num_kb > 0 ? 1 : 0) : (num_kb + TC_KC - 1) / TC_KC;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
@@ -179,22 +205,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_wait(empty_bar + s, ph ^ 1u, p.error_flag);
         uint8_t* st = tiles + s * SM::STAGE_BYTES;
         mbar_expect_tx(full_bar + s, SM::STAGE_BYTES);
-        const int k0 = (kb0 + kb) * TC_BK;
+        const int k0 = (kb0 + kb) * BK;
         tma_load_2d(st, &map_a_hi, full_bar + s, k0, m0);
-        tma_load_2d(st + SM::A_BYTES, &map_a_lo, full_bar + s, k0, m0);
-        tma_load_2d(st + 2 * SM::A_BYTES, &map_b_hi, full_bar + s, k0, n0);
-        tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &map_b_lo, full_bar + s, k0, n0);
+        tma_load_2d(st + SM::B_OFF, &map_b_hi, full_bar + s, k0, n0);
+        if (PASSES == 3) {
+          tma_load_2d(st + SM::A_BYTES, &map_a_lo, full_bar + s, k0, m0);
+          tma_load_2d(st + SM::B_OFF + SM::B_BYTES, &map_b_lo, full_bar + s, k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- MMA issuer ------------------------------------------------------------------------
-      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+      constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(TC_BM, BN) : umma_idesc_tf32(TC_BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        const int chunk = kb / TC_KC, buf = chunk & 1;
-        if (kb % TC_KC == 0) {   // new chunk: its TMEM buffer must have been drained
+        const int chunk = PASSES == 1 ? 0 : kb / TC_KC, buf = chunk & 1;
+        const bool chunk_first = PASSES == 1 ? kb == 0 : kb % TC_KC == 0;
+        const bool chunk_last = PASSES == 1 ? kb == num_kb - 1 : (kb % TC_KC == TC_KC - 1 || kb == num_kb - 1);
+        if (chunk_first) {   // new chunk: its TMEM buffer must have been drained
           mbar_wait(hi_empty + buf, ((uint32_t)(chunk >> 1) & 1u) ^ 1u, p.error_flag);
           tc_fence_after();
         }
@@ -202,18 +232,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tc_fence_after();
         const uint32_t st = smem_u32(tiles + s * SM::STAGE_BYTES);
         const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + SM::A_BYTES);
-        const uint64_t b_hi = umma_desc_sw128(st + 2 * SM::A_BYTES);
-        const uint64_t b_lo = umma_desc_sw128(st + 2 * SM::A_BYTES + SM::B_BYTES);
+        const uint64_t b_hi = umma_desc_sw128(st + SM::B_OFF);
+        const uint64_t b_lo = umma_desc_sw128(st + SM::B_OFF + SM::B_BYTES);
         const uint32_t d_hi = tmem_base + (uint32_t)(buf * BN);
 #pragma unroll
         for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
           const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);   // +32 bytes along K inside the swizzle row
-          tc_mma_tf32(tmem_lo, a_lo + adv, b_hi + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-          tc_mma_tf32(tmem_lo, a_hi + adv, b_lo + adv, idesc, 1u);
-          tc_mma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, (kb % TC_KC == 0 && k == 0) ? 0u : 1u);
+          if (PASSES == 3) {
+            tc_mma_tf32(tmem_lo, a_lo + adv, b_hi + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+            tc_mma_tf32(tmem_lo, a_hi + adv, b_lo + adv, idesc, 1u);
+          }
+          if (BF16) tc_mma_bf16(d_hi, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
+          else tc_mma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
         }
         tc_commit(empty_bar + s);            // frees the smem stage once these MMAs have read it
-        if (kb % TC_KC == TC_KC - 1 || kb == num_kb - 1) tc_commit(hi_full + buf);   // chunk complete
+        if (chunk_last) tc_commit(hi_full + buf);   // chunk complete
       }
     }
   } else {
@@ -222,37 +255,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     const int64_t row = (int64_t)m0 + quarter * 32 + lane;
     const bool row_ok = row < p.M;
-    float run[BN];
+    float run[PASSES == 3 ? BN : 1];
+    if (PASSES == 3) {
 #pragma unroll
-    for (int j = 0; j < BN; ++j) run[j] = 0.0f;
-    for (int chunk = 0; chunk < num_chunks; ++chunk) {
-      const int buf = chunk & 1;
-      mbar_wait(hi_full + buf, (uint32_t)(chunk >> 1) & 1u, p.error_flag);
-      tc_fence_after();
+      for (int j = 0; j < (PASSES == 3 ? BN : 1); ++j) run[j] = 0.0f;
+      for (int chunk = 0; chunk < num_chunks; ++chunk) {
+        const int buf = chunk & 1;
+        mbar_wait(hi_full + buf, (uint32_t)(chunk >> 1) & 1u, p.error_flag);
+        tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tc_ld16(tmem_base + lane_sel + (uint32_t)(buf * BN + c0), v);
+        for (int c0 = 0; c0 < (PASSES == 3 ? BN : 0); c0 += 16) {
+          float v[16];
+          tc_ld16(tmem_base + lane_sel + (uint32_t)(buf * BN + c0), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) run[c0 + j] = __fadd_rn(run[c0 + j], v[j]);
+          for (int j = 0; j < 16; ++j) run[c0 + j] = __fadd_rn(run[c0 + j], v[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(hi_empty + buf);
       }
-      tc_fence_before();
-      mbar_arrive(hi_empty + buf);
+    } else if (num_chunks > 0) {   // the one accumulation over the whole K range
+      mbar_wait(hi_full, 0u, p.error_flag);
+      tc_fence_after();
     }
     // the last hi_full commit also covers every cross-term MMA
     float dot = 0.0f;
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
-      tc_ld16(tmem_lo + lane_sel + (uint32_t)c0, v);
+      tc_ld16((PASSES == 3 ? tmem_lo : tmem_base) + lane_sel + (uint32_t)c0, v);
       if (num_kb == 0) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.0f;       // empty k range: TMEM was never written
       }
       const int64_t col = (int64_t)n0 + c0;
       if (!row_ok || col >= p.N) continue;
+      if (PASSES == 3) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(run[c0 + j], v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(run[c0 + j], v[j]);
+      }
       if (EPI == TC_HESS_SYM) {
         // symmetric accumulate: only n >= m is computed here; each value is written to (m, n) and
         // mirrored to (n, m) (coalesced: consecutive lanes are consecutive m), so H stays
@@ -272,6 +312,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (col + j < p.N) cc[j] = v[j];
+      } else if (EPI == TC_ROWDOT && BF16) {
+        const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(p.R) + row * p.ldr + col;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col + j < p.N) dot = __fmaf_rn(v[j], __bfloat162float(rr[j]), dot);
       } else if (EPI == TC_ROWDOT) {
         const float* rr = p.R + row * p.ldr + col;
         const float* r2 = p.R2 ? p.R2 + row * p.ldr + col : nullptr;
@@ -387,14 +432,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 // rows x cols fp32, row pitch ld elements; box = box_rows x 32 columns, 128B swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    bool bf16 = false) {
   EncodeTiledFn fn = encode_fn();
   SLK_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * TC_BK : TC_BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult rc = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SLK_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
@@ -411,17 +457,17 @@ bool tc_gemm_usable(const void* a, int64_t lda, const void* b, int64_t ldb) {
   return ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && encode_fn() != nullptr;
 }
 
-template <int BN, int STAGES, int EPI>
-static int tc_launch_s(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
+template <int BN, int STAGES, int EPI, int PASSES = 3, bool BF16 = false>
+static int tc_launch_s(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
                        int64_t ldb, const TcParams& p, cudaStream_t st, int splits = 1) {
-  typedef TcSmem<BN, STAGES> SM;
+  typedef TcSmem<BN, STAGES, PASSES> SM;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a_hi, p.M, p.K, lda, TC_BM))) return rc;
-  if ((rc = make_map(&ma_lo, a_lo, p.M, p.K, lda, TC_BM))) return rc;
-  if ((rc = make_map(&mb_hi, b_hi, p.N, p.K, ldb, BN))) return rc;
-  if ((rc = make_map(&mb_lo, b_lo, p.N, p.K, ldb, BN))) return rc;
-  auto kern = tc_gemm_kernel<BN, STAGES, EPI>;
+  if ((rc = make_map(&ma_hi, a_hi, p.M, p.K, lda, TC_BM, BF16))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo, p.M, p.K, lda, TC_BM, BF16))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, p.N, p.K, ldb, BN, BF16))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo, p.N, p.K, ldb, BN, BF16))) return rc;
+  auto kern = tc_gemm_kernel<BN, STAGES, EPI, PASSES, BF16>;
   SLK_SMEM_ATTR_ONCE(kern, SM::TOTAL);
   dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, TC_BM), (unsigned)splits);
   kern<<<grid, TC_THREADS, SM::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
@@ -486,6 +532,22 @@ int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t 
   }
   SLK_REQUIRE(false, "tc_gemm_presplit: unsupported epilogue %d", epi);
   return SLK_ERR_ARG;
+}
+
+// Screening product (see the PASSES == 1 note at the kernel): rows of (A B^T) dotted with the rows of p.R,
+// partials per column tile of width bn (128 or 256) in p.C [M, ceil(N / bn)].  A and B hold TF32-representable
+// values.  Six (bn = 128) or four (bn = 256) 32 / 48 KB stages.
+int tc_gemm_screen_f32(const float* a, int64_t lda, const float* b, int64_t ldb, TcParams p, int bn, cudaStream_t st) {
+  if (bn == 256) return tc_launch_s<256, 4, TC_ROWDOT, 1>(a, a, lda, b, b, ldb, p, st);
+  SLK_REQUIRE(bn == 128, "tc_gemm_screen: tile width %d", bn);
+  return tc_launch_s<128, 6, TC_ROWDOT, 1>(a, a, lda, b, b, ldb, p, st);
+}
+// same with bf16 operands (pitches in elements, multiples of 8; p.R: the bf16 rows, pitch p.ldr elements)
+int tc_gemm_screen_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, TcParams p, int bn, cudaStream_t st) {
+  SLK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm_screen_bf16: row pitches must be multiples of 16 bytes");
+  if (bn == 256) return tc_launch_s<256, 4, TC_ROWDOT, 1, true>(a, a, lda, b, b, ldb, p, st);
+  SLK_REQUIRE(bn == 128, "tc_gemm_screen: tile width %d", bn);
+  return tc_launch_s<128, 6, TC_ROWDOT, 1, true>(a, a, lda, b, b, ldb, p, st);
 }
 
 // hi / lo TF32 parts of a [rows, cols] matrix (row pitch ld) into two matrices of pitch ldo

@@ -28,6 +28,11 @@ int tc_gemm_f32(int epi, const float* A, const float* A2, int64_t lda, const flo
 // same from operands already split into TF32 hi / lo parts (see split_tf32 below)
 int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi,
                          const float* b_lo, int64_t ldb, TcParams p, cudaStream_t st);
+// one kind::tf32 pass of TF32-representable operands with the row-dot epilogue (tiles of bn = 128 | 256 columns):
+// ~1e-3 relative, for screening only
+int tc_gemm_screen_f32(const float* a, int64_t lda, const float* b, int64_t ldb, TcParams p, int bn, cudaStream_t st);
+// the same with bf16 operands (kind::f16; pitches in elements, multiples of 8; p.R = the bf16 rows): ~4e-3 relative
+int tc_gemm_screen_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, TcParams p, int bn, cudaStream_t st);
 int tc_split_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, int64_t ldo, float* hi, float* lo,
                  cudaStream_t st);
 // the split the tensor path expects: hi = v with 13 low mantissa bits cleared, lo = RN_tf32(v - hi)

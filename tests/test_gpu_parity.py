@@ -272,6 +272,49 @@ def test_full_h_scale_search_vs_oracle(slk):
                       "[48,256] c=3 fp64 H - m m^T")
 
 
+@pytest.mark.parametrize("r,n,c,samples", [(200, 1024, 8, 2048), (96, 4096, 16, 2048), (130, 300, 3, 128),
+                                           (64, 2048, 4, 512)])
+def test_full_h_search_screening_is_exact(slk, r, n, c, samples):
+    """The full-H search ranks all grid points with one low-precision pass (bf16, or one TF32 pass) and
+    evaluates only the best-ranked candidates exactly (dense.cu): scales AND errors must be bit-identical to
+    evaluating every grid point (fullh_topk = 0), for 4 / 8 / 16 candidates, both operand types and both
+    tile widths of the screening product; the
+    all-points result is itself compared with the oracle (scaling.py:98-134) on a slice of the rows.
+    Rows of zeros and a row of tiny weights (every grid point gives the same error: first one wins)."""
+    from sleekit_b200 import ops, _convert as cv
+    from sleekit_b200.scaling import _factors
+
+    W, H, m = wl.synthetic_layer(r, n, 23, samples=samples)
+    W[3] = 0.0
+    W[5] *= 1e-30
+    cb, grid = slk.codebook.UniformCodebook(c, -1, 1), orc.UniformGrid(c, -1, 1)
+    Wd, Hd = cv.to_dev(W, torch.float32), cv.to_dev(H, torch.float32)
+    f = _factors(0.05, 1.0, 100, Wd.device)
+    res = {}
+    try:
+        for topk, bn, bf16 in [(0, 256, 1), (8, 256, 1), (8, 128, 1), (4, 256, 1), (16, 128, 1), (8, 256, 0),
+                               (4, 128, 0)]:
+            ops.set_option("fullh_topk", topk)
+            ops.set_option("fullh_bn", bn)
+            ops.set_option("fullh_bf16", bf16)
+            sc, err = ops.scale_search_fullh(Wd, cb, f, Hd, want_err=True)
+            res[(topk, bn, bf16)] = (sc.cpu().numpy(), err.cpu().numpy())
+    finally:
+        ops.set_option("fullh_topk", 8)
+        ops.set_option("fullh_bn", 256)
+        ops.set_option("fullh_bf16", 1)
+    base = res[(0, 256, 1)]
+    for key, (sc, err) in res.items():
+        same = float((sc == base[0]).mean())
+        print(f"[{r}x{n} c={c}] topk, tile, bf16 = {key}: scales identical in {same:.6f} of rows")
+        np.testing.assert_array_equal(sc, base[0], err_msg=str(key))
+        np.testing.assert_array_equal(err, base[1], err_msg=str(key))
+    rows = slice(0, 24)
+    want = orc.search_scale(W[rows], grid, 0, H=H)
+    scales_equivalent(base[0][rows], want, row_error_fn(W[rows], grid, H), "test_full_h_search_screening_is_exact",
+                      f"[{r},{n}] c={c}")
+
+
 # ---------------------------------------------------------------------------
 # K2 factor, ordering
 # ---------------------------------------------------------------------------
