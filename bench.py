@@ -529,7 +529,13 @@ def phase_rooflines(phases, profile, shapes, groups, cfg, peaks):
         elif name == "scale_search_fullh":
             ent.update(bound="tensor", unit="TFLOP/s", achieved=2.0 * GRID * rn2 / (ms * 1e-3) / 1e12,
                        peak=peaks["tf32_tflops"], peak_source=peaks["tf32_source"],
-                       note="full-H scale search: 2*G*r*n^2 algorithmic flop per layer (scaling.py:84-95 per grid point)")
+                       note=("full-H scale search: achieved = the REFERENCE's work, 2*G*r*n^2 flop per layer (scaling.py:84-95 "
+                             "per grid point), over the measured time.  The kernel path issues less: one bf16 tcgen05 pass over "
+                             "all G grid points (ranking only) plus the fp32-faithful 3xTF32 product for the 8 best-ranked "
+                             "points of each row -- results bit-identical to evaluating every point "
+                             "(test_full_h_search_screening_is_exact).  Issued: (G + 24) / G x the algorithmic flop, G/(G+24) "
+                             "of it on the bf16 pipe (ncu, profiles/r2_ncu_raw_fullh_screen.csv: tensor pipe 47.7 % active "
+                             "in the bf16 pass, 59.8 % in the exact pass); peak = the TF32 rate the unscreened search ran at"))
         elif name == "scale_search":
             ent.update(bound="hbm", unit="GB/s", achieved=4.0 * GRID * rn / (ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
                        peak_source=peaks["hbm_source"],
@@ -982,9 +988,9 @@ def run_ours(args):
         del outs, scs
 
     roofline = rooflines.get(top) if top else None
-    if in_step and in_step["factor_launches"]:
+    big = max(in_step["factor_launches"], key=lambda e: e["ms"]) if in_step and in_step["factor_launches"] else None
+    if big and (top == "chol_factor" or big["share_of_step"] >= 0.4):
         # the kernel with the largest share of the TIMED step: the batched factor launch of the widest layers
-        big = max(in_step["factor_launches"], key=lambda e: e["ms"])
         tr_ = ncu_traffic().get(f"chol_factor_batched:n={big['n']}x{big['matrices']}")
         roofline = {"kernel": "chol_dag_kernel (slk_chol_factor_batched_f32, %d matrices of n = %d in one launch)" % (big["matrices"], big["n"]),
                     "bound": "tensor", "unit": "TFLOP/s", "achieved": big["achieved"], "peak": peaks["fp64_tflops"],
@@ -998,7 +1004,7 @@ def run_ours(args):
                              "searches and sweeps share the SMs).  FP64 tensor path (DMMA); peak = cuBLAS fp64 GEMM measured in "
                              "this run.  Alone on the GPU the same launch reaches the figure in profiles/ (ncu: DMMA pipe 56 % "
                              "active).  rooflines_all_phases has every operation of the serial profile pass.")}
-    issued3 = {"gptq_sweep", "hweighted_error", "scale_search_fullh", "local_search"}
+    issued3 = {"gptq_sweep", "hweighted_error", "local_search"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -14,6 +14,8 @@
 int64_t g_opt_fullh_topk = 8;
 int64_t g_opt_fullh_bn = 256;
 int64_t g_opt_fullh_bf16 = 1;
+int64_t g_opt_fullh_ctas = 2;      // ("fullh_ctas", 1 | 2): CTAs per SM of the screening product
+int64_t g_opt_fullh_compact = 1;   // ("fullh_compact", 0 | 1): candidates within 2^-5 of the best-ranked one only, compacted
 
 namespace slk {
 
@@ -85,12 +87,16 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 // pitch allows it (the pass is then bound by its stores, not by index arithmetic).
 // SCREEN: 0 exact residuals (+ TF32 parts), 1 residuals rounded to TF32, 2 residuals rounded to bf16 (resid then
 // points to a bf16 matrix of the same shape)
+// The three divides (by the scale, by the codebook step, by the reciprocal scale) go through the correctly
+// rounded reciprocal scheme of common.cuh: same results as the IEEE divides, a quarter of the instructions.
+struct ResidDiv { FastDivF scale, rs, step; };
+
 template <int SCREEN>
-__device__ __forceinline__ float grid_resid_value(const DevGrid<float>& g, float x, float scale, float rs, bool live) {
+__device__ __forceinline__ float grid_resid_value(const DevGrid<float>& g, float x, const ResidDiv& d, bool live) {
   float e = 0.0f;
   if (live) {
-    const float v = grid_value(g, __fdiv_rn(x, scale));
-    e = __fsub_rn(__fdiv_rn(v, rs), x);
+    const float v = g.kind == 0 ? uniform_value_fast(g, d.step, fastdiv(x, d.scale)) : grid_value(g, __fdiv_rn(x, d.scale.d));
+    e = __fsub_rn(fastdiv(v, d.rs), x);
   }
   return SCREEN == 1 ? __uint_as_float((__float_as_uint(e) + 0x1000u) & 0xffffe000u) : e;
 }
@@ -101,19 +107,23 @@ __global__ void __launch_bounds__(128) grid_resid_kernel(const float* __restrict
                                                          int g0, int gcount, const float* __restrict__ init,
                                                          TE* __restrict__ resid, float* __restrict__ rhi = nullptr,
                                                          float* __restrict__ rlo = nullptr,
-                                                         const int* __restrict__ cand = nullptr) {
-  const int64_t pairs = (int64_t)gcount * r;
+                                                         const int* __restrict__ cand = nullptr,
+                                                         const int* __restrict__ pair_row = nullptr,
+                                                         const int* __restrict__ pair_count = nullptr) {
+  // pair_row != nullptr: a compacted list of *pair_count (row, grid point) pairs: pair_row[i], cand[i]
+  const int64_t pairs = pair_row ? (int64_t)__ldg(pair_count) : (int64_t)gcount * r;
   const bool vec = sizeof(TE) == 4 && (n & 3) == 0 && (((uintptr_t)w | (uintptr_t)resid | (uintptr_t)rhi | (uintptr_t)rlo) & 15) == 0;
   for (int64_t pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
     const int gi = (int)(pr / r);
-    const int64_t row = pr - (int64_t)gi * r;
+    const int64_t row = pair_row ? (int64_t)__ldg(pair_row + pr) : pr - (int64_t)gi * r;
     const int gp = cand ? __ldg(cand + pr) : g0 + gi;
     const bool live = gp >= 0;
-    float scale = 1.0f, rs = 1.0f;
-    if (live) {
-      scale = __fmul_rn(__ldg(factors + gp), __ldg(init + row));
-      rs = __fdiv_rn(1.0f, scale);
-    }
+    float scale = 1.0f;
+    if (live) scale = __fmul_rn(__ldg(factors + gp), __ldg(init + row));
+    ResidDiv dv;
+    dv.scale = make_fastdiv(scale);
+    dv.rs = make_fastdiv(dv.scale.y);             // y = RN(1 / scale): the reciprocal scale of scaling.py:80
+    dv.step = make_fastdiv(g.step);
     const float* wr = w + row * n;
     TE* out = resid + pr * n;
     if (vec) {
@@ -121,10 +131,10 @@ __global__ void __launch_bounds__(128) grid_resid_kernel(const float* __restrict
       for (int64_t j = threadIdx.x; j < (n >> 2); j += blockDim.x) {
         const float4 x = __ldg(w4 + j);
         float4 e;
-        e.x = grid_resid_value<SCREEN>(g, x.x, scale, rs, live);
-        e.y = grid_resid_value<SCREEN>(g, x.y, scale, rs, live);
-        e.z = grid_resid_value<SCREEN>(g, x.z, scale, rs, live);
-        e.w = grid_resid_value<SCREEN>(g, x.w, scale, rs, live);
+        e.x = grid_resid_value<SCREEN>(g, x.x, dv, live);
+        e.y = grid_resid_value<SCREEN>(g, x.y, dv, live);
+        e.z = grid_resid_value<SCREEN>(g, x.z, dv, live);
+        e.w = grid_resid_value<SCREEN>(g, x.w, dv, live);
         if (SCREEN == 2) {
           __nv_bfloat162 lo2 = __floats2bfloat162_rn(e.x, e.y), hi2 = __floats2bfloat162_rn(e.z, e.w);
           uint2 pk;
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(128) grid_resid_kernel(const float* __restrict
       }
     } else {
       for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-        const float e = grid_resid_value<SCREEN>(g, __ldg(wr + j), scale, rs, live);
+        const float e = grid_resid_value<SCREEN>(g, __ldg(wr + j), dv, live);
         if (SCREEN == 2) {
           reinterpret_cast<__nv_bfloat16*>(resid)[pr * n + j] = __float2bfloat16_rn(e);
           continue;
@@ -223,6 +233,95 @@ __global__ void __launch_bounds__(128) screen_topk_kernel(const float* __restric
   }
 #pragma unroll
   for (int j = 0; j < TOPK; ++j) cand[(int64_t)j * r + row] = bg[j];
+}
+
+// Compacted candidates: a row keeps the (at most TOPK) best-ranked grid points whose screening error lies within
+// `tau` of its best one -- with a ranking error eps, the true minimum is within (1 + eps) / (1 - eps) of the best
+// screening value, so tau = 2^-5 against eps <= 5e-3 (bf16) cuts nothing that could win; typically 2-3 points
+// remain of 8.  count[row] = kept candidates (>= 1 when the row has a finite error at all).
+template <int TOPK>
+__global__ void __launch_bounds__(128) screen_select_kernel(const float* __restrict__ err, int64_t r, int G, float tau,
+                                                            int* __restrict__ cand, int* __restrict__ count) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  float be[TOPK];
+  int bg[TOPK];
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) { be[j] = __int_as_float(0x7f800000); bg[j] = -1; }
+  for (int gi = 0; gi < G; ++gi) {
+    const float e = err[(int64_t)gi * r + row];
+    if (e < be[TOPK - 1]) {
+      be[TOPK - 1] = e; bg[TOPK - 1] = gi;
+#pragma unroll
+      for (int j = TOPK - 1; j > 0; --j) {
+        const bool sw = be[j] < be[j - 1];
+        const float te = sw ? be[j - 1] : be[j];
+        const int tg = sw ? bg[j - 1] : bg[j];
+        be[j - 1] = sw ? be[j] : be[j - 1];
+        bg[j - 1] = sw ? bg[j] : bg[j - 1];
+        be[j] = te; bg[j] = tg;
+      }
+    }
+  }
+  const float thr = __fadd_rn(be[0], __fmul_rn(tau, fabsf(be[0])));
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < TOPK; ++j) {
+    const bool keep = bg[j] >= 0 && (j == 0 || be[j] <= thr);
+    cand[(int64_t)j * r + row] = keep ? bg[j] : -1;     // sorted by screening error: the kept ones are a prefix
+    c += keep ? 1 : 0;
+  }
+  count[row] = c;
+}
+
+// offsets[row] = min(capacity, sum of count[0..row)), offsets[r] = total pairs (one CTA: r is a layer's row count),
+// then the pair lists in row order
+__global__ void __launch_bounds__(1024) screen_pairs_kernel(const int* __restrict__ count, const int* __restrict__ cand,
+                                                            int64_t r, int capacity, int* __restrict__ offsets,
+                                                            int* __restrict__ pair_row, int* __restrict__ pair_g) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (r + 1023) / 1024;
+  const int64_t lo = t * per, hi = lo + per < r ? lo + per : r;
+  int s = 0;
+  for (int64_t i = lo; i < hi; ++i) s += count[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {        // inclusive scan of the per-thread sums
+    const int v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = t ? part[t - 1] : 0;
+  for (int64_t i = lo; i < hi; ++i) {
+    const int b = run < capacity ? run : capacity;
+    run += count[i];
+    const int e = run < capacity ? run : capacity;
+    offsets[i] = b;
+    for (int k = b; k < e; ++k) {
+      pair_row[k] = (int)i;
+      pair_g[k] = cand[(int64_t)(k - b) * r + i];
+    }
+  }
+  if (t == 1023) offsets[r] = part[1023] < capacity ? part[1023] : capacity;
+}
+
+__global__ void __launch_bounds__(256) pairs_argmin_kernel(const float* __restrict__ err, const int* __restrict__ pair_g,
+                                                           const int* __restrict__ offsets, int64_t r,
+                                                           const float* __restrict__ factors, float* __restrict__ best_err,
+                                                           float* __restrict__ best_f) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  float be = best_err[row];
+  int bg = -1;
+  for (int i = offsets[row]; i < offsets[row + 1]; ++i) {
+    const float e = err[i];
+    const int gp = pair_g[i];
+    if (e < be || (e == be && bg >= 0 && gp < bg)) { be = e; bg = gp; }
+  }
+  best_err[row] = be;
+  if (bg >= 0) best_f[row] = __ldg(factors + bg);
 }
 
 // first minimum in grid order over the evaluated candidates (strict '<'; equal errors: the lower grid index)
@@ -355,7 +454,8 @@ size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t 
     bytes += 2 * align256((size_t)chunk * r * n * 4) + 2 * align256((size_t)n * n * 4);
     // screening: errors of all grid points, candidate lists, best index, row-dot partials of 2 * chunk points
     bytes += align256((size_t)G * r * 4) + align256((size_t)FULLH_TOPK_MAX * r * 4) + align256((size_t)r * 4) +
-             align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4) + align256((size_t)n * n * 2);
+             align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4) + align256((size_t)n * n * 2) +
+             3 * align256((size_t)(FULLH_TOPK_MAX * r + 2) * 4);   // row counts / offsets, pair rows, pair grid points
   }
   return bytes;
 }
@@ -395,12 +495,16 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
   float *errs_all = nullptr, *part_s = nullptr;
   int *cand = nullptr, *best_g = nullptr;
   __nv_bfloat16* hbf = nullptr;
+  int *offsets = nullptr, *pair_row = nullptr, *pair_g = nullptr;
   if (screen) {
     errs_all = (float*)base; base += align256((size_t)G * r * 4);
     cand = (int*)base; base += align256((size_t)FULLH_TOPK_MAX * r * 4);
     best_g = (int*)base; base += align256((size_t)r * 4);
     part_s = (float*)base; base += align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4);
-    hbf = (__nv_bfloat16*)base;
+    hbf = (__nv_bfloat16*)base; base += align256((size_t)n * n * 2);
+    offsets = (int*)base; base += align256((size_t)(FULLH_TOPK_MAX * r + 2) * 4);
+    pair_row = (int*)base; base += align256((size_t)(FULLH_TOPK_MAX * r + 2) * 4);
+    pair_g = (int*)base;
   }
 
   rc = slk_row_noclip_scale_f32(w, r, n, cb->lo, cb->hi, init, stream);
@@ -432,10 +536,39 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
       TcParams tp;
       tp.C = part_s; tp.ldc = tiles_s; tp.R = rhi; tp.R2 = nullptr; tp.ldr = n;
       tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
-      rc = bf16 ? tc_gemm_screen_bf16(rhi, n, hbf, n, tp, bn, st) : tc_gemm_screen_f32(rhi, n, hhi, n, tp, bn, st);
+      rc = bf16 ? tc_gemm_screen_bf16(rhi, n, hbf, n, tp, bn, (int)g_opt_fullh_ctas, st)
+                : tc_gemm_screen_f32(rhi, n, hhi, n, tp, bn, (int)g_opt_fullh_ctas, st);
       if (rc) return rc;
       rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>(part_s, rows, tiles_s, errs_all + (int64_t)g0 * r);
       SLK_LAUNCH_CHECK();
+    }
+    if (g_opt_fullh_compact && topk <= chunk && (int64_t)topk * r < (1ll << 30)) {
+      // 2a. compacted candidates (see screen_select_kernel): capacity topk * r pairs, GEMM row tiles beyond the
+      //     device-side pair count exit at once
+      const int cap = (int)((int64_t)topk * r);
+      int* count = best_g;
+      screen_select_kernel<FULLH_TOPK_MAX><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, 0.03125f, cand, count);
+      SLK_LAUNCH_CHECK();
+      screen_pairs_kernel<<<1, 1024, 0, st>>>(count, cand, r, cap, offsets, pair_row, pair_g);
+      SLK_LAUNCH_CHECK();
+      grid_resid_kernel<float><<<resid_blocks(cap), 128, 0, st>>>(w, r, n, g, factors, 0, topk, init, (float*)resid, rhi, rlo,
+                                                                  pair_g, pair_row, offsets + r);
+      SLK_LAUNCH_CHECK();
+      TcParams tp;
+      tp.C = (float*)part; tp.ldc = ceil_div(n, TC_TILE_N); tp.R = (const float*)resid; tp.R2 = nullptr; tp.ldr = n;
+      tp.M = cap; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+      tp.m_limit = offsets + r;
+      rc = tc_gemm_presplit_f32(TC_ROWDOT, rhi, rlo, n, hhi, hlo, n, tp, st);
+      if (rc) return rc;
+      rowdot_reduce_kernel<float><<<(int)ceil_div(cap, 256), 256, 0, st>>>((const float*)part, cap, ceil_div(n, TC_TILE_N),
+                                                                          (float*)errs);
+      SLK_LAUNCH_CHECK();
+      pairs_argmin_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, pair_g, offsets, r, factors, best_err,
+                                                                 best_f);
+      SLK_LAUNCH_CHECK();
+      finish_scale_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(init, best_f, best_err, r, out_scale, out_err);
+      SLK_LAUNCH_CHECK();
+      return SLK_OK;
     }
     if (topk == 4) screen_topk_kernel<4><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
     else if (topk == 8) screen_topk_kernel<8><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);

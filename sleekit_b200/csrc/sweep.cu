@@ -19,7 +19,7 @@
 #include <stdlib.h>
 
 static int64_t g_opt_sweep_ctas = 0;     // slk_set_option("sweep_ctas", v)
-extern int64_t g_opt_fullh_topk, g_opt_fullh_bn, g_opt_fullh_bf16;   // dense.cu
+extern int64_t g_opt_fullh_topk, g_opt_fullh_bn, g_opt_fullh_bf16, g_opt_fullh_ctas, g_opt_fullh_compact;   // dense.cu
 
 namespace slk {
 
@@ -1081,6 +1081,8 @@ extern "C" int slk_set_option(const char* name, int64_t value) {
     g_opt_fullh_topk = value;
     return SLK_OK;
   }
+  if (strcmp(name, "fullh_ctas") == 0) { g_opt_fullh_ctas = value == 1 ? 1 : 2; return SLK_OK; }
+  if (strcmp(name, "fullh_compact") == 0) { g_opt_fullh_compact = value != 0; return SLK_OK; }
   if (strcmp(name, "fullh_bf16") == 0) { g_opt_fullh_bf16 = value != 0; return SLK_OK; }
   if (strcmp(name, "fullh_bn") == 0) {
     SLK_REQUIRE(value == 128 || value == 256, "fullh_bn must be 128 or 256");

@@ -163,6 +163,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   static_assert(PASSES == 3 || EPI == TC_ROWDOT, "the single-pass product only feeds the row-dot screening");
   static_assert(!BF16 || PASSES == 1, "bf16 operands: screening pass only");
   constexpr int BK = BF16 ? 2 * TC_BK : TC_BK;   // elements per 128-byte k-block
+  // the single-pass tile allocates only its own accumulator columns, so that two CTAs can share an SM (one's
+  // epilogue under the other's main loop) when their shared memory allows it
+  constexpr uint32_t TMEM_COLS = PASSES == 1 ? (uint32_t)BN : 512u;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024 B alignment
   uint64_t* bars = (uint64_t*)(tiles + STAGES * SM::STAGE_BYTES);
@@ -175,6 +178,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   if ((EPI == TC_HESS_SYM || EPI == TC_SYM_PART) && n0 + BN <= m0) return;   // strictly-lower tile of a symmetric product
+  if (p.m_limit != nullptr && m0 >= __ldg(p.m_limit)) return;                // beyond the device-side row count
   const int num_kb_all = (int)((p.K + BK - 1) / BK);
   // split-K (TC_SYM_PART): this CTA covers k-blocks [kb0, kb0 + num_kb) and writes plane blockIdx.z
   const int kb0 = EPI == TC_SYM_PART ? (int)blockIdx.z * p.kb_per_split : 0;
@@ -187,7 +191,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -368,7 +372,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -536,17 +540,26 @@ int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t 
 
 // Screening product (see the PASSES == 1 note at the kernel): rows of (A B^T) dotted with the rows of p.R,
 // partials per column tile of width bn (128 or 256) in p.C [M, ceil(N / bn)].  A and B hold TF32-representable
-// values.  Six (bn = 128) or four (bn = 256) 32 / 48 KB stages.
-int tc_gemm_screen_f32(const float* a, int64_t lda, const float* b, int64_t ldb, TcParams p, int bn, cudaStream_t st) {
+// values.  ctas = 1: six (bn = 128) or four (bn = 256) 32 / 48 KB stages, one CTA per SM; ctas = 2: half the
+// stages (96 KB), two CTAs per SM.  (Measured and dropped: two 128-row tiles per CTA sharing each B tile --
+// 64 KB per 256 x 256 x 64 block, one CTA per SM -- 3.7 ms against 3.4 ms at [102400, 4096] x 4096: its
+// epilogue cannot overlap a main loop, the 512 TMEM columns being taken by the one tile pair.)
+int tc_gemm_screen_f32(const float* a, int64_t lda, const float* b, int64_t ldb, TcParams p, int bn, int ctas,
+                       cudaStream_t st) {
+  if (bn == 256 && ctas == 2) return tc_launch_s<256, 2, TC_ROWDOT, 1>(a, a, lda, b, b, ldb, p, st);
   if (bn == 256) return tc_launch_s<256, 4, TC_ROWDOT, 1>(a, a, lda, b, b, ldb, p, st);
   SLK_REQUIRE(bn == 128, "tc_gemm_screen: tile width %d", bn);
+  if (ctas == 2) return tc_launch_s<128, 3, TC_ROWDOT, 1>(a, a, lda, b, b, ldb, p, st);
   return tc_launch_s<128, 6, TC_ROWDOT, 1>(a, a, lda, b, b, ldb, p, st);
 }
 // same with bf16 operands (pitches in elements, multiples of 8; p.R: the bf16 rows, pitch p.ldr elements)
-int tc_gemm_screen_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, TcParams p, int bn, cudaStream_t st) {
+int tc_gemm_screen_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, TcParams p, int bn, int ctas,
+                        cudaStream_t st) {
   SLK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm_screen_bf16: row pitches must be multiples of 16 bytes");
+  if (bn == 256 && ctas == 2) return tc_launch_s<256, 2, TC_ROWDOT, 1, true>(a, a, lda, b, b, ldb, p, st);
   if (bn == 256) return tc_launch_s<256, 4, TC_ROWDOT, 1, true>(a, a, lda, b, b, ldb, p, st);
   SLK_REQUIRE(bn == 128, "tc_gemm_screen: tile width %d", bn);
+  if (ctas == 2) return tc_launch_s<128, 3, TC_ROWDOT, 1, true>(a, a, lda, b, b, ldb, p, st);
   return tc_launch_s<128, 6, TC_ROWDOT, 1, true>(a, a, lda, b, b, ldb, p, st);
 }
 

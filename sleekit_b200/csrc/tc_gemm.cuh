@@ -14,6 +14,8 @@ struct TcParams {
   float alpha, keep, count;
   int* error_flag;               // set (and the kernel traps) if a barrier wait exceeds its budget
   int kb_per_split = 0;          // TC_SYM_PART: k-blocks (of 32) per blockIdx.z; plane z of C is C + z*M*ldc
+  const int* m_limit = nullptr;  // device scalar: row tiles starting at or beyond *m_limit exit at once (a row count only
+                                 // known on the device; M is then the capacity the grid is sized for)
 };
 
 constexpr int TC_TILE_N = 128;
@@ -28,11 +30,13 @@ int tc_gemm_f32(int epi, const float* A, const float* A2, int64_t lda, const flo
 // same from operands already split into TF32 hi / lo parts (see split_tf32 below)
 int tc_gemm_presplit_f32(int epi, const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi,
                          const float* b_lo, int64_t ldb, TcParams p, cudaStream_t st);
-// one kind::tf32 pass of TF32-representable operands with the row-dot epilogue (tiles of bn = 128 | 256 columns):
-// ~1e-3 relative, for screening only
-int tc_gemm_screen_f32(const float* a, int64_t lda, const float* b, int64_t ldb, TcParams p, int bn, cudaStream_t st);
+// one kind::tf32 pass of TF32-representable operands with the row-dot epilogue (tiles of bn = 128 | 256 columns,
+// ctas = 1 | 2 CTAs per SM): ~1e-3 relative, for screening only
+int tc_gemm_screen_f32(const float* a, int64_t lda, const float* b, int64_t ldb, TcParams p, int bn, int ctas,
+                       cudaStream_t st);
 // the same with bf16 operands (kind::f16; pitches in elements, multiples of 8; p.R = the bf16 rows): ~4e-3 relative
-int tc_gemm_screen_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, TcParams p, int bn, cudaStream_t st);
+int tc_gemm_screen_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, TcParams p, int bn, int ctas,
+                        cudaStream_t st);
 int tc_split_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, int64_t ldo, float* hi, float* lo,
                  cudaStream_t st);
 // the split the tensor path expects: hi = v with 13 low mantissa bits cleared, lo = RN_tf32(v - hi)

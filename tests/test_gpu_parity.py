@@ -277,8 +277,8 @@ def test_full_h_scale_search_vs_oracle(slk):
 def test_full_h_search_screening_is_exact(slk, r, n, c, samples):
     """The full-H search ranks all grid points with one low-precision pass (bf16, or one TF32 pass) and
     evaluates only the best-ranked candidates exactly (dense.cu): scales AND errors must be bit-identical to
-    evaluating every grid point (fullh_topk = 0), for 4 / 8 / 16 candidates, both operand types and both
-    tile widths of the screening product; the
+    evaluating every grid point (fullh_topk = 0), for 4 / 8 / 16 candidates (fixed per row, or compacted to
+    those within 2^-5 of the best-ranked one), both operand types and both tile widths of the screening product; the
     all-points result is itself compared with the oracle (scaling.py:98-134) on a slice of the rows.
     Rows of zeros and a row of tiny weights (every grid point gives the same error: first one wins)."""
     from sleekit_b200 import ops, _convert as cv
@@ -292,21 +292,25 @@ def test_full_h_search_screening_is_exact(slk, r, n, c, samples):
     f = _factors(0.05, 1.0, 100, Wd.device)
     res = {}
     try:
-        for topk, bn, bf16 in [(0, 256, 1), (8, 256, 1), (8, 128, 1), (4, 256, 1), (16, 128, 1), (8, 256, 0),
-                               (4, 128, 0)]:
+        for topk, bn, bf16, compact in [(0, 256, 1, 1), (8, 256, 1, 1), (8, 128, 1, 0), (4, 256, 1, 1), (16, 128, 1, 1),
+                                        (8, 256, 0, 1), (4, 128, 0, 0), (16, 256, 1, 0)]:
+            ops.set_option("fullh_compact", compact)
+            ops.set_option("fullh_ctas", 1 if (topk, bn) == (8, 256) else 2)
             ops.set_option("fullh_topk", topk)
             ops.set_option("fullh_bn", bn)
             ops.set_option("fullh_bf16", bf16)
             sc, err = ops.scale_search_fullh(Wd, cb, f, Hd, want_err=True)
-            res[(topk, bn, bf16)] = (sc.cpu().numpy(), err.cpu().numpy())
+            res[(topk, bn, bf16, compact)] = (sc.cpu().numpy(), err.cpu().numpy())
     finally:
         ops.set_option("fullh_topk", 8)
         ops.set_option("fullh_bn", 256)
         ops.set_option("fullh_bf16", 1)
-    base = res[(0, 256, 1)]
+        ops.set_option("fullh_ctas", 2)
+        ops.set_option("fullh_compact", 1)
+    base = res[(0, 256, 1, 1)]
     for key, (sc, err) in res.items():
         same = float((sc == base[0]).mean())
-        print(f"[{r}x{n} c={c}] topk, tile, bf16 = {key}: scales identical in {same:.6f} of rows")
+        print(f"[{r}x{n} c={c}] topk, tile, bf16, compacted = {key}: scales identical in {same:.6f} of rows")
         np.testing.assert_array_equal(sc, base[0], err_msg=str(key))
         np.testing.assert_array_equal(err, base[1], err_msg=str(key))
     rows = slice(0, 24)

@@ -29,14 +29,18 @@ def main():
     f = _factors(0.05, 1.0, 100, dev)
     out = []
     shapes = [tuple(int(v) for v in args.shape.split(","))] if args.shape else [(1024, 1024), (4096, 1024), (1024, 4096)]
-    variants = [(0, 256, 1), (8, 256, 1), (8, 128, 1), (4, 256, 1), (16, 256, 1), (8, 256, 0), (4, 256, 0)]
+    # (candidates, screening tile width, bf16 operands, CTAs per SM, compacted candidate list)
+    variants = [(0, 256, 1, 2, 1), (8, 256, 1, 2, 1), (8, 256, 1, 2, 0), (8, 256, 1, 1, 0), (8, 128, 1, 2, 0),
+                (4, 256, 1, 2, 0), (16, 256, 1, 2, 1), (16, 256, 1, 2, 0), (8, 256, 0, 2, 0)]
     if args.topk:
-        variants = [(int(args.topk), 256, 1)]
+        variants = [(int(args.topk), 256, 1, 2, 1)]
     for r, n in shapes:
         W, H, _ = wl.synthetic_layer(r, n, 31, samples=2048)
         Wd, Hd = torch.from_numpy(W).to(dev), torch.from_numpy(H).to(dev)
         base = None
-        for topk, bn, bf16 in variants:
+        for topk, bn, bf16, ctas, compact in variants:
+            ops.set_option("fullh_ctas", ctas)
+            ops.set_option("fullh_compact", compact)
             ops.set_option("fullh_topk", topk)
             ops.set_option("fullh_bn", bn)
             ops.set_option("fullh_bf16", bf16)
@@ -52,7 +56,8 @@ def main():
             ms = e0.elapsed_time(e1) / args.reps
             if base is None:
                 base = (sc.clone(), err.clone())
-            rec = {"rows": r, "cols": n, "grid_points": 100, "fullh_topk": topk, "screen_tile_n": bn if topk else None,
+            rec = {"rows": r, "cols": n, "grid_points": 100, "fullh_topk": topk, "screen_tile_n": bn if topk else None, "screen_ctas_per_sm": ctas if topk else None,
+                   "candidates": ("within 2^-5 of the best-ranked, compacted" if compact else "fixed per row") if topk else None,
                    "screen_operands": ("bf16" if bf16 else "tf32") if topk else None,
                    "ms": round(ms, 3), "algorithmic_tflops": round(2.0 * 100 * r * n * n / ms / 1e9, 1),
                    "scales_identical": bool(torch.equal(sc, base[0])), "errors_identical": bool(torch.equal(err, base[1]))}
@@ -61,6 +66,8 @@ def main():
     ops.set_option("fullh_topk", 8)
     ops.set_option("fullh_bn", 256)
     ops.set_option("fullh_bf16", 1)
+    ops.set_option("fullh_ctas", 2)
+    ops.set_option("fullh_compact", 1)
     return out
 
 
