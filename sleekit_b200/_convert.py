@@ -59,6 +59,7 @@ D2H_BYTES = 0
 
 _STAGE_BYTES = 32 << 20
 _STAGE_MIN = 4 << 20          # below this a plain copy is as fast
+_PIN_MIN = 256 << 10          # results at least this large are returned in page-locked arrays
 _stage = None                 # [pinned uint8 buffer, event] x 2
 
 
@@ -94,7 +95,7 @@ def _download(t):
     global D2H_BYTES
     t = t.detach()
     D2H_BYTES += t.numel() * t.element_size()
-    if t.numel() * t.element_size() < _STAGE_MIN or t.dtype in (torch.uint16, torch.uint32):
+    if t.numel() * t.element_size() < _PIN_MIN or t.dtype in (torch.uint16, torch.uint32):
         return t.cpu().numpy()
     host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     host.copy_(t, non_blocking=True)
@@ -121,13 +122,18 @@ def _key(a):
     return (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
 
 
+_FP_SAMPLES = 1024            # strided elements (each one a cache miss on a large array: ~0.1 ms per 1024)
+_FP_DIAG = 512
+
+
 def _fingerprint(a):
     flat = a.reshape(-1) if a.flags.c_contiguous else np.ascontiguousarray(a).reshape(-1)
-    step = max(1, flat.size // 4096)
-    h = zlib.crc32(flat[::step][:4096].tobytes())
+    step = max(1, flat.size // _FP_SAMPLES)
+    h = zlib.crc32(flat[::step][:_FP_SAMPLES].tobytes())
     h = zlib.crc32(flat[-64:].tobytes(), h)
     if a.ndim == 2 and a.shape[0] == a.shape[1]:
-        h = zlib.crc32(np.ascontiguousarray(a.diagonal()).tobytes(), h)
+        d = a.diagonal()
+        h = zlib.crc32(d[::max(1, d.size // _FP_DIAG)].tobytes(), h)
     return h
 
 
@@ -172,15 +178,21 @@ def _insert(a, key, dtype_key, t):
         _drop(next(iter(_cache)))
 
 
-def _lookup(a, key, dtype_key):
+def _lookup(a, key, dtype_keys):
+    """First cached tensor among dtype_keys (None if the array is unknown, replaced or modified); the content
+    check runs once per call."""
     ent = _cache.get(key)
     if ent is None:
-        return None
+        return None, None
     if ent[0]() is not a or ent[1] != _fingerprint(a):
         _drop(key)                                   # another array at this address, or its content changed
-        return None
+        return None, None
     _cache.move_to_end(key)
-    return ent[2].get(dtype_key)
+    for dk in dtype_keys:
+        t = ent[2].get(dk)
+        if t is not None:
+            return dk, t
+    return None, None
 
 
 def to_dev_cached(x, dtype=None):
@@ -192,16 +204,15 @@ def to_dev_cached(x, dtype=None):
         return to_dev(x, dtype)
     dev = ops.device()
     key = _key(x)
-    dkey = (dtype, dev.index)
-    t = _lookup(x, key, dkey)
-    if t is not None:
+    dkey, bkey = (dtype, dev.index), (None, dev.index)
+    found, base = _lookup(x, key, (dkey, bkey))
+    if found == dkey and found != bkey:
         CACHE_HITS += 1
-        return t
-    base = _lookup(x, key, (None, dev.index))
+        return base
     if base is None:
         CACHE_MISSES += 1
         base = _upload(np.ascontiguousarray(x), dev)
-        _insert(x, key, (None, dev.index), base)
+        _insert(x, key, bkey, base)
     else:
         CACHE_HITS += 1
     if dtype is None or base.dtype == dtype:

@@ -200,3 +200,29 @@ def test_symmetric_upload_accounting_without_gpu():
     assert lib.slk_upload_symmetric_bytes(3072, ops.symmetric_block_rows(3072)) / (4 * 3072 * 3072) < 0.54
     # argument errors are reported, not crashed
     assert lib.slk_upload_symmetric_f32(None, None, 16, 32, None) != 0
+
+
+def test_upload_cache_fingerprint_detects_in_place_edits():
+    """_convert._fingerprint (host only): the sampled content check of the identity-keyed upload cache changes
+    under the in-place edits the reference's callers make -- dampening the diagonal (obq.py:45-47 style),
+    rescaling or shifting the whole array, overwriting its tail -- and is stable for untouched content,
+    for 1-D, rectangular, square and non-contiguous arrays."""
+    from sleekit_b200 import _convert as cv
+
+    rng = np.random.default_rng(0)
+    for shape in [(3072, 3072), (768, 3072), (100000,), (5, 7)]:
+        a = rng.standard_normal(shape).astype(np.float32)
+        f0 = cv._fingerprint(a)
+        assert cv._fingerprint(a) == f0 and cv._fingerprint(a.copy()) == f0
+        b = a.copy()
+        b *= np.float32(1.5)
+        assert cv._fingerprint(b) != f0
+        b = a.copy()
+        b.reshape(-1)[-3:] += 1
+        assert cv._fingerprint(b) != f0
+        if len(shape) == 2 and shape[0] == shape[1]:
+            b = a.copy()
+            b[np.arange(shape[0]), np.arange(shape[0])] += np.float32(0.01)
+            assert cv._fingerprint(b) != f0
+    t = rng.standard_normal((64, 128)).astype(np.float32).T      # a transposed view
+    assert cv._fingerprint(t) == cv._fingerprint(np.ascontiguousarray(t))
