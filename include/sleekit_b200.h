@@ -139,7 +139,9 @@ int slk_gain_f64(const double* w, const double* q, const double* h, const double
                  int64_t n, double* out, void* stream);
 
 /* full-H scale-grid search: compute_min_mse_scaling with a 2-D H  scaling.py:98-134
- * h_dtype 1: H fp32, 2: H fp64 (errors then accumulate in fp64). */
+ * h_dtype 1: H fp32, 2: H fp64 (errors then accumulate in fp64).  With an fp32 H (n % 4 == 0) all G grid points
+ * are ranked by one low-precision tensor pass and only the best-ranked ones of each row are evaluated by the
+ * fp32-faithful product: the same scales and errors, bit for bit, as evaluating every point (options below). */
 size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t h_dtype);
 int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb_host,
                                const float* factors, int32_t G, const void* h, int32_t h_dtype,
@@ -267,7 +269,12 @@ int slk_sym_unpack_f32(const float* packed, int64_t n, int64_t bs, float scale, 
 int slk_stream_create(int priority, void** stream_host);
 int slk_stream_destroy(void* stream);
 /* Process-wide tuning knobs, by name: "sweep_ctas" = CTAs wanted per macro-block sweep launch (0 = the
- * single-layer default; a layer set that runs many sweeps side by side prefers fewer, taller CTAs). */
+ * single-layer default; a layer set that runs many sweeps side by side prefers fewer, taller CTAs).
+ * Full-H search: "fullh_topk" = exactly evaluated candidates per row, 0 | 4 | 8 | 16 (0: no screening, every grid
+ * point is evaluated; default 8), "fullh_compact" 1 | 0 (only the candidates within 2^-5 of the best-ranked one,
+ * as a compacted list of at most topk per row on average | a fixed topk per row), "fullh_bf16" 1 | 0 (ranking
+ * pass on bf16 | TF32 operands), "fullh_bn" 256 | 128 and "fullh_ctas" 2 | 1 (tile width and CTAs per SM of the
+ * ranking product). */
 int slk_set_option(const char* name, int64_t value);
 
 /* Development aid: stores %globaltimer (ns, uint64) into *slot when the stream reaches the call. */
