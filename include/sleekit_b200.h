@@ -327,6 +327,12 @@ size_t slk_local_search_ws_bytes(int64_t r, int64_t n);
 int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n,
                          const slk_codebook* cb_host, int32_t moves, void* ws, size_t ws_bytes,
                          void* stream);
+/* slk_local_search_f32 that also returns err_sums [r, 2] = (channelwise_error of each row after its moves under
+ * h (obq.py:89-95), 0) -- the row-sum layout of slk_sweep_error_f32, which applies row scales and the mean.
+ * The search keeps p = (Q - W) H current, so the error is p . (Q - W): no second 2 r n^2 product. */
+int slk_local_search_err_f32(const float* w, float* q, const float* h, int64_t r, int64_t n,
+                             const slk_codebook* cb_host, int32_t moves, void* ws, size_t ws_bytes,
+                             float* err_sums, void* stream);
 /* The same moves in instalments (LocalSearchQuantizer.do_move, obq.py:338-346: one move per call): the
  * workspace keeps P = (Q - W) H between calls.  resume = 0 forms it, resume = 1 continues from the P the
  * previous call left for the same q, w, h, so a move costs one pass over the gains instead of a GEMM. */

@@ -107,6 +107,7 @@ SIGNATURES = {
     "slk_gptq_sweep_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _CB, _I32, _I32, _I32, _P]),
     "slk_local_search_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_local_search_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _P]),
+    "slk_local_search_err_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _P, _P]),
     "slk_local_search_step_f32": (_INT, [_P, _P, _P, _I64, _I64, _CB, _I32, _P, _SZ, _I32, _P]),
     "slk_row_wsq_f32": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "slk_row_wsq_f64": (_INT, [_P, _P, _I64, _I64, _P, _P]),

@@ -42,11 +42,13 @@ __device__ __forceinline__ Best warp_best(Best x) {
 __global__ void __launch_bounds__(256) local_search_kernel(float* __restrict__ Q, float* __restrict__ P,
                                                            const float* __restrict__ H, const float* __restrict__ hdiag,
                                                            int64_t r, int64_t n, DevGrid<float> g, int moves,
-                                                           int keep_p) {
+                                                           int keep_p, const float* __restrict__ W = nullptr,
+                                                           float2* __restrict__ err_sums = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* p = (float*)smem_raw;                       // [n]
   uint16_t* code = (uint16_t*)(p + n);               // [n]
   __shared__ Best red_up[8], red_dn[8];
+  __shared__ float red_err[8];
   __shared__ int s_col, s_newk;
   __shared__ float s_delta;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -100,9 +102,25 @@ __global__ void __launch_bounds__(256) local_search_kernel(float* __restrict__ Q
       if (tid == 0) code[col] = (uint16_t)s_newk;
       __syncthreads();
     }
+    float part = 0.0f;
     for (int64_t j = tid; j < n; j += blockDim.x) {
-      Q[row * n + j] = grid_value_of_index(g, code[j]);
+      const float v = grid_value_of_index(g, code[j]);
+      Q[row * n + j] = v;
       if (keep_p) P[row * n + j] = p[j];             // (Q - W) H of the row after its moves, for a later resume
+      if (err_sums) part = __fmaf_rn(p[j], __fsub_rn(v, __ldg(W + row * n + j)), part);
+    }
+    if (err_sums) {
+      // channelwise_error of the row after its moves (obq.py:89-95): ((Q - W) H) . (Q - W) = p . (Q - W); p is kept
+      // current by every move, so the 2 r n^2 product of K6 is not needed again.  Fixed order: deterministic.
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
+      if (lane == 0) red_err[wid] = part;
+      __syncthreads();
+      if (tid == 0) {
+        float tot = red_err[0];
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) tot = __fadd_rn(tot, red_err[k]);
+        err_sums[row] = make_float2(tot, 0.0f);
+      }
     }
     __syncthreads();
   }
@@ -123,11 +141,20 @@ size_t slk_local_search_ws_bytes(int64_t r, int64_t n) {
 }
 
 static int local_search_impl(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
-                             int32_t moves, void* ws, size_t ws_bytes, int resume, int keep_p, void* stream);
+                             int32_t moves, void* ws, size_t ws_bytes, int resume, int keep_p, void* stream,
+                             float* err_sums = nullptr);
 
 int slk_local_search_f32(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
                          int32_t moves, void* ws, size_t ws_bytes, void* stream) {
   return local_search_impl(w, q, h, r, n, cb, moves, ws, ws_bytes, 0, 0, stream);
+}
+
+/* The same, also returning err_sums [r, 2] = (channelwise_error of the row after its moves under h, 0): the layout
+   slk_sweep_error_f32 takes (row scales and the mean are applied there).  obq.py:89-95 without a second product. */
+int slk_local_search_err_f32(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
+                             int32_t moves, void* ws, size_t ws_bytes, float* err_sums, void* stream) {
+  SLK_REQUIRE(err_sums != nullptr && moves >= 1, "err_sums needs at least one move");
+  return local_search_impl(w, q, h, r, n, cb, moves, ws, ws_bytes, 0, 0, stream, err_sums);
 }
 
 /* The same moves in instalments (LocalSearchQuantizer.do_move, obq.py:338-346, one move per call): the
@@ -141,7 +168,8 @@ int slk_local_search_step_f32(const float* w, float* q, const float* h, int64_t 
 }  // extern "C"
 
 static int local_search_impl(const float* w, float* q, const float* h, int64_t r, int64_t n, const slk_codebook* cb,
-                             int32_t moves, void* ws, size_t ws_bytes, int resume, int keep_p, void* stream) {
+                             int32_t moves, void* ws, size_t ws_bytes, int resume, int keep_p, void* stream,
+                             float* err_sums) {
   int rc = check_codebook(cb);
   if (rc) return rc;
   SLK_REQUIRE(r >= 0 && n >= 1 && moves >= 0, "bad arguments");
@@ -175,7 +203,8 @@ static int local_search_impl(const float* w, float* q, const float* h, int64_t r
   if (smem > 48 * 1024)
     SLK_CUDA(cudaFuncSetAttribute(local_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(r < (int64_t)sm_count() * 8 ? r : (int64_t)sm_count() * 8);
-  local_search_kernel<<<grid, 256, smem, st>>>(q, P, h, hdiag, r, n, make_grid<float>(cb), moves, keep_p);
+  local_search_kernel<<<grid, 256, smem, st>>>(q, P, h, hdiag, r, n, make_grid<float>(cb), moves, keep_p, w,
+                                               reinterpret_cast<float2*>(err_sums));
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }

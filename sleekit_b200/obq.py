@@ -243,7 +243,12 @@ def gptq_finish(st, factor=None, check=False):
     if check:
         _raise_if_not_pd(info)
     if nb_ls_moves:
-        ops.local_search(st.Wd, Q, Hd, quantizer, nb_ls_moves)            # obq.py:216
+        if want_err and USE_SWEEP_ERROR:
+            # the search keeps p = (Q - W) H current: the rows' errors are p . (Q - W), no K6 product afterwards
+            sums = torch.empty((Q.shape[0], 2), dtype=torch.float32, device=Q.device)
+        ops.local_search(st.Wd, Q, Hd, quantizer, nb_ls_moves, err_sums=sums)   # obq.py:216
+        if sums is not None:
+            err = ops.sweep_error(sums, row_scale, None, want_rows=True)
     if row_scale is not None:
         Q = ops.scale_rows(Q, row_scale, 1)                               # scaling.py:80
     if want_err:
@@ -263,7 +268,8 @@ def gptq_device(Wd, Hd, quantizer, act_order="diag", damp=0.01, nb_ls_moves=0, m
     want_err: also return (mean layer error [1], row errors [r]) = quantization_error / channelwise_error
     (obq.py:89-103) of the returned weights against Wd under Hd, taken from the sweep's residuals
     (sum E^2 - damp * sum (W-Q)^2, ops.sweep_error) when the factor-form sweep ran and no local-search
-    move follows, from the K6 product otherwise.  (The residual form subtracts two fp32 row sums: when
+    move follows, from the local search's own p = (Q - W) H after its moves (p . (Q - W) per row), from the
+    K6 product otherwise.  (The residual form subtracts two fp32 row sums: when
     delta H delta is smaller than ~1e-6 of damp * |delta|^2 -- a Hessian of much lower rank than n under a large
     damp -- it cancels; call channelwise_error for such inputs.  Measured agreement with the product on the
     rank-deficient bench layers: 1.4e-5.)  factor_fn(Hd, order, dampval) -> (r32, rt32, ud32,

@@ -797,19 +797,27 @@ def local_search_step(w, q, h, cb, moves, state):
 
 
 @_timed("local_search")
-def local_search(w, q, h, cb, moves):
-    """In place on q (values on the codebook)."""
+def local_search(w, q, h, cb, moves, err_sums=None):
+    """In place on q (values on the codebook).  err_sums: optional [rows, 2] fp32 tensor that receives
+    (channelwise_error of the row after its moves, 0), the layout sweep_error() takes (moves >= 1)."""
     cb = device_codebook(cb)
     _chk(w, torch.float32)
     _chk(q, torch.float32)
     _chk(h, torch.float32)
     if moves <= 0:
+        assert err_sums is None, "the row errors come out of the moves"
         return q
     r, n = w.shape
     lib = _lib.load()
     nbytes = lib.slk_local_search_ws_bytes(r, n)
     ws = _ws(nbytes, w.device)
-    _call("slk_local_search_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(ws), nbytes, _stream())
+    if err_sums is not None:
+        _chk(err_sums, torch.float32)
+        assert err_sums.shape == (r, 2)
+        _call("slk_local_search_err_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(ws), nbytes,
+              _ptr(err_sums), _stream())
+    else:
+        _call("slk_local_search_f32", _ptr(w), _ptr(q), _ptr(h), r, n, cb.ref, int(moves), _ptr(ws), nbytes, _stream())
     return q
 
 

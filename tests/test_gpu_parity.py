@@ -508,6 +508,35 @@ def test_layer_error_from_sweep_residuals_equals_product(slk, r, n, c, rule, sam
         assert rel(err, e_ref) <= 1e-4
 
 
+@pytest.mark.parametrize("r,n,c,moves", [(64, 1024, 4, 10), (24, 4096, 16, 10), (40, 300, 3, 50)])
+def test_layer_error_after_local_search_equals_product(slk, r, n, c, moves):
+    """gptq_device(want_err=True, nb_ls_moves > 0): the row errors taken from the local search's own
+    p = (Q - W) H after its moves (p . (Q - W), local_search.cu) against the explicit K6 product and the
+    oracle's quantization_error (obq.py:89-103) on the same weights, with and without row scales."""
+    from sleekit_b200 import _convert as cv
+
+    W, H, m = wl.synthetic_layer(r, n, 17, samples=max(256, n // 2))
+    cb, grid = slk.codebook.UniformCodebook(c, -1, 1), orc.UniformGrid(c, -1, 1)
+    sc = orc.search_scale(W, grid, 0, H=H.diagonal())
+    Wd, Hd, sd = cv.to_dev(W, torch.float32), cv.to_dev(H, torch.float32), cv.to_dev(sc, torch.float32)
+    for scaled in (True, False):
+        args = dict(row_scale=sd if scaled else None, want_err=True, nb_ls_moves=moves)
+        q, (err, rows) = slk.obq.gptq_device(Wd, Hd, cb, "diag", 0.01, **args)
+        old, slk.obq.USE_SWEEP_ERROR = slk.obq.USE_SWEEP_ERROR, False
+        try:
+            q2, (err2, rows2) = slk.obq.gptq_device(Wd, Hd, cb, "diag", 0.01, **args)
+        finally:
+            slk.obq.USE_SWEEP_ERROR = old
+        assert torch.equal(q, q2)
+        rows, rows2 = rows.cpu().numpy(), rows2.cpu().numpy()
+        worst = float(np.max(np.abs(rows - rows2) / np.abs(rows2)))
+        e_ref = orc.mean_error(W, q.cpu().numpy(), H)
+        print(f"[{r}x{n} c={c} scaled={scaled}] error {float(err):.6e} product {float(err2):.6e} oracle {e_ref:.6e} "
+              f"worst row {worst:.2e}")
+        assert rel(err, err2) <= 2e-5 and worst <= 1e-4
+        assert rel(err, e_ref) <= 1e-4
+
+
 def test_factor_not_positive_definite_raises(slk):
     H = np.eye(70)
     H[40, 40] = -1.0
