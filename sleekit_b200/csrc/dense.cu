@@ -371,6 +371,208 @@ static inline int fullh_chunk(int64_t r, int64_t n, int G, size_t elem) {
   return (int)per;
 }
 
+// Workspace of the full-H search; one layout for the size query (ws == nullptr) and the entry point.
+struct FullhWs {
+  int chunk;                // grid points per exact GEMM launch
+  int64_t tiles;            // row-dot partials per row of the CUDA-core GEMM
+  void *resid, *part, *errs;
+  float *init, *best_err, *best_f;
+  float *rhi, *rlo, *hhi, *hlo;                  // tensor-core path: TF32 parts of the residuals and of H
+  float *errs_all, *part_s;                      // screening: ranking values [G, r], their row-dot partials
+  int *cand, *best_g, *offsets, *pair_row, *pair_g;
+  __nv_bfloat16* hbf;
+  size_t bytes;
+};
+
+static FullhWs fullh_layout(void* ws, int64_t r, int64_t n, int G, int h_dtype) {
+  FullhWs L = {};
+  const size_t elem = h_dtype == 2 ? 8 : 4;
+  L.chunk = fullh_chunk(r, n, G, elem);
+  L.tiles = h_dtype == 2 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    char* p = ws ? (char*)ws + off : nullptr;
+    off += align256(b);
+    return p;
+  };
+  const size_t chunk = (size_t)L.chunk, pairs = (size_t)FULLH_TOPK_MAX * r + 2;
+  L.resid = take(chunk * r * n * elem);
+  L.part = take(chunk * r * L.tiles * elem);
+  L.errs = take(chunk * r * elem);
+  L.init = (float*)take((size_t)r * 4);
+  L.best_err = (float*)take((size_t)r * 4);
+  L.best_f = (float*)take((size_t)r * 4);
+  if (h_dtype == 1 && n % 4 == 0) {
+    L.rhi = (float*)take(chunk * r * n * 4);     // rhi | rlo: also the 2 * chunk grid points of a ranking pass
+    L.rlo = (float*)take(chunk * r * n * 4);
+    L.hhi = (float*)take((size_t)n * n * 4);
+    L.hlo = (float*)take((size_t)n * n * 4);
+    L.errs_all = (float*)take((size_t)G * r * 4);
+    L.cand = (int*)take((size_t)FULLH_TOPK_MAX * r * 4);
+    L.best_g = (int*)take((size_t)r * 4);
+    L.part_s = (float*)take(2 * chunk * r * ceil_div(n, TC_TILE_N) * 4);
+    L.hbf = (__nv_bfloat16*)take((size_t)n * n * 2);
+    L.offsets = (int*)take(pairs * 4);
+    L.pair_row = (int*)take(pairs * 4);
+    L.pair_g = (int*)take(pairs * 4);
+  }
+  L.bytes = off;
+  return L;
+}
+
+struct FullhCtx {
+  const float* w; int64_t r, n; DevGrid<float> g; const float* factors; int G; const void* h; int h_dtype;
+  bool tc; cudaStream_t st; FullhWs L;
+};
+
+static inline int resid_blocks(int64_t pairs) {    // one CTA per (grid point, row) pair, grid-stride beyond 64 per SM
+  const int64_t cap = (int64_t)sm_count() * 64;
+  return (int)(pairs < cap ? pairs : cap);
+}
+
+// errs[0 .. rows) = e H e^T of the fp32 residual rows in L.resid / rhi / rlo: the fp32-faithful product with the
+// row dot in its epilogue (H symmetric: its own K-major B operand), partials reduced in fixed order.  m_limit:
+// device-side row count (row tiles beyond it exit).
+static int fullh_exact_errors(const FullhCtx& c, int64_t rows, const int* m_limit) {
+  const int64_t tiles = ceil_div(c.n, TC_TILE_N);
+  TcParams tp;
+  tp.C = (float*)c.L.part; tp.ldc = tiles; tp.R = (const float*)c.L.resid; tp.R2 = nullptr; tp.ldr = c.n;
+  tp.M = rows; tp.N = c.n; tp.K = c.n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+  tp.m_limit = m_limit;
+  int rc = tc_gemm_presplit_f32(TC_ROWDOT, c.L.rhi, c.L.rlo, c.n, c.L.hhi, c.L.hlo, c.n, tp, c.st);
+  if (rc) return rc;
+  rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, c.st>>>((const float*)c.L.part, rows, tiles,
+                                                                          (float*)c.L.errs);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+// 1. ranking values of all G grid points into L.errs_all [G, r]: bf16 residuals against a bf16 H (kind::f16), or,
+//    when n % 8 != 0, TF32-rounded residuals against the truncated H (one kind::tf32 pass); 2 * chunk grid
+//    points per launch, in the rhi | rlo region
+static int fullh_rank(const FullhCtx& c) {
+  const FullhWs& L = c.L;
+  const int bn = g_opt_fullh_bn == 128 ? 128 : 256, ctas = (int)g_opt_fullh_ctas;
+  const bool bf16 = g_opt_fullh_bf16 != 0 && c.n % 8 == 0;
+  const int64_t tiles_s = ceil_div(c.n, bn);
+  const int chunk_s = 2 * L.chunk < c.G ? 2 * L.chunk : c.G;
+  if (bf16) {
+    to_bf16_kernel<<<resid_blocks(ceil_div(c.n * c.n, 256)), 256, 0, c.st>>>((const float*)c.h, c.n * c.n, L.hbf);
+    SLK_LAUNCH_CHECK();
+  }
+  for (int g0 = 0; g0 < c.G; g0 += chunk_s) {
+    const int gc = (c.G - g0) < chunk_s ? (c.G - g0) : chunk_s;
+    const int64_t rows = (int64_t)gc * c.r;
+    if (bf16)
+      grid_resid_kernel<float, 2><<<resid_blocks(rows), 128, 0, c.st>>>(c.w, c.r, c.n, c.g, c.factors, g0, gc, L.init, L.rhi);
+    else
+      grid_resid_kernel<float, 1><<<resid_blocks(rows), 128, 0, c.st>>>(c.w, c.r, c.n, c.g, c.factors, g0, gc, L.init, L.rhi);
+    SLK_LAUNCH_CHECK();
+    TcParams tp;
+    tp.C = L.part_s; tp.ldc = tiles_s; tp.R = L.rhi; tp.R2 = nullptr; tp.ldr = c.n;
+    tp.M = rows; tp.N = c.n; tp.K = c.n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
+    int rc = bf16 ? tc_gemm_screen_bf16(L.rhi, c.n, L.hbf, c.n, tp, bn, ctas, c.st)
+                  : tc_gemm_screen_f32(L.rhi, c.n, L.hhi, c.n, tp, bn, ctas, c.st);
+    if (rc) return rc;
+    rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, c.st>>>(L.part_s, rows, tiles_s,
+                                                                            L.errs_all + (int64_t)g0 * c.r);
+    SLK_LAUNCH_CHECK();
+  }
+  return SLK_OK;
+}
+
+// 2a. compacted candidates (screen_select_kernel): at most topk * r (row, grid point) pairs evaluated exactly by one
+//     product whose row tiles beyond the device-side pair count exit at once
+static int fullh_eval_pairs(const FullhCtx& c, int topk) {
+  const FullhWs& L = c.L;
+  const int cap = (int)((int64_t)topk * c.r);
+  int* count = L.best_g;
+  screen_select_kernel<FULLH_TOPK_MAX><<<(int)ceil_div(c.r, 128), 128, 0, c.st>>>(L.errs_all, c.r, c.G, 0.03125f, L.cand, count);
+  SLK_LAUNCH_CHECK();
+  screen_pairs_kernel<<<1, 1024, 0, c.st>>>(count, L.cand, c.r, cap, L.offsets, L.pair_row, L.pair_g);
+  SLK_LAUNCH_CHECK();
+  const int* npairs = L.offsets + c.r;
+  grid_resid_kernel<float><<<resid_blocks(cap), 128, 0, c.st>>>(c.w, c.r, c.n, c.g, c.factors, 0, topk, L.init, (float*)L.resid,
+                                                                L.rhi, L.rlo, L.pair_g, L.pair_row, npairs);
+  SLK_LAUNCH_CHECK();
+  int rc = fullh_exact_errors(c, cap, npairs);
+  if (rc) return rc;
+  pairs_argmin_kernel<<<(int)ceil_div(c.r, 256), 256, 0, c.st>>>((const float*)L.errs, L.pair_g, L.offsets, c.r, c.factors,
+                                                                 L.best_err, L.best_f);
+  SLK_LAUNCH_CHECK();
+  return SLK_OK;
+}
+
+// 2b. a fixed topk candidates per row, `chunk` slots per product (also the path of layers whose residuals do not
+//     fit topk at a time)
+static int fullh_eval_slots(const FullhCtx& c, int topk) {
+  const FullhWs& L = c.L;
+  const int rb = (int)ceil_div(c.r, 128);
+  if (topk == 4) screen_topk_kernel<4><<<rb, 128, 0, c.st>>>(L.errs_all, c.r, c.G, L.cand);
+  else if (topk == 8) screen_topk_kernel<8><<<rb, 128, 0, c.st>>>(L.errs_all, c.r, c.G, L.cand);
+  else screen_topk_kernel<16><<<rb, 128, 0, c.st>>>(L.errs_all, c.r, c.G, L.cand);
+  SLK_LAUNCH_CHECK();
+  fill_int_kernel<<<(int)ceil_div(c.r, 256), 256, 0, c.st>>>(L.best_g, -1, c.r);
+  SLK_LAUNCH_CHECK();
+  for (int s0 = 0; s0 < topk; s0 += L.chunk) {
+    const int sc = (topk - s0) < L.chunk ? (topk - s0) : L.chunk;
+    const int64_t rows = (int64_t)sc * c.r;
+    const int* cs = L.cand + (int64_t)s0 * c.r;
+    grid_resid_kernel<float><<<resid_blocks(rows), 128, 0, c.st>>>(c.w, c.r, c.n, c.g, c.factors, 0, sc, L.init, (float*)L.resid,
+                                                                   L.rhi, L.rlo, cs);
+    SLK_LAUNCH_CHECK();
+    int rc = fullh_exact_errors(c, rows, nullptr);
+    if (rc) return rc;
+    cand_argmin_kernel<<<(int)ceil_div(c.r, 256), 256, 0, c.st>>>((const float*)L.errs, cs, c.r, sc, c.factors, L.best_err,
+                                                                  L.best_f, L.best_g);
+    SLK_LAUNCH_CHECK();
+  }
+  return SLK_OK;
+}
+
+// every grid point evaluated exactly, `chunk` points per product: the reference's loop (scaling.py:125-134)
+static int fullh_all_points(const FullhCtx& c) {
+  const FullhWs& L = c.L;
+  const int rb = (int)ceil_div(c.r, 256);
+  for (int g0 = 0; g0 < c.G; g0 += L.chunk) {
+    const int gc = (c.G - g0) < L.chunk ? (c.G - g0) : L.chunk;
+    const int64_t rows = (int64_t)gc * c.r;
+    const int blocks = resid_blocks(rows);
+    int rc;
+    if (c.h_dtype == 1) {
+      grid_resid_kernel<float><<<blocks, 128, 0, c.st>>>(c.w, c.r, c.n, c.g, c.factors, g0, gc, L.init, (float*)L.resid,
+                                                         c.tc ? L.rhi : nullptr, c.tc ? L.rlo : nullptr);
+      SLK_LAUNCH_CHECK();
+      if (c.tc) {
+        rc = fullh_exact_errors(c, rows, nullptr);
+        if (rc) return rc;
+      } else {
+        GemmParams<float> p = gemm_params<float>((const float*)L.resid, c.n, (const float*)c.h, c.n, (float*)L.part, 0, rows,
+                                                 c.n, c.n);
+        rc = gemm_launch<float, false, false, EPI_ROWDOT>(p, 1, c.st);
+        if (rc) return rc;
+        rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, c.st>>>((const float*)L.part, rows, L.tiles,
+                                                                                (float*)L.errs);
+        SLK_LAUNCH_CHECK();
+      }
+      grid_argmin_kernel<float><<<rb, 256, 0, c.st>>>((const float*)L.errs, c.r, g0, gc, c.factors, L.best_err, L.best_f);
+    } else {
+      grid_resid_kernel<double><<<blocks, 128, 0, c.st>>>(c.w, c.r, c.n, c.g, c.factors, g0, gc, L.init, (double*)L.resid);
+      SLK_LAUNCH_CHECK();
+      GemmParams<double> p = gemm_params<double>((const double*)L.resid, c.n, (const double*)c.h, c.n, (double*)L.part, 0,
+                                                 rows, c.n, c.n);
+      rc = gemm_launch<double, false, false, EPI_ROWDOT>(p, 1, c.st);
+      if (rc) return rc;
+      rowdot_reduce_kernel<double><<<(int)ceil_div(rows, 256), 256, 0, c.st>>>((const double*)L.part, rows, L.tiles,
+                                                                               (double*)L.errs);
+      SLK_LAUNCH_CHECK();
+      grid_argmin_kernel<double><<<rb, 256, 0, c.st>>>((const double*)L.errs, c.r, g0, gc, c.factors, L.best_err, L.best_f);
+    }
+    SLK_LAUNCH_CHECK();
+  }
+  return SLK_OK;
+}
+
 }  // namespace slk
 
 using namespace slk;
@@ -442,22 +644,7 @@ int slk_hessian_accum_f32(const float* x, int64_t S, int64_t n, int64_t ldx, flo
 }
 
 size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t h_dtype) {
-  size_t elem = h_dtype == 2 ? 8 : 4;
-  int chunk = fullh_chunk(r, n, G, elem);
-  int64_t tiles = h_dtype == 2 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
-  size_t bytes = 0;
-  bytes += align256((size_t)chunk * r * n * elem);       // residuals
-  bytes += align256((size_t)chunk * r * tiles * elem);   // row-dot partials
-  bytes += align256((size_t)chunk * r * elem);           // errors
-  bytes += 3 * align256((size_t)r * sizeof(float));      // init, best_err, best_f
-  if (h_dtype == 1 && n % 4 == 0) {                      // tensor-core path: TF32 parts of the residuals and of H
-    bytes += 2 * align256((size_t)chunk * r * n * 4) + 2 * align256((size_t)n * n * 4);
-    // screening: errors of all grid points, candidate lists, best index, row-dot partials of 2 * chunk points
-    bytes += align256((size_t)G * r * 4) + align256((size_t)FULLH_TOPK_MAX * r * 4) + align256((size_t)r * 4) +
-             align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4) + align256((size_t)n * n * 2) +
-             3 * align256((size_t)(FULLH_TOPK_MAX * r + 2) * 4);   // row counts / offsets, pair rows, pair grid points
-  }
-  return bytes;
+  return fullh_layout(nullptr, r, n, G, h_dtype).bytes;
 }
 
 int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb, const float* factors,
@@ -467,171 +654,32 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
   if (rc) return rc;
   SLK_REQUIRE(w && factors && h && out_scale && r >= 1 && n >= 1 && G >= 1, "bad arguments");
   SLK_REQUIRE(h_dtype == 1 || h_dtype == 2, "h_dtype %d", h_dtype);
-  SLK_REQUIRE(ws && ws_bytes >= slk_scale_search_fullh_ws_bytes(r, n, G, h_dtype), "workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t elem = h_dtype == 2 ? 8 : 4;
-  const int chunk = fullh_chunk(r, n, G, elem);
-  const int64_t tiles = h_dtype == 2 ? rowdot_tiles<double>(n) : rowdot_tiles<float>(n);
-  char* base = (char*)ws;
-  void* resid = base; base += align256((size_t)chunk * r * n * elem);
-  void* part = base; base += align256((size_t)chunk * r * tiles * elem);
-  void* errs = base; base += align256((size_t)chunk * r * elem);
-  float* init = (float*)base; base += align256((size_t)r * sizeof(float));
-  float* best_err = (float*)base; base += align256((size_t)r * sizeof(float));
-  float* best_f = (float*)base; base += align256((size_t)r * sizeof(float));
+  FullhCtx c;
+  c.L = fullh_layout(ws, r, n, G, h_dtype);
+  SLK_REQUIRE(ws && ws_bytes >= c.L.bytes, "workspace too small");
+  c.w = w; c.r = r; c.n = n; c.g = make_grid<float>(cb); c.factors = factors; c.G = G; c.h = h; c.h_dtype = h_dtype;
+  c.st = (cudaStream_t)stream;
   // tensor-core path (fp32 H): residuals are written with their TF32 parts, H is split once
-  const bool tc = h_dtype == 1 && n % 4 == 0 && n >= 32 && tc_gemm_usable(resid, n, h, n);
-  float *rhi = nullptr, *rlo = nullptr, *hhi = nullptr, *hlo = nullptr;
-  if (tc) {
-    rhi = (float*)base; base += align256((size_t)chunk * r * n * 4);
-    rlo = (float*)base; base += align256((size_t)chunk * r * n * 4);
-    hhi = (float*)base; base += align256((size_t)n * n * 4);
-    hlo = (float*)base; base += align256((size_t)n * n * 4);
-    rc = tc_split_f32((const float*)h, n, n, n, n, hhi, hlo, st);
+  c.tc = c.L.rhi != nullptr && n >= 32 && tc_gemm_usable(c.L.resid, n, h, n);
+  if (c.tc) {
+    rc = tc_split_f32((const float*)h, n, n, n, n, c.L.hhi, c.L.hlo, c.st);
     if (rc) return rc;
   }
-  const int topk = tc ? (int)g_opt_fullh_topk : 0;
-  const bool screen = tc && (topk == 4 || topk == 8 || topk == 16) && G >= 4 * topk;
-  float *errs_all = nullptr, *part_s = nullptr;
-  int *cand = nullptr, *best_g = nullptr;
-  __nv_bfloat16* hbf = nullptr;
-  int *offsets = nullptr, *pair_row = nullptr, *pair_g = nullptr;
-  if (screen) {
-    errs_all = (float*)base; base += align256((size_t)G * r * 4);
-    cand = (int*)base; base += align256((size_t)FULLH_TOPK_MAX * r * 4);
-    best_g = (int*)base; base += align256((size_t)r * 4);
-    part_s = (float*)base; base += align256((size_t)2 * chunk * r * ceil_div(n, TC_TILE_N) * 4);
-    hbf = (__nv_bfloat16*)base; base += align256((size_t)n * n * 2);
-    offsets = (int*)base; base += align256((size_t)(FULLH_TOPK_MAX * r + 2) * 4);
-    pair_row = (int*)base; base += align256((size_t)(FULLH_TOPK_MAX * r + 2) * 4);
-    pair_g = (int*)base;
-  }
-
-  rc = slk_row_noclip_scale_f32(w, r, n, cb->lo, cb->hi, init, stream);
+  rc = slk_row_noclip_scale_f32(w, r, n, cb->lo, cb->hi, c.L.init, stream);
   if (rc) return rc;
-  fill_inf_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(best_err, best_f, r);
+  fill_inf_kernel<<<(int)ceil_div(r, 256), 256, 0, c.st>>>(c.L.best_err, c.L.best_f, r);
   SLK_LAUNCH_CHECK();
-  DevGrid<float> g = make_grid<float>(cb);
-  auto resid_blocks = [](int64_t pairs) {           // one CTA per (grid point, row) pair, grid-stride beyond 64 per SM
-    const int64_t cap = (int64_t)sm_count() * 64;
-    return (int)(pairs < cap ? pairs : cap);
-  };
-  if (screen) {
-    // 1. rank all grid points with one TF32 pass: TF32-rounded residuals (one array over the rhi | rlo region,
-    //    2 * chunk grid points at a time) against the truncated H
-    const int bn = g_opt_fullh_bn == 128 ? 128 : 256;
-    const bool bf16 = g_opt_fullh_bf16 != 0 && n % 8 == 0;
-    const int64_t tiles_s = ceil_div(n, bn);
-    const int chunk_s = 2 * chunk < G ? 2 * chunk : G;
-    if (bf16) {
-      to_bf16_kernel<<<resid_blocks(ceil_div(n * n, 256)), 256, 0, st>>>((const float*)h, n * n, hbf);
-      SLK_LAUNCH_CHECK();
-    }
-    for (int g0 = 0; g0 < G; g0 += chunk_s) {
-      const int gc = (G - g0) < chunk_s ? (G - g0) : chunk_s;
-      const int64_t rows = (int64_t)gc * r;
-      if (bf16) grid_resid_kernel<float, 2><<<resid_blocks(rows), 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, rhi);
-      else grid_resid_kernel<float, 1><<<resid_blocks(rows), 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, rhi);
-      SLK_LAUNCH_CHECK();
-      TcParams tp;
-      tp.C = part_s; tp.ldc = tiles_s; tp.R = rhi; tp.R2 = nullptr; tp.ldr = n;
-      tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
-      rc = bf16 ? tc_gemm_screen_bf16(rhi, n, hbf, n, tp, bn, (int)g_opt_fullh_ctas, st)
-                : tc_gemm_screen_f32(rhi, n, hhi, n, tp, bn, (int)g_opt_fullh_ctas, st);
-      if (rc) return rc;
-      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>(part_s, rows, tiles_s, errs_all + (int64_t)g0 * r);
-      SLK_LAUNCH_CHECK();
-    }
-    if (g_opt_fullh_compact && topk <= chunk && (int64_t)topk * r < (1ll << 30)) {
-      // 2a. compacted candidates (see screen_select_kernel): capacity topk * r pairs, GEMM row tiles beyond the
-      //     device-side pair count exit at once
-      const int cap = (int)((int64_t)topk * r);
-      int* count = best_g;
-      screen_select_kernel<FULLH_TOPK_MAX><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, 0.03125f, cand, count);
-      SLK_LAUNCH_CHECK();
-      screen_pairs_kernel<<<1, 1024, 0, st>>>(count, cand, r, cap, offsets, pair_row, pair_g);
-      SLK_LAUNCH_CHECK();
-      grid_resid_kernel<float><<<resid_blocks(cap), 128, 0, st>>>(w, r, n, g, factors, 0, topk, init, (float*)resid, rhi, rlo,
-                                                                  pair_g, pair_row, offsets + r);
-      SLK_LAUNCH_CHECK();
-      TcParams tp;
-      tp.C = (float*)part; tp.ldc = ceil_div(n, TC_TILE_N); tp.R = (const float*)resid; tp.R2 = nullptr; tp.ldr = n;
-      tp.M = cap; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
-      tp.m_limit = offsets + r;
-      rc = tc_gemm_presplit_f32(TC_ROWDOT, rhi, rlo, n, hhi, hlo, n, tp, st);
-      if (rc) return rc;
-      rowdot_reduce_kernel<float><<<(int)ceil_div(cap, 256), 256, 0, st>>>((const float*)part, cap, ceil_div(n, TC_TILE_N),
-                                                                          (float*)errs);
-      SLK_LAUNCH_CHECK();
-      pairs_argmin_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, pair_g, offsets, r, factors, best_err,
-                                                                 best_f);
-      SLK_LAUNCH_CHECK();
-      finish_scale_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(init, best_f, best_err, r, out_scale, out_err);
-      SLK_LAUNCH_CHECK();
-      return SLK_OK;
-    }
-    if (topk == 4) screen_topk_kernel<4><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
-    else if (topk == 8) screen_topk_kernel<8><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
-    else screen_topk_kernel<16><<<(int)ceil_div(r, 128), 128, 0, st>>>(errs_all, r, G, cand);
-    SLK_LAUNCH_CHECK();
-    fill_int_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(best_g, -1, r);
-    SLK_LAUNCH_CHECK();
-    // 2. the candidates, exactly as the unscreened path evaluates a grid point
-    for (int s0 = 0; s0 < topk; s0 += chunk) {
-      const int sc = (topk - s0) < chunk ? (topk - s0) : chunk;
-      const int64_t rows = (int64_t)sc * r;
-      const int* cs = cand + (int64_t)s0 * r;
-      grid_resid_kernel<float><<<resid_blocks(rows), 128, 0, st>>>(w, r, n, g, factors, 0, sc, init, (float*)resid,
-                                                                      rhi, rlo, cs);
-      SLK_LAUNCH_CHECK();
-      TcParams tp;
-      tp.C = (float*)part; tp.ldc = ceil_div(n, TC_TILE_N); tp.R = (const float*)resid; tp.R2 = nullptr; tp.ldr = n;
-      tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
-      rc = tc_gemm_presplit_f32(TC_ROWDOT, rhi, rlo, n, hhi, hlo, n, tp, st);
-      if (rc) return rc;
-      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const float*)part, rows, ceil_div(n, TC_TILE_N),
-                                                                           (float*)errs);
-      SLK_LAUNCH_CHECK();
-      cand_argmin_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, cs, r, sc, factors, best_err, best_f,
-                                                                best_g);
-      SLK_LAUNCH_CHECK();
-    }
+  const int topk = c.tc ? (int)g_opt_fullh_topk : 0;
+  if ((topk == 4 || topk == 8 || topk == 16) && G >= 4 * topk) {
+    rc = fullh_rank(c);
+    if (rc) return rc;
+    const bool compact = g_opt_fullh_compact && topk <= c.L.chunk && (int64_t)topk * r < (1ll << 30);
+    rc = compact ? fullh_eval_pairs(c, topk) : fullh_eval_slots(c, topk);
+  } else {
+    rc = fullh_all_points(c);
   }
-  for (int g0 = 0; g0 < G && !screen; g0 += chunk) {
-    const int gc = (G - g0) < chunk ? (G - g0) : chunk;
-    const int64_t rows = (int64_t)gc * r;
-    const int blocks = resid_blocks(rows);
-    if (h_dtype == 1) {
-      grid_resid_kernel<float><<<blocks, 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, (float*)resid, rhi, rlo);
-      SLK_LAUNCH_CHECK();
-      if (tc) {
-        // (E H) . E per row on tcgen05: H symmetric, hence its own K-major B operand; row dot in the epilogue
-        TcParams tp;
-        tp.C = (float*)part; tp.ldc = ceil_div(n, TC_TILE_N); tp.R = (const float*)resid; tp.R2 = nullptr; tp.ldr = n;
-        tp.M = rows; tp.N = n; tp.K = n; tp.alpha = 1.0f; tp.keep = 0.0f; tp.count = 1.0f; tp.error_flag = nullptr;
-        rc = tc_gemm_presplit_f32(TC_ROWDOT, rhi, rlo, n, hhi, hlo, n, tp, st);
-      } else {
-        GemmParams<float> p = gemm_params<float>((const float*)resid, n, (const float*)h, n, (float*)part, 0, rows, n, n);
-        rc = gemm_launch<float, false, false, EPI_ROWDOT>(p, 1, st);
-      }
-      if (rc) return rc;
-      rowdot_reduce_kernel<float><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const float*)part, rows,
-                                                                           tc ? ceil_div(n, TC_TILE_N) : tiles, (float*)errs);
-      SLK_LAUNCH_CHECK();
-      grid_argmin_kernel<float><<<(int)ceil_div(r, 256), 256, 0, st>>>((const float*)errs, r, g0, gc, factors, best_err, best_f);
-    } else {
-      grid_resid_kernel<double><<<blocks, 128, 0, st>>>(w, r, n, g, factors, g0, gc, init, (double*)resid);
-      SLK_LAUNCH_CHECK();
-      GemmParams<double> p = gemm_params<double>((const double*)resid, n, (const double*)h, n, (double*)part, 0, rows, n, n);
-      rc = gemm_launch<double, false, false, EPI_ROWDOT>(p, 1, st);
-      if (rc) return rc;
-      rowdot_reduce_kernel<double><<<(int)ceil_div(rows, 256), 256, 0, st>>>((const double*)part, rows, tiles, (double*)errs);
-      SLK_LAUNCH_CHECK();
-      grid_argmin_kernel<double><<<(int)ceil_div(r, 256), 256, 0, st>>>((const double*)errs, r, g0, gc, factors, best_err, best_f);
-    }
-    SLK_LAUNCH_CHECK();
-  }
-  finish_scale_kernel<<<(int)ceil_div(r, 256), 256, 0, st>>>(init, best_f, best_err, r, out_scale, out_err);
+  if (rc) return rc;
+  finish_scale_kernel<<<(int)ceil_div(r, 256), 256, 0, c.st>>>(c.L.init, c.L.best_f, c.L.best_err, r, out_scale, out_err);
   SLK_LAUNCH_CHECK();
   return SLK_OK;
 }
