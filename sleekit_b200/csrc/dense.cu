@@ -274,37 +274,49 @@ __global__ void __launch_bounds__(128) screen_select_kernel(const float* __restr
   count[row] = c;
 }
 
-// offsets[row] = min(capacity, sum of count[0..row)), offsets[r] = total pairs (one CTA: r is a layer's row count),
-// then the pair lists in row order
+// offsets[row] = pairs before the row, offsets[r] = total pairs (one CTA: r is a layer's row count), then the pair
+// lists in row order.  If the rows ask for more than `capacity` pairs in total (flat error landscapes, e.g. many
+// all-zero rows whose grid points all tie), every row is cut to its capacity / r best-ranked candidates, so the
+// total fits and no row is left without its best ones.
 __global__ void __launch_bounds__(1024) screen_pairs_kernel(const int* __restrict__ count, const int* __restrict__ cand,
                                                             int64_t r, int capacity, int* __restrict__ offsets,
                                                             int* __restrict__ pair_row, int* __restrict__ pair_g) {
   __shared__ int part[1024];
+  __shared__ int s_limit;
   const int t = threadIdx.x;
   const int64_t per = (r + 1023) / 1024;
   const int64_t lo = t * per, hi = lo + per < r ? lo + per : r;
-  int s = 0;
-  for (int64_t i = lo; i < hi; ++i) s += count[i];
-  part[t] = s;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {        // inclusive scan of the per-thread sums
-    const int v = t >= d ? part[t - d] : 0;
+  const int per_row = (int)(capacity / r) > 0 ? (int)(capacity / r) : 1;
+  int limit = 0x7fffffff;
+  for (int pass = 0; pass < 2; ++pass) {
+    int s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += min(count[i], limit);
+    part[t] = s;
     __syncthreads();
-    part[t] += v;
+    for (int d = 1; d < 1024; d <<= 1) {        // inclusive scan of the per-thread sums
+      const int v = t >= d ? part[t - d] : 0;
+      __syncthreads();
+      part[t] += v;
+      __syncthreads();
+    }
+    if (t == 0) s_limit = part[1023] > capacity ? per_row : limit;
     __syncthreads();
+    const bool again = s_limit != limit;
+    limit = s_limit;
+    if (!again) break;                          // uniform: s_limit is the same for every thread
+    __syncthreads();                            // part[] is rewritten by the second pass
   }
   int run = t ? part[t - 1] : 0;
   for (int64_t i = lo; i < hi; ++i) {
-    const int b = run < capacity ? run : capacity;
-    run += count[i];
-    const int e = run < capacity ? run : capacity;
-    offsets[i] = b;
-    for (int k = b; k < e; ++k) {
-      pair_row[k] = (int)i;
-      pair_g[k] = cand[(int64_t)(k - b) * r + i];
+    const int c = min(count[i], limit);
+    offsets[i] = run;
+    for (int k = 0; k < c; ++k) {
+      pair_row[run + k] = (int)i;
+      pair_g[run + k] = cand[(int64_t)k * r + i];
     }
+    run += c;
   }
-  if (t == 1023) offsets[r] = part[1023] < capacity ? part[1023] : capacity;
+  if (t == 1023) offsets[r] = part[1023];
 }
 
 __global__ void __launch_bounds__(256) pairs_argmin_kernel(const float* __restrict__ err, const int* __restrict__ pair_g,

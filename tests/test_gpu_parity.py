@@ -319,6 +319,39 @@ def test_full_h_search_screening_is_exact(slk, r, n, c, samples):
                       f"[{r},{n}] c={c}")
 
 
+def test_full_h_search_screening_many_flat_rows(slk):
+    """Rows whose grid points all tie (all-zero rows of a pruned layer) ask for the maximum number of
+    candidates each; when that exceeds the candidate capacity every row is cut to its best-ranked ones
+    (screen_pairs_kernel) -- no row may be left without candidates, and the result stays bit-identical to
+    evaluating every grid point (the first grid point wins the ties, scaling.py:131)."""
+    from sleekit_b200 import ops, _convert as cv
+    from sleekit_b200.scaling import _factors
+
+    r, n = 300, 1024
+    W, H, m = wl.synthetic_layer(r, n, 29, samples=1024)
+    W[20:260] = 0.0                                   # 80 % of the rows
+    W[5, ::2] = 0.0
+    for c in (3, 8):
+        cb = slk.codebook.UniformCodebook(c, -1, 1)
+        Wd, Hd = cv.to_dev(W, torch.float32), cv.to_dev(H, torch.float32)
+        f = _factors(0.05, 1.0, 100, Wd.device)
+        res = {}
+        try:
+            for topk in (0, 4, 8, 16):
+                ops.set_option("fullh_topk", topk)
+                sc, err = ops.scale_search_fullh(Wd, cb, f, Hd, want_err=True)
+                res[topk] = (sc.cpu().numpy(), err.cpu().numpy())
+        finally:
+            ops.set_option("fullh_topk", 8)
+        assert np.all(np.isfinite(res[0][0]))
+        for topk in (4, 8, 16):
+            np.testing.assert_array_equal(res[topk][0], res[0][0], err_msg=f"c={c} topk={topk}")
+            np.testing.assert_array_equal(res[topk][1], res[0][1], err_msg=f"c={c} topk={topk}")
+        want = orc.search_scale(W[:40], orc.UniformGrid(c, -1, 1), 0, H=H)
+        scales_equivalent(res[0][0][:40], want, row_error_fn(W[:40], orc.UniformGrid(c, -1, 1), H),
+                          "test_full_h_search_screening_many_flat_rows", f"[{r},{n}] c={c}, 80 % zero rows")
+
+
 # ---------------------------------------------------------------------------
 # K2 factor, ordering
 # ---------------------------------------------------------------------------
