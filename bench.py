@@ -763,8 +763,15 @@ def run_ours(args):
     # one stream: an event pair then brackets exactly one operation's kernels (on overlapping streams
     # they would include each other); the factorisations are batched exactly as in the timed pass
     serial = make(1, not args.model_order)
+    fullh_uncertified = None
+    if cfg["scaling"].startswith("hessian"):
+        # the screened full-H search counts the rows whose minimum it cannot certify as global (0 expected)
+        scaling.FULLH_UNCERTIFIED = torch.zeros(1, dtype=torch.int32, device=dev)
     serial(Wd, Hd, errs_out=errs, keep_outputs=False, means=means)
     torch.cuda.synchronize()
+    if scaling.FULLH_UNCERTIFIED is not None:
+        fullh_uncertified = int(scaling.FULLH_UNCERTIFIED.item())
+        scaling.FULLH_UNCERTIFIED = None
     ops.PROFILE = {}
     serial(Wd, Hd, errs_out=errs, keep_outputs=False, means=means)
     torch.cuda.synchronize()
@@ -1020,7 +1027,7 @@ def run_ours(args):
                                  for k, v in rooflines.items()},
         "tensor_issue_note": f"3xTF32: kernels {sorted(issued3 & set(rooflines))} issue 3 TF32 MMA flop per algorithmic flop",
         "cpu_baseline": cpu_baseline, "parity": parity,
-        "layer_error_mean": layer_err, "layer_error_check": err_check,
+        "layer_error_mean": layer_err, "layer_error_check": err_check, "fullh_uncertified_rows": fullh_uncertified,
         "serial_phases_ms_per_step": {k: round(v[0], 3) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
         "xtx": {"tflops": xtx_flop / (xtx_ms * 1e-3) / 1e12 if xtx_ms else None, "ms_total": xtx_ms,
                 "note": (f"K1 X^T X over the {L} calibration matrices (S={SAMPLES}), one launch each, algorithmic 2*S*n^2 flop; "

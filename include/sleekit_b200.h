@@ -147,6 +147,13 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
                                const float* factors, int32_t G, const void* h, int32_t h_dtype,
                                void* ws, size_t ws_bytes, float* out_scale, float* out_err,
                                void* stream);
+/* The same; uncertified_rows (device int32, may be NULL) receives the number of rows for which the screened search
+ * could not show, from the ranking values of the grid points it did not evaluate exactly, that its minimum is the
+ * minimum over all G points (0 when every point is evaluated; 0 on every input tested so far). */
+int slk_scale_search_fullh_checked_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb_host,
+                                       const float* factors, int32_t G, const void* h, int32_t h_dtype,
+                                       void* ws, size_t ws_bytes, float* out_scale, float* out_err,
+                                       int32_t* uncertified_rows, void* stream);
 
 /* ---- K1: calibration statistics ---------------------------------------------
  * Sleekit.add_batch                                         statistics.py:76-87

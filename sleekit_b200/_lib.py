@@ -60,6 +60,7 @@ SIGNATURES = {
     "slk_gain_f64": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
     "slk_scale_search_fullh_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
     "slk_scale_search_fullh_f32": (_INT, [_P, _I64, _I64, _CB, _P, _I32, _P, _I32, _P, _SZ, _P, _P, _P]),
+    "slk_scale_search_fullh_checked_f32": (_INT, [_P, _I64, _I64, _CB, _P, _I32, _P, _I32, _P, _SZ, _P, _P, _P, _P]),
     "slk_hessian_accum_ws_bytes": (_SZ, [_I64, _I64]),
     "slk_hessian_accum_f32": (_INT, [_P, _I64, _I64, _I64, _P, _P, _D, _D, _P, _SZ, _P]),
     "slk_remove_input_bias_f32": (_INT, [_P, _P, _I64, _P, _P]),

@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(128) screen_select_kernel(const float* __restr
 #pragma unroll
   for (int j = 0; j < TOPK; ++j) {
     const bool keep = bg[j] >= 0 && (j == 0 || be[j] <= thr);
-    cand[(int64_t)j * r + row] = keep ? bg[j] : -1;     // sorted by screening error: the kept ones are a prefix
-    c += keep ? 1 : 0;
+    cand[(int64_t)j * r + row] = bg[j];                 // sorted by ranking value: the kept ones are a prefix, the
+    c += keep ? 1 : 0;                                  // next one is the best-ranked EXCLUDED point (fullh_certify)
   }
   count[row] = c;
 }
@@ -334,6 +334,26 @@ __global__ void __launch_bounds__(256) pairs_argmin_kernel(const float* __restri
   }
   best_err[row] = be;
   if (bg >= 0) best_f[row] = __ldg(factors + bg);
+}
+
+// Certificate of the screened search: every grid point that was NOT evaluated exactly has a ranking value >= `next`
+// (the best-ranked excluded one; the last list entry when the 16-entry list itself was full).  With a ranking error
+// of at most eps relative, such a point's exact error is >= next - eps * |next|; if that is not below the row's
+// exact minimum, the minimum over the candidates is the minimum over all G points.  Rows for which this cannot be
+// shown are counted (0 on every tested input; a caller that sees a non-zero count can rerun with "fullh_topk" 0).
+__global__ void __launch_bounds__(256) fullh_certify_kernel(const float* __restrict__ rank, const int* __restrict__ cand,
+                                                            const int* __restrict__ offsets, int64_t r, int G, int topk_max,
+                                                            float eps, const float* __restrict__ best_err,
+                                                            int* __restrict__ uncertified) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= r) return;
+  const int kept = offsets[row + 1] - offsets[row];
+  if (kept == 0 || kept >= G) return;                    // nothing finite to choose from / everything evaluated
+  const int slot = kept < topk_max ? kept : topk_max - 1;
+  const int gp = cand[(int64_t)slot * r + row];
+  if (gp < 0) return;                                    // fewer finite ranking values than list entries: all evaluated
+  const float next = rank[(int64_t)gp * r + row];
+  if (__fsub_rn(next, __fmul_rn(eps, fabsf(next))) < best_err[row]) atomicAdd(uncertified, 1);
 }
 
 // first minimum in grid order over the evaluated candidates (strict '<'; equal errors: the lower grid index)
@@ -435,6 +455,7 @@ static FullhWs fullh_layout(void* ws, int64_t r, int64_t n, int G, int h_dtype) 
 struct FullhCtx {
   const float* w; int64_t r, n; DevGrid<float> g; const float* factors; int G; const void* h; int h_dtype;
   bool tc; cudaStream_t st; FullhWs L;
+  int* uncertified;          // optional device counter of rows without a certificate (fullh_certify_kernel)
 };
 
 static inline int resid_blocks(int64_t pairs) {    // one CTA per (grid point, row) pair, grid-stride beyond 64 per SM
@@ -512,6 +533,11 @@ static int fullh_eval_pairs(const FullhCtx& c, int topk) {
   pairs_argmin_kernel<<<(int)ceil_div(c.r, 256), 256, 0, c.st>>>((const float*)L.errs, L.pair_g, L.offsets, c.r, c.factors,
                                                                  L.best_err, L.best_f);
   SLK_LAUNCH_CHECK();
+  if (c.uncertified) {
+    fullh_certify_kernel<<<(int)ceil_div(c.r, 256), 256, 0, c.st>>>(L.errs_all, L.cand, L.offsets, c.r, c.G, FULLH_TOPK_MAX,
+                                                                    0.015625f, L.best_err, c.uncertified);
+    SLK_LAUNCH_CHECK();
+  }
   return SLK_OK;
 }
 
@@ -537,6 +563,10 @@ static int fullh_eval_slots(const FullhCtx& c, int topk) {
     if (rc) return rc;
     cand_argmin_kernel<<<(int)ceil_div(c.r, 256), 256, 0, c.st>>>((const float*)L.errs, cs, c.r, sc, c.factors, L.best_err,
                                                                   L.best_f, L.best_g);
+    SLK_LAUNCH_CHECK();
+  }
+  if (c.uncertified) {                                   // no certificate on this path: -1 = not checked
+    fill_int_kernel<<<1, 256, 0, c.st>>>(c.uncertified, -1, 1);
     SLK_LAUNCH_CHECK();
   }
   return SLK_OK;
@@ -662,6 +692,13 @@ size_t slk_scale_search_fullh_ws_bytes(int64_t r, int64_t n, int32_t G, int32_t 
 int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb, const float* factors,
                                int32_t G, const void* h, int32_t h_dtype, void* ws, size_t ws_bytes,
                                float* out_scale, float* out_err, void* stream) {
+  return slk_scale_search_fullh_checked_f32(w, r, n, cb, factors, G, h, h_dtype, ws, ws_bytes, out_scale, out_err, nullptr,
+                                            stream);
+}
+
+int slk_scale_search_fullh_checked_f32(const float* w, int64_t r, int64_t n, const slk_codebook* cb, const float* factors,
+                                       int32_t G, const void* h, int32_t h_dtype, void* ws, size_t ws_bytes,
+                                       float* out_scale, float* out_err, int32_t* uncertified_rows, void* stream) {
   int rc = check_codebook(cb);
   if (rc) return rc;
   SLK_REQUIRE(w && factors && h && out_scale && r >= 1 && n >= 1 && G >= 1, "bad arguments");
@@ -671,6 +708,8 @@ int slk_scale_search_fullh_f32(const float* w, int64_t r, int64_t n, const slk_c
   SLK_REQUIRE(ws && ws_bytes >= c.L.bytes, "workspace too small");
   c.w = w; c.r = r; c.n = n; c.g = make_grid<float>(cb); c.factors = factors; c.G = G; c.h = h; c.h_dtype = h_dtype;
   c.st = (cudaStream_t)stream;
+  c.uncertified = uncertified_rows;
+  if (uncertified_rows) SLK_CUDA(cudaMemsetAsync(uncertified_rows, 0, sizeof(int32_t), c.st));
   // tensor-core path (fp32 H): residuals are written with their TF32 parts, H is split once
   c.tc = c.L.rhi != nullptr && n >= 32 && tc_gemm_usable(c.L.resid, n, h, n);
   if (c.tc) {

@@ -261,7 +261,10 @@ def scale_search(w, cb, factors, hdiag=None, want_err=False, want_init=False):
 
 
 @_timed("scale_search_fullh")
-def scale_search_fullh(w, cb, factors, h, want_err=False):
+def scale_search_fullh(w, cb, factors, h, want_err=False, want_check=False):
+    """compute_min_mse_scaling with a 2-D H (scaling.py:98-134): (scales, errors or None[, uncertified]).
+    want_check: also an int32 [1] tensor = rows whose minimum the screened search could not certify as the
+    minimum over all grid points (slk_scale_search_fullh_checked_f32; 0 expected, -1 = path without a check)."""
     cb = device_codebook(cb)
     _chk(w, torch.float32)
     _chk(factors, torch.float32)
@@ -274,6 +277,11 @@ def scale_search_fullh(w, cb, factors, h, want_err=False):
     ws = _ws(nbytes, w.device)
     out = torch.empty(r, dtype=torch.float32, device=w.device)
     err = torch.empty(r, dtype=torch.float32, device=w.device) if want_err else None
+    if want_check:
+        bad = torch.zeros(1, dtype=torch.int32, device=w.device)
+        _call("slk_scale_search_fullh_checked_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(h), h_dtype,
+              _ptr(ws), nbytes, _ptr(out), _ptr(err), _ptr(bad), _stream())
+        return out, err, bad
     _call("slk_scale_search_fullh_f32", _ptr(w), r, n, cb.ref, _ptr(factors), factors.numel(), _ptr(h), h_dtype,
               _ptr(ws), nbytes, _ptr(out), _ptr(err), _stream())
     return out, err

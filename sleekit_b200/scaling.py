@@ -142,11 +142,18 @@ def _factors(min_factor, max_factor, grid_size, dev):
     return t
 
 
+FULLH_UNCERTIFIED = None   # optional int32 CUDA tensor [1]: the full-H searches add the rows they could not certify
+
+
 def search_scale_device(Wd, codebook, Hd=None, min_factor=0.05, max_factor=1.0, grid_size=100):
     """compute_min_mse_scaling for a device [r, n] fp32 matrix, axis 0."""
     f = _factors(min_factor, max_factor, grid_size, Wd.device)
     if Hd is None or Hd.ndim == 1:
         return ops.scale_search(Wd, codebook, f, Hd)[0]
+    if FULLH_UNCERTIFIED is not None:
+        sc, _, bad = ops.scale_search_fullh(Wd, codebook, f, Hd, want_check=True)
+        FULLH_UNCERTIFIED.add_(bad.clamp_min(0))
+        return sc
     return ops.scale_search_fullh(Wd, codebook, f, Hd)[0]
 
 

@@ -307,6 +307,9 @@ def test_full_h_search_screening_is_exact(slk, r, n, c, samples):
         ops.set_option("fullh_bf16", 1)
         ops.set_option("fullh_ctas", 2)
         ops.set_option("fullh_compact", 1)
+    sc_c, err_c, bad = ops.scale_search_fullh(Wd, cb, f, Hd, want_err=True, want_check=True)
+    assert int(bad.item()) == 0, "rows without a certificate"          # and the certificate itself (fullh_certify_kernel)
+    res[("default", "checked")] = (sc_c.cpu().numpy(), err_c.cpu().numpy())
     base = res[(0, 256, 1, 1)]
     for key, (sc, err) in res.items():
         same = float((sc == base[0]).mean())
@@ -344,6 +347,7 @@ def test_full_h_search_screening_many_flat_rows(slk):
         finally:
             ops.set_option("fullh_topk", 8)
         assert np.all(np.isfinite(res[0][0]))
+        assert int(ops.scale_search_fullh(Wd, cb, f, Hd, want_check=True)[2].item()) == 0
         for topk in (4, 8, 16):
             np.testing.assert_array_equal(res[topk][0], res[0][0], err_msg=f"c={c} topk={topk}")
             np.testing.assert_array_equal(res[topk][1], res[0][1], err_msg=f"c={c} topk={topk}")
