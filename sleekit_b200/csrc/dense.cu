@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) screen_topk_kernel(const float* __restric
 
 // Compacted candidates: a row keeps the (at most TOPK) best-ranked grid points whose screening error lies within
 // `tau` of its best one -- with a ranking error eps, the true minimum is within (1 + eps) / (1 - eps) of the best
-// screening value, so tau = 2^-5 against eps <= 5e-3 (bf16) cuts nothing that could win; typically 2-3 points
+// screening value, so tau = 2^-5 against eps <= 1e-2 (bf16; tests/test_fullh_rank_model.py) cuts nothing that could win; typically 2-3 points
 // remain of 8.  count[row] = kept candidates (>= 1 when the row has a finite error at all).
 template <int TOPK>
 __global__ void __launch_bounds__(128) screen_select_kernel(const float* __restrict__ err, int64_t r, int G, float tau,
